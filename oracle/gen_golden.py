@@ -1,0 +1,204 @@
+"""gen_golden.py -- generates tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE.
+
+Run in the authoring container only (needs /root/reference):
+    python oracle/gen_golden.py [--only syn1|syn4|rand|graph]
+
+What is pinned (the reference has no tests of its own, so the
+only possible pin is the reference's own output under a fixed seed):
+  * graph + trained model weights + cg 'pred' (gengraph.gen_syn1/gen_syn4 with
+    np.random.seed(0); train.train_node_classifier, reference defaults)
+  * per explained node: neighbors / node_idx_new from Explainer.extract_neighborhood
+    (explain.py:492-501), the mask initialisation M0 drawn exactly as
+    ExplainModule.construct_edge_mask does (explain.py:645-652) under
+    torch.manual_seed(seed), and the mask returned by Explainer.explain
+    (explain.py:74-221), both stored at the directed-edge entries of the
+    sub-adjacency in row-major (canonical CSR) order.  Off-edge entries of the
+    returned mask are asserted to be exactly 0 here.
+"""
+import argparse
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def state_to_np(model):
+    sd = model.state_dict()
+    return {
+        "W1": sd["conv_first.weight"].numpy().astype(np.float32),
+        "b1": sd["conv_first.bias"].numpy().astype(np.float32),
+        "W2": sd["conv_block.0.weight"].numpy().astype(np.float32),
+        "b2": sd["conv_block.0.bias"].numpy().astype(np.float32),
+        "W3": sd["conv_last.weight"].numpy().astype(np.float32),
+        "b3": sd["conv_last.bias"].numpy().astype(np.float32),
+        "Wp": sd["pred_model.weight"].numpy().astype(np.float32),
+        "bp": sd["pred_model.bias"].numpy().astype(np.float32),
+    }
+
+
+def edges_of(adj):
+    iu, ju = np.nonzero(np.triu(adj, 1))
+    return np.stack([iu, ju], 1).astype(np.int32)
+
+
+def explain_nodes_ref(R, model, cg, args, nodes, seed_base):
+    """Run the reference explainer; return dict of per-node golden arrays."""
+    with ref_harness.quiet():
+        ex = R.explain.Explainer(model=model, adj=cg["adj"], feat=cg["feat"], label=cg["label"],
+                                 pred=cg["pred"], train_idx=cg["train_idx"], args=args,
+                                 writer=None, print_training=False, graph_idx=-1)
+    out = {}
+    t0 = time.time()
+    for node in nodes:
+        seed = seed_base + int(node)
+        with ref_harness.quiet():
+            node_idx_new, sub_adj, sub_feat, sub_label, nbrs = ex.extract_neighborhood(node, 0)
+        n = len(nbrs)
+        # M0 exactly as construct_edge_mask draws it (explain.py:645-652)
+        torch.manual_seed(seed)
+        std = torch.nn.init.calculate_gain("relu") * math.sqrt(2.0 / (n + n))
+        M0 = torch.FloatTensor(n, n).normal_(1.0, std).numpy()
+        torch.manual_seed(seed)
+        with ref_harness.quiet():
+            masked = ex.explain(node, graph_idx=0)
+        masked = np.asarray(masked)
+        ei, ej = np.nonzero(sub_adj)          # row-major == canonical CSR order
+        off = masked.copy()
+        off[ei, ej] = 0
+        assert np.all(off == 0), "reference mask non-zero off the edges"
+        out["n%d_nbrs" % node] = nbrs.astype(np.int32)
+        out["n%d_idx_new" % node] = np.int64(node_idx_new)
+        out["n%d_seed" % node] = np.int64(seed)
+        out["n%d_m0" % node] = M0[ei, ej].astype(np.float32)
+        out["n%d_mask" % node] = masked[ei, ej].astype(np.float32)
+    print("  explained %d nodes in %.1fs" % (len(nodes), time.time() - t0))
+    # sanity of the M0 capture: a 1-epoch run returns A * sym(sigmoid(M0)) (SURVEY 'north_star' table)
+    node = int(nodes[0])
+    args1 = ref_harness.explainer_args(**{**vars(args), "num_epochs": 1})
+    with ref_harness.quiet():
+        ex1 = R.explain.Explainer(model=model, adj=cg["adj"], feat=cg["feat"], label=cg["label"],
+                                  pred=cg["pred"], train_idx=cg["train_idx"], args=args1,
+                                  writer=None, print_training=False, graph_idx=-1)
+        torch.manual_seed(seed_base + node)
+        m1 = np.asarray(ex1.explain(node, graph_idx=0))
+        _, sub_adj, _, _, nbrs = ex1.extract_neighborhood(node, 0)
+    n = len(nbrs)
+    torch.manual_seed(seed_base + node)
+    std = torch.nn.init.calculate_gain("relu") * math.sqrt(2.0 / (n + n))
+    M0 = torch.FloatTensor(n, n).normal_(1.0, std)
+    S = torch.sigmoid(M0)
+    exp1 = ((S + S.t()) / 2).numpy() * sub_adj
+    assert np.abs(exp1 - m1).max() < 1e-7, "M0 capture does not reproduce the reference's draw"
+    return out
+
+
+def train_args(**over):
+    import types
+    d = dict(datadir="data", logdir="/tmp/gnnx_ref_log", ckptdir="/tmp/gnnx_ref_ckpt", dataset="syn1",
+             bmname=None, opt="adam", opt_scheduler="none", max_nodes=100, cuda="1",
+             feature_type="default", lr=0.001, clip=2.0, batch_size=20, num_epochs=1000,
+             train_ratio=0.8, test_ratio=0.1, num_workers=1, input_dim=10, hidden_dim=20,
+             output_dim=20, num_classes=2, num_gc_layers=3, dropout=0.0, weight_decay=0.005,
+             method="base", name_suffix="", assign_ratio=0.1, gpu=False, bias=True, bn=False)
+    d.update(over)
+    os.makedirs(d["ckptdir"], exist_ok=True)
+    os.makedirs(d["logdir"], exist_ok=True)
+    return types.SimpleNamespace(**d)
+
+
+def gen_syn(R, which, nodes, train_epochs):
+    np.random.seed(0)
+    torch.manual_seed(0)
+    fg = R.featgen.ConstFeatureGen(np.ones(10, dtype=float))
+    with ref_harness.quiet():
+        if which == "syn1":
+            G, labels, _ = R.gengraph.gen_syn1(feature_generator=fg)
+        else:
+            G, labels, _ = R.gengraph.gen_syn4(feature_generator=fg)
+    C = max(labels) + 1
+    targs = train_args(dataset=which, num_epochs=train_epochs)
+    model = R.models.GcnEncoderNode(10, 20, 20, C, 3, bn=False, args=targs)
+    t0 = time.time()
+    with ref_harness.quiet():
+        R.train.train_node_classifier(G, labels, model, targs, writer=None)
+    print("  trained %s (%d nodes) in %.1fs" % (which, G.number_of_nodes(), time.time() - t0))
+    ck = torch.load(
+        R.io_utils.create_filename(targs.ckptdir, targs), weights_only=False)
+    cg = ck["cg"]
+    model.eval()
+    acc = (np.argmax(cg["pred"][0], 1) == cg["label"][0]).mean()
+    print("  %s: N=%d edges=%d C=%d acc=%.3f" % (which, cg["adj"].shape[1], int(cg["adj"].sum() / 2), C, acc))
+    eargs = ref_harness.explainer_args(dataset=which)
+    gold = explain_nodes_ref(R, model, cg, eargs, nodes, seed_base=1000)
+    graph = dict(N=np.int64(cg["adj"].shape[1]), edges=edges_of(cg["adj"][0]),
+                 feat=cg["feat"][0].astype(np.float32), label=cg["label"][0].astype(np.int64),
+                 pred=cg["pred"][0].astype(np.float32), **state_to_np(model))
+    np.savez_compressed(os.path.join(OUT, which + "_graph.npz"), **graph)
+    np.savez_compressed(os.path.join(OUT, which + "_golden.npz"), nodes=np.asarray(nodes, np.int64), **gold)
+    # the dense hop matrix rows for a few nodes pin graph_utils.neighborhoods itself
+    with ref_harness.quiet():
+        hop = R.graph_utils.neighborhoods(cg["adj"], 3, False)
+    np.savez_compressed(os.path.join(OUT, which + "_hops.npz"),
+                        hop_rowsum=hop[0].sum(1).astype(np.int32),
+                        hop_bits=np.packbits(hop[0].astype(np.uint8), axis=1))
+
+
+def gen_rand(R):
+    """BA graph, Gaussian features, random (untrained) weights AND non-zero biases: exercises
+    feature masking and the bias/normalise path harder than the all-ones syn features."""
+    import networkx as nx
+    rng = np.random.default_rng(7)
+    G = nx.barabasi_albert_graph(150, 2, seed=3)
+    N, d, C = G.number_of_nodes(), 16, 3
+    adj = nx.to_numpy_array(G)[None]
+    feat = rng.normal(size=(1, N, d))
+    label = rng.integers(0, C, size=(1, N))
+    torch.manual_seed(11)
+    targs = train_args(input_dim=d)
+    model = R.models.GcnEncoderNode(d, 20, 20, C, 3, bn=False, args=targs)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("bias"):
+                p.normal_(0.0, 0.3)
+    model.eval()
+    with torch.no_grad():
+        pred, _ = model(torch.tensor(feat, dtype=torch.float), torch.tensor(adj, dtype=torch.float))
+    cg = dict(adj=adj, feat=feat, label=label, pred=pred.numpy(), train_idx=list(range(N)))
+    eargs = ref_harness.explainer_args(dataset="rand")
+    nodes = [0, 1, 7, 33, 77, 100, 149]
+    gold = explain_nodes_ref(R, model, cg, eargs, nodes, seed_base=5000)
+    graph = dict(N=np.int64(N), edges=edges_of(adj[0]), feat=feat[0].astype(np.float32),
+                 label=label[0].astype(np.int64), pred=cg["pred"][0].astype(np.float32),
+                 **state_to_np(model))
+    np.savez_compressed(os.path.join(OUT, "rand_graph.npz"), **graph)
+    np.savez_compressed(os.path.join(OUT, "rand_golden.npz"), nodes=np.asarray(nodes, np.int64), **gold)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    R = ref_harness.load()
+    if a.only in (None, "syn1"):
+        nodes = sorted(set([300, 301, 400, 550, 699, 10, 0, 5, 350, 450, 620, 683] + list(range(3, 700, 10))))
+        gen_syn(R, "syn1", nodes, 1000)
+    if a.only in (None, "syn4"):
+        nodes = sorted(set([512, 0, 1, 8, 100, 511, 870] + list(range(4, 871, 20))))
+        gen_syn(R, "syn4", nodes, 1000)
+    if a.only in (None, "rand"):
+        gen_rand(R)
+
+
+if __name__ == "__main__":
+    main()
