@@ -1,0 +1,584 @@
+// api.cu -- C-ABI host side of libgnnx.so (see include/gnnx.h for the contract and the reference
+// call sites each entry point replaces).  Owns the handle: device copies of graph/model, the
+// extraction plan, launch classes and workspaces.  No CPU compute path exists here: every
+// algorithmic step is a kernel in khop.cu / explain_node.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "gnnx_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LaunchClass {
+  int cap_bytes;  // dynamic shared memory per CTA (0: global-memory slab variant)
+  int threads;
+  int ctas_per_sm;
+};
+// k CTAs per SM share 227 KB (1 KB per CTA is reserved by the system)
+static const LaunchClass kClasses[] = {
+    {13 * 1024, 128, 16}, {27 * 1024, 256, 8}, {55 * 1024, 256, 4},
+    {112 * 1024, 512, 2}, {226 * 1024, 512, 1}, {0, 512, 1}};
+constexpr int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
+constexpr int kNumStreams = kNumClasses;
+
+}  // namespace
+
+struct gx_handle {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t side[kNumStreams] = {};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[kNumStreams] = {};
+  int64_t launches = 0;
+
+  // graph
+  bool has_graph = false;
+  GxGraphDev g{};
+  DevBuf g_rowptr, g_col, g_feat, g_label, g_pred;
+  // model
+  bool has_model = false;
+  GxModelDev m{};
+  DevBuf m_buf;
+  // plan
+  bool has_plan = false;
+  int count = 0, n_hops = 0;
+  int64_t total_n = 0, total_e = 0;
+  std::vector<GxTask> tasks;
+  std::vector<int32_t> class_order[kNumClasses];
+  std::vector<int> class_idx16;
+  int64_t gws_stride_words = 0;
+  DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
+  DevBuf d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
+  GxPlanArrays plan{};
+  // slot workspace
+  DevBuf ws_buf;
+  GxSlotWs ws{};
+};
+
+namespace {
+
+int ensure_slot_ws(gx_handle* h) {
+  const int64_t N = h->g.N;
+  const int W = (int)((N + 31) / 32);
+  int slots = h->num_sms * 4;
+  const size_t per_slot = (size_t)W * 4 + (size_t)(W + 1) * 4 + (size_t)N + (size_t)(N + 1) * 4 * 2 + (size_t)N * 4 * 2 + 64;
+  const size_t budget = (size_t)4 << 30;
+  while (slots > 1 && per_slot * slots > budget) slots /= 2;
+  if (h->ws.slots == slots && h->ws.W == W && h->ws_buf.p) return GX_OK;
+  // carve (each array 16B aligned)
+  auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+  size_t o = 0;
+  const size_t o_bm = o; o += al((size_t)slots * W * 4);
+  const size_t o_wp = o; o += al((size_t)slots * (W + 1) * 4);
+  const size_t o_q = o; o += al((size_t)slots * (N + 1) * 4);
+  const size_t o_loc = o; o += al((size_t)slots * N * 4);
+  const size_t o_cof = o; o += al((size_t)slots * N * 4);
+  const size_t o_pb = o; o += al((size_t)slots * (N + 1) * 4);
+  const size_t o_dist = o; o += al((size_t)slots * N);
+  GX_CUDA_CHECK(h->ws_buf.reserve(o));
+  char* b = h->ws_buf.as<char>();
+  h->ws.bm = (uint32_t*)(b + o_bm);
+  h->ws.wpref = (int32_t*)(b + o_wp);
+  h->ws.q = (int32_t*)(b + o_q);
+  h->ws.loc = (int32_t*)(b + o_loc);
+  h->ws.cof = (int32_t*)(b + o_cof);
+  h->ws.pbase = (int32_t*)(b + o_pb);
+  h->ws.dist = (uint8_t*)(b + o_dist);
+  h->ws.W = W;
+  h->ws.slots = slots;
+  GX_CUDA_CHECK(cudaMemsetAsync(h->ws.bm, 0, (size_t)slots * W * 4, h->stream));
+  return GX_OK;
+}
+
+int task_smem_class(const GxTask& T, const GxModelDev& m, int* bytes_out, int* idx16_out) {
+  // shared-memory classes always use 16-bit indices: a task with n or e1 >= 65535 cannot fit 227 KB anyway
+  const bool small_idx = T.n < 65535 && T.e1 < 65535;
+  for (int c = 0; small_idx && c < kNumClasses - 1; ++c) {
+    const int nwarps = kClasses[c].threads / 32;
+    const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs, m.d, m.hid, m.emb, m.C, nwarps, 2);
+    const int64_t bytes = (int64_t)L.total_words * 4;
+    if (bytes <= kClasses[c].cap_bytes) {
+      *bytes_out = (int)bytes;
+      *idx16_out = 1;
+      return c;
+    }
+  }
+  const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs, m.d, m.hid, m.emb, m.C,
+                                    kClasses[kNumClasses - 1].threads / 32, 4);
+  *bytes_out = L.total_words;  // words (may exceed int bytes range for huge tasks)
+  *idx16_out = 0;
+  return kNumClasses - 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gx_last_error(void) { return g_err; }
+int gx_version(void) { return GX_VERSION; }
+
+void gx_default_hparams(gx_hparams* hp) {
+  if (!hp) return;
+  hp->num_epochs = 100;
+  hp->lr = 0.1f;
+  hp->beta1 = 0.9f;
+  hp->beta2 = 0.999f;
+  hp->eps = 1e-8f;
+  hp->coef_size = 0.005f;
+  hp->coef_feat_size = 1.0f;
+  hp->coef_ent = 1.0f;
+  hp->coef_lap = 1.0f;
+  hp->mask_act = 0;
+  hp->mask_bias = 0;
+  hp->init = GX_INIT_M0;
+  hp->seed = 0;
+}
+
+int gx_create(int device, gx_handle** out) {
+  if (!out) { gx_set_error("gx_create: out is NULL"); return GX_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    gx_set_error("gx_create: no CUDA device (%s); libgnnx has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return GX_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { gx_set_error("gx_create: device %d out of range [0,%d)", device, ndev); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    gx_set_error("gx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return GX_ERR_CUDA;
+  }
+  gx_handle* h = new gx_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  for (int i = 0; i < kNumStreams; ++i) {
+    GX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+    GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+  }
+  GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  *out = h;
+  return GX_OK;
+}
+
+int gx_destroy(gx_handle* h) {
+  if (!h) return GX_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&h->g_rowptr, &h->g_col, &h->g_feat, &h->g_label, &h->g_pred, &h->m_buf, &h->d_nodes,
+                    &h->d_tasks, &h->d_nbrs, &h->d_lo2gid, &h->d_srp, &h->d_scol, &h->d_irp, &h->d_icol,
+                    &h->d_pairs, &h->d_order, &h->d_counters, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
+                    &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < kNumStreams; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  delete h;
+  return GX_OK;
+}
+
+int gx_set_stream(gx_handle* h, void* cuda_stream) {
+  if (!h) { gx_set_error("gx_set_stream: NULL handle"); return GX_ERR_INVALID; }
+  h->stream = (cudaStream_t)cuda_stream;
+  return GX_OK;
+}
+
+int gx_sync(gx_handle* h) {
+  if (!h) { gx_set_error("gx_sync: NULL handle"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return GX_OK;
+}
+
+int64_t gx_launch_count(gx_handle* h) { return h ? h->launches : 0; }
+
+int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* conv_w,
+                 const float* const* conv_b, const float* pred_w, const float* pred_b) {
+  if (!h || !dims || !conv_w || !pred_w || !pred_b) { gx_set_error("gx_set_model: NULL argument"); return GX_ERR_INVALID; }
+  if (dims->num_layers != 3) {
+    gx_set_error("gx_set_model: num_layers=%d; this build implements the reference default num_gc_layers=3", dims->num_layers);
+    return GX_ERR_UNSUPPORTED;
+  }
+  if (dims->flags & GX_MODEL_BN) { gx_set_error("gx_set_model: --bn (models.py:222-228) is not built"); return GX_ERR_UNSUPPORTED; }
+  if (dims->hidden_dim != 20 || dims->embed_dim != 20) {
+    gx_set_error("gx_set_model: hidden_dim=%d output_dim=%d; this build instantiates the reference default 20/20",
+                 dims->hidden_dim, dims->embed_dim);
+    return GX_ERR_UNSUPPORTED;
+  }
+  if (dims->input_dim < 1 || dims->input_dim > 128) {
+    gx_set_error("gx_set_model: input_dim=%d outside [1,128] supported by the shared-memory kernel", dims->input_dim);
+    return GX_ERR_UNSUPPORTED;
+  }
+  if (dims->num_classes < 1) { gx_set_error("gx_set_model: num_classes < 1"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int d = dims->input_dim, hid = dims->hidden_dim, emb = dims->embed_dim, C = dims->num_classes;
+  const int in_dim[3] = {d, hid, hid}, out_dim[3] = {hid, hid, emb};
+  const int PD = 2 * hid + emb;
+  std::vector<float> host;
+  size_t offW[3], offWt[3], offb[3], offWp, offbp;
+  auto al4 = [&]() { while (host.size() % 4) host.push_back(0.f); };
+  for (int l = 0; l < 3; ++l) {
+    if (!conv_w[l]) { gx_set_error("gx_set_model: conv_w[%d] is NULL", l); return GX_ERR_INVALID; }
+    al4(); offW[l] = host.size();
+    host.insert(host.end(), conv_w[l], conv_w[l] + (size_t)in_dim[l] * out_dim[l]);
+    al4(); offWt[l] = host.size();
+    for (int c = 0; c < out_dim[l]; ++c)
+      for (int f = 0; f < in_dim[l]; ++f) host.push_back(conv_w[l][(size_t)f * out_dim[l] + c]);
+    al4(); offb[l] = host.size();
+    for (int c = 0; c < out_dim[l]; ++c) host.push_back((conv_b && conv_b[l]) ? conv_b[l][c] : 0.f);
+  }
+  al4(); offWp = host.size();
+  host.insert(host.end(), pred_w, pred_w + (size_t)C * PD);
+  al4(); offbp = host.size();
+  host.insert(host.end(), pred_b, pred_b + C);
+  GX_CUDA_CHECK(h->m_buf.reserve(host.size() * 4));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->m_buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  float* b = h->m_buf.as<float>();
+  h->m.d = d; h->m.hid = hid; h->m.emb = emb; h->m.C = C; h->m.L = 3;
+  for (int l = 0; l < 3; ++l) { h->m.W[l] = b + offW[l]; h->m.Wt[l] = b + offWt[l]; h->m.b[l] = b + offb[l]; }
+  h->m.Wp = b + offWp;
+  h->m.bp = b + offbp;
+  h->has_model = true;
+  h->has_plan = false;
+  return GX_OK;
+}
+
+int gx_set_graph_csr(gx_handle* h, int64_t N, const int32_t* rowptr, const int32_t* col,
+                     const float* feat, int32_t d, const int32_t* label, const int32_t* pred_label) {
+  if (!h || !rowptr || !col || !feat || !pred_label) { gx_set_error("gx_set_graph_csr: NULL argument"); return GX_ERR_INVALID; }
+  if (N < 1 || N > 0x7fffffff - 64) { gx_set_error("gx_set_graph_csr: num_nodes out of range"); return GX_ERR_INVALID; }
+  if (rowptr[0] != 0) { gx_set_error("gx_set_graph_csr: rowptr[0] != 0"); return GX_ERR_INVALID; }
+  const int64_t nnz = rowptr[N];
+  for (int64_t i = 0; i < N; ++i) {
+    if (rowptr[i + 1] < rowptr[i]) { gx_set_error("gx_set_graph_csr: rowptr not monotone at %lld", (long long)i); return GX_ERR_INVALID; }
+    for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+      if (col[e] < 0 || col[e] >= N) { gx_set_error("gx_set_graph_csr: col out of range in row %lld", (long long)i); return GX_ERR_INVALID; }
+      if (e > rowptr[i] && col[e] <= col[e - 1]) { gx_set_error("gx_set_graph_csr: row %lld columns not strictly ascending", (long long)i); return GX_ERR_INVALID; }
+    }
+  }
+  // symmetric pattern (the reference's datasets are undirected 0/1 adjacency)
+  for (int64_t i = 0; i < N; ++i)
+    for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+      const int32_t j = col[e];
+      if (!std::binary_search(col + rowptr[j], col + rowptr[j + 1], (int32_t)i)) {
+        gx_set_error("gx_set_graph_csr: adjacency not symmetric: (%lld,%d) present, (%d,%lld) absent", (long long)i, j, j, (long long)i);
+        return GX_ERR_UNSUPPORTED;
+      }
+    }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  GX_CUDA_CHECK(h->g_rowptr.reserve((size_t)(N + 1) * 4));
+  GX_CUDA_CHECK(h->g_col.reserve((size_t)std::max<int64_t>(nnz, 1) * 4));
+  GX_CUDA_CHECK(h->g_feat.reserve((size_t)N * d * 4));
+  GX_CUDA_CHECK(h->g_label.reserve((size_t)N * 4));
+  GX_CUDA_CHECK(h->g_pred.reserve((size_t)N * 4));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->g_rowptr.p, rowptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->g_col.p, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->g_feat.p, feat, (size_t)N * d * 4, cudaMemcpyHostToDevice, h->stream));
+  if (label) GX_CUDA_CHECK(cudaMemcpyAsync(h->g_label.p, label, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
+  else GX_CUDA_CHECK(cudaMemsetAsync(h->g_label.p, 0, (size_t)N * 4, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->g_pred.p, pred_label, (size_t)N * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->g.N = N; h->g.nnz = (int32_t)nnz;
+  h->g.rowptr = h->g_rowptr.as<int32_t>(); h->g.col = h->g_col.as<int32_t>();
+  h->g.feat = h->g_feat.as<float>(); h->g.d = d;
+  h->g.label = h->g_label.as<int32_t>(); h->g.pred_label = h->g_pred.as<int32_t>();
+  h->has_graph = true;
+  h->has_plan = false;
+  h->ws.slots = 0;
+  return GX_OK;
+}
+
+int gx_neighborhood_rows(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_hops, uint8_t* out_rows) {
+  if (!h || !nodes || !out_rows) { gx_set_error("gx_neighborhood_rows: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_graph) { gx_set_error("gx_neighborhood_rows: call gx_set_graph_csr first"); return GX_ERR_INVALID; }
+  if (n_hops < 1 || n_hops >= GX_MAX_LEVELS) { gx_set_error("gx_neighborhood_rows: n_hops=%d outside [1,%d]", n_hops, GX_MAX_LEVELS - 1); return GX_ERR_INVALID; }
+  if (count <= 0) return GX_OK;
+  for (int t = 0; t < count; ++t)
+    if (nodes[t] < 0 || nodes[t] >= h->g.N) { gx_set_error("gx_neighborhood_rows: node %d out of range", nodes[t]); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = ensure_slot_ws(h);
+  if (rc != GX_OK) return rc;
+  const size_t bytes = (size_t)count * h->g.N;
+  GX_CUDA_CHECK(h->d_nodes.reserve((size_t)count * 4));
+  GX_CUDA_CHECK(h->d_rows.reserve(bytes));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_nodes.p, nodes, (size_t)count * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemsetAsync(h->d_rows.p, 0, bytes, h->stream));
+  GX_CUDA_CHECK(gx_launch_hop_rows(h->g, h->d_nodes.as<int32_t>(), count, n_hops, h->ws, h->d_rows.as<uint8_t>(), h->stream));
+  h->launches += 1;
+  GX_CUDA_CHECK(cudaMemcpyAsync(out_rows, h->d_rows.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return GX_OK;
+}
+
+int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_hops,
+                  int64_t* total_nodes, int64_t* total_edges) {
+  if (!h || !nodes) { gx_set_error("gx_plan_nodes: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_graph || !h->has_model) { gx_set_error("gx_plan_nodes: call gx_set_model and gx_set_graph_csr first"); return GX_ERR_INVALID; }
+  if (h->g.d != h->m.d) { gx_set_error("gx_plan_nodes: graph feat_dim %d != model input_dim %d", h->g.d, h->m.d); return GX_ERR_INVALID; }
+  if (n_hops < 1 || n_hops >= GX_MAX_LEVELS) { gx_set_error("gx_plan_nodes: n_hops=%d outside [1,%d]", n_hops, GX_MAX_LEVELS - 1); return GX_ERR_INVALID; }
+  if (n_hops < 2) { gx_set_error("gx_plan_nodes: n_hops=1 never contains the node itself without a self loop"); return GX_ERR_UNSUPPORTED; }
+  if (count <= 0) { gx_set_error("gx_plan_nodes: count <= 0"); return GX_ERR_INVALID; }
+  for (int t = 0; t < count; ++t)
+    if (nodes[t] < 0 || nodes[t] >= h->g.N) { gx_set_error("gx_plan_nodes: node %d out of range [0,%lld)", nodes[t], (long long)h->g.N); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  h->has_plan = false;
+  int rc = ensure_slot_ws(h);
+  if (rc != GX_OK) return rc;
+  GX_CUDA_CHECK(h->d_nodes.reserve((size_t)count * 4));
+  GX_CUDA_CHECK(h->d_tasks.reserve((size_t)count * sizeof(GxTask)));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_nodes.p, nodes, (size_t)count * 4, cudaMemcpyHostToDevice, h->stream));
+  const int row_lvl = h->m.L - 1;
+  GX_CUDA_CHECK(gx_launch_khop_count(h->g, h->d_nodes.as<int32_t>(), count, n_hops, row_lvl, h->ws, h->d_tasks.as<GxTask>(), h->stream));
+  h->launches += 1;
+  h->tasks.resize(count);
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  // host: offsets, launch classes, work order
+  int64_t tn = 0, te = 0, tp = 0;
+  for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
+  h->class_idx16.assign(kNumClasses, 1);
+  h->class_idx16[kNumClasses - 1] = 0;
+  int64_t gws_words = 0;
+  for (int t = 0; t < count; ++t) {
+    GxTask& T = h->tasks[t];
+    if (T.status != 0) {
+      gx_set_error("gx_plan_nodes: node %d is not inside its own %d-hop neighbourhood (isolated node?)", T.node, n_hops);
+      return GX_ERR_NODE;
+    }
+    if (T.e_d % 2 != 0) { gx_set_error("gx_plan_nodes: induced sub-adjacency of node %d is not symmetric", T.node); return GX_ERR_INVALID; }
+    T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
+    tn += T.n; te += T.e_d; tp += T.npairs;
+    int bytes = 0, idx16 = 0;
+    const int cls = task_smem_class(T, h->m, &bytes, &idx16);
+    T.smem_bytes = bytes;
+    if (cls == kNumClasses - 1) gws_words = std::max<int64_t>(gws_words, bytes);
+    h->class_order[cls].push_back(t);
+  }
+  h->gws_stride_words = (gws_words + 3) / 4 * 4;
+  auto cost = [&](int32_t t) { const GxTask& T = h->tasks[t]; return (int64_t)T.e1 * (h->m.d + 2 * h->m.hid) + (int64_t)T.n2 * 600 + (int64_t)T.npairs * 60; };
+  std::vector<int32_t> order_all;
+  for (int c = 0; c < kNumClasses; ++c) {
+    auto& v = h->class_order[c];
+    std::stable_sort(v.begin(), v.end(), [&](int32_t x, int32_t y) { return cost(x) > cost(y); });
+    order_all.insert(order_all.end(), v.begin(), v.end());
+  }
+  h->count = count; h->n_hops = n_hops; h->total_n = tn; h->total_e = te;
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), (size_t)count * sizeof(GxTask), cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(h->d_order.reserve((size_t)count * 4));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_order.p, order_all.data(), (size_t)count * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(h->d_counters.reserve(kNumClasses * 4));
+  GX_CUDA_CHECK(h->d_nbrs.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
+  GX_CUDA_CHECK(h->d_lo2gid.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
+  GX_CUDA_CHECK(h->d_srp.reserve((size_t)(tn + count) * 4));
+  GX_CUDA_CHECK(h->d_irp.reserve((size_t)(tn + count) * 4));
+  GX_CUDA_CHECK(h->d_scol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+  GX_CUDA_CHECK(h->d_icol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+  GX_CUDA_CHECK(h->d_pairs.reserve((size_t)std::max<int64_t>(tp, 1) * 4 * 6));
+  h->plan.tasks = h->d_tasks.as<GxTask>();
+  h->plan.nbrs = h->d_nbrs.as<int32_t>();
+  h->plan.lo2gid = h->d_lo2gid.as<int32_t>();
+  h->plan.sub_rowptr = h->d_srp.as<int32_t>();
+  h->plan.irowptr = h->d_irp.as<int32_t>();
+  h->plan.sub_col = h->d_scol.as<int32_t>();
+  h->plan.icol = h->d_icol.as<int32_t>();
+  int32_t* pb = h->d_pairs.as<int32_t>();
+  h->plan.pair_i = pb; h->plan.pair_j = pb + tp; h->plan.pair_pij = pb + 2 * tp;
+  h->plan.pair_pji = pb + 3 * tp; h->plan.pair_oij = pb + 4 * tp; h->plan.pair_oji = pb + 5 * tp;
+  GX_CUDA_CHECK(gx_launch_khop_fill(h->g, count, n_hops, h->ws, h->plan, h->stream));
+  h->launches += 1;
+  // idx_new comes back with the canonical description
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->has_plan = true;
+  if (total_nodes) *total_nodes = tn;
+  if (total_edges) *total_edges = te;
+  return GX_OK;
+}
+
+int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* neighbors,
+                  int32_t* node_idx_new, int32_t* sub_rowptr, int32_t* sub_col) {
+  if (!h || !h->has_plan) { gx_set_error("gx_plan_fetch: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int count = h->count;
+  if (node_off) { for (int t = 0; t < count; ++t) node_off[t] = h->tasks[t].node_off; node_off[count] = h->total_n; }
+  if (edge_off) { for (int t = 0; t < count; ++t) edge_off[t] = h->tasks[t].edge_off; edge_off[count] = h->total_e; }
+  if (node_idx_new) for (int t = 0; t < count; ++t) node_idx_new[t] = h->tasks[t].idx_new;
+  if (neighbors) GX_CUDA_CHECK(cudaMemcpyAsync(neighbors, h->d_nbrs.p, (size_t)h->total_n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (sub_rowptr) GX_CUDA_CHECK(cudaMemcpyAsync(sub_rowptr, h->d_srp.p, (size_t)(h->total_n + count) * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (sub_col) GX_CUDA_CHECK(cudaMemcpyAsync(sub_col, h->d_scol.p, (size_t)h->total_e * 4, cudaMemcpyDeviceToHost, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return GX_OK;
+}
+
+int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
+                     float* edge_mask, float* feat_mask) {
+  if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_nodes: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_plan) { gx_set_error("gx_explain_nodes: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
+  if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built"); return GX_ERR_UNSUPPORTED; }
+  if (hp->mask_bias != 0) { gx_set_error("gx_explain_nodes: --mask-bias is not built"); return GX_ERR_UNSUPPORTED; }
+  if (hp->num_epochs < 1) { gx_set_error("gx_explain_nodes: num_epochs < 1"); return GX_ERR_INVALID; }
+  if (hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_nodes: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
+  if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int count = h->count;
+  const int64_t te = h->total_e;
+  const int iters = hp->num_epochs - 1;
+  // Adam bias-correction table in double, exactly as torch's python scalars (torch/optim/adam.py)
+  std::vector<float2> tab(std::max(iters, 1));
+  for (int t = 1; t <= iters; ++t) {
+    const double bc1 = 1.0 - std::pow((double)hp->beta1, (double)t);
+    const double bc2 = 1.0 - std::pow((double)hp->beta2, (double)t);
+    tab[t - 1].x = (float)((double)hp->lr / bc1);
+    tab[t - 1].y = (float)std::sqrt(bc2);
+  }
+  GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_adam.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  const float* m0_dev = nullptr;
+  float* out_dev = nullptr;
+  float* feat_dev = nullptr;
+  if (space == GX_DEVICE) {
+    m0_dev = m0_edges; out_dev = edge_mask; feat_dev = feat_mask;
+  } else {
+    if (hp->init == GX_INIT_M0) {
+      GX_CUDA_CHECK(h->d_m0.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+      GX_CUDA_CHECK(cudaMemcpyAsync(h->d_m0.p, m0_edges, (size_t)te * 4, cudaMemcpyHostToDevice, h->stream));
+      m0_dev = h->d_m0.as<float>();
+    }
+    GX_CUDA_CHECK(h->d_out.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+    out_dev = h->d_out.as<float>();
+    if (feat_mask) {
+      GX_CUDA_CHECK(h->d_feat.reserve((size_t)count * h->m.d * 4));
+      feat_dev = h->d_feat.as<float>();
+    }
+  }
+  GxHparamsDev hd;
+  hd.iters = iters;
+  hd.one_minus_b1 = 1.0f - hp->beta1;
+  hd.b2 = hp->beta2;
+  hd.one_minus_b2 = 1.0f - hp->beta2;
+  hd.eps = hp->eps;
+  hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = hp->coef_lap;
+  hd.adam_tab = h->d_adam.as<float2>();
+  hd.init = hp->init;
+  hd.seed = hp->seed;
+  GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
+  const auto& last = h->class_order[kNumClasses - 1];
+  int last_grid = 0;
+  if (!last.empty()) {
+    last_grid = std::min<int>((int)last.size(), h->num_sms);
+    GX_CUDA_CHECK(h->d_gws.reserve((size_t)last_grid * h->gws_stride_words * 4));
+  }
+  GX_CUDA_CHECK(cudaEventRecord(h->ev_fork, h->stream));
+  int off = 0;
+  std::vector<int> used;
+  // most expensive class first so that its long tasks start at t=0 and the small ones fill around them
+  std::vector<int> offs(kNumClasses);
+  for (int c = 0; c < kNumClasses; ++c) { offs[c] = off; off += (int)h->class_order[c].size(); }
+  for (int c = kNumClasses - 1; c >= 0; --c) {
+    const int nt = (int)h->class_order[c].size();
+    if (nt == 0) continue;
+    GxExplainLaunch cfg;
+    cfg.order = h->d_order.as<int32_t>() + offs[c];
+    cfg.ntasks = nt;
+    cfg.counter = h->d_counters.as<int32_t>() + c;
+    cfg.smem_bytes = kClasses[c].cap_bytes;
+    cfg.threads = kClasses[c].threads;
+    cfg.idx16 = h->class_idx16[c];
+    cfg.gws = h->d_gws.as<float>();
+    cfg.gws_stride_words = h->gws_stride_words;
+    if (c == kNumClasses - 1) cfg.grid = last_grid;
+    else {
+      // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)
+      int need = 0;
+      for (int32_t t : h->class_order[c]) need = std::max(need, h->tasks[t].smem_bytes);
+      cfg.smem_bytes = std::max(need, 1024);
+      cfg.grid = std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
+    }
+    GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
+    GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    h->launches += 1;
+    GX_CUDA_CHECK(cudaEventRecord(h->ev_join[c], h->side[c]));
+    used.push_back(c);
+  }
+  for (int c : used) GX_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_join[c], 0));
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(edge_mask, out_dev, (size_t)te * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (feat_mask) GX_CUDA_CHECK(cudaMemcpyAsync(feat_mask, feat_dev, (size_t)count * h->m.d * 4, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return GX_OK;
+}
+
+int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* out) {
+  if (!h || !edge_mask || !out) { gx_set_error("gx_densify: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_plan) { gx_set_error("gx_densify: no plan"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int count = h->count;
+  std::vector<int64_t> doff(count + 1);
+  int64_t acc = 0;
+  for (int t = 0; t < count; ++t) { doff[t] = acc; acc += (int64_t)h->tasks[t].n * h->tasks[t].n; }
+  doff[count] = acc;
+  GX_CUDA_CHECK(h->d_dense_off.reserve((size_t)(count + 1) * 8));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_dense_off.p, doff.data(), (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  const float* em = edge_mask;
+  double* o = out;
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(h->d_out.reserve((size_t)std::max<int64_t>(h->total_e, 1) * 4));
+    GX_CUDA_CHECK(cudaMemcpyAsync(h->d_out.p, edge_mask, (size_t)h->total_e * 4, cudaMemcpyHostToDevice, h->stream));
+    GX_CUDA_CHECK(h->d_dense.reserve((size_t)std::max<int64_t>(acc, 1) * 8));
+    em = h->d_out.as<float>();
+    o = h->d_dense.as<double>();
+  }
+  GX_CUDA_CHECK(gx_launch_densify(h->plan, count, h->d_dense_off.as<int64_t>(), em, o, h->stream));
+  h->launches += 1;
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)acc * 8, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return GX_OK;
+}
+
+}  // extern "C"

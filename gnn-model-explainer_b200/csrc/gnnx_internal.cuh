@@ -1,0 +1,186 @@
+// gnnx_internal.cuh -- structures shared by the plan (k-hop extraction) kernels, the persistent
+// explainer kernel and the C-ABI host code.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gnnx.h"
+
+#define GX_MAX_LEVELS 8  // n_hops <= 7
+#define GX_NONE16 0xFFFFu
+
+// One explained node ("task").  Counts are produced by khop_count_kernel, offsets by the host
+// prefix sums, the packed arrays by khop_fill_kernel.
+struct GxTask {
+  int32_t node;     // global node id
+  int32_t n;        // |k-hop set|
+  int32_t e_d;      // directed entries of the induced sub-adjacency (self loops dropped)
+  int32_t npairs;   // e_d / 2 undirected edges
+  int32_t idx_new;  // rank of `node` among its ascending neighbours (explain.py:496)
+  int32_t gt_label; // label[node]
+  int32_t n1, n2;   // level-order prefix sizes: |dist<=L-2|, |dist<=L-1| for L=3 -> |dist<=1|, |dist<=2|
+  int32_t e1;       // directed entries whose source row is < n2 (what the forward ever gathers)
+  int32_t status;   // 0 ok; 1 node not inside its own neighbourhood
+  int32_t cum[GX_MAX_LEVELS + 1];  // cum[t] = #nodes with dist <= t (dist measured from `node`)
+  int32_t smem_bytes;              // shared-memory footprint of this task in the explainer kernel
+  int64_t node_off;  // into nbrs / lo2gid
+  int64_t rp_off;    // into sub_rowptr / irowptr (= node_off + task index: n+1 entries per task)
+  int64_t edge_off;  // into sub_col / icol / m0 / edge_mask
+  int64_t pair_off;  // into the pair arrays
+};
+
+// Device-resident plan arrays (all int32).
+struct GxPlanArrays {
+  GxTask* tasks;
+  int32_t* nbrs;        // [total_n] ascending global ids (canonical order)
+  int32_t* lo2gid;      // [total_n] global id of the node with level-order id i
+  int32_t* sub_rowptr;  // [total_n + count] canonical CSR, task-local
+  int32_t* sub_col;     // [total_e]
+  int32_t* irowptr;     // [total_n + count] level-order CSR, task-local
+  int32_t* icol;        // [total_e] level-order ids, ascending per row
+  int32_t* pair_i;      // [total_e/2] i < j, level-order ids
+  int32_t* pair_j;
+  int32_t* pair_pij;    // position of j in internal row i (absolute, task-local)
+  int32_t* pair_pji;
+  int32_t* pair_oij;    // canonical edge slot of (i,j) (task-local index into the edge arrays)
+  int32_t* pair_oji;
+};
+
+struct GxGraphDev {
+  int64_t N;
+  int32_t nnz;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* feat;  // [N*d]
+  int32_t d;
+  const int32_t* label;
+  const int32_t* pred_label;
+};
+
+struct GxModelDev {
+  int32_t d, hid, emb, C, L;
+  const float* W[3];   // row-major (in,out)
+  const float* Wt[3];  // row-major (out,in)
+  const float* b[3];   // never NULL on device (zeros when --nobias)
+  const float* Wp;     // (C, 2*hid+emb)
+  const float* bp;
+};
+
+struct GxHparamsDev {
+  int32_t iters;  // num_epochs - 1 observed updates
+  float one_minus_b1, b2, one_minus_b2, eps;
+  float c_size, c_feat_size, c_ent, c_lap;
+  const float2* adam_tab;  // [iters] (step_size_t = lr/(1-b1^t), sqrt(1-b2^t)), computed in double on the host
+  int32_t init;
+  uint64_t seed;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory layout of one task in the explainer kernel.  Computed identically on host
+// (classification of tasks into launch classes) and device (carve-up).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int gx_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct GxLayout {
+  // float arrays (offsets in 4-byte words)
+  int X, U, Yh1, q1, Yh2, q2, dZ2, dZ1s, a, M, lap2, W1s, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
+  // index arrays (offsets in 4-byte words; element type IdxT)
+  int icol, irp, pi, pj, ppij, ppji;
+  int total_words;
+  int dp, hs;
+};
+
+// idx_bytes = sizeof(IdxT) (2 or 4)
+__host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1, int np, int d,
+                                                   int hid, int emb, int C, int nwarps,
+                                                   int idx_bytes) {
+  GxLayout L;
+  const int dp = gx_round_up(d, 4), hs = gx_round_up(hid, 4), es = gx_round_up(emb, 4);
+  L.dp = dp;
+  L.hs = hs;
+  int o = 0;
+  auto takef = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
+  auto takei = [&](int elems) { int r = o; o += gx_round_up((elems * idx_bytes + 3) / 4, 4); return r; };
+  L.X = takef(n * dp);
+  L.U = takef(n2 * dp);
+  L.Yh1 = takef(n2 * hs);
+  L.q1 = takef(n2);
+  L.Yh2 = takef(n1 * hs);
+  L.q2 = takef(n1);
+  L.dZ2 = takef(n1 * hs);
+  L.dZ1s = takef(n2 * dp);
+  L.a = takef(e1);
+  L.M = takef(6 * np);  // M_ij, M_ji, m_ij, m_ji, v_ij, v_ji  (SoA, np each)
+  L.lap2 = takef(np);
+  L.W1s = takef(d * hs);
+  L.sF = takef(dp);
+  L.F = takef(dp);
+  L.mF = takef(dp);
+  L.vF = takef(dp);
+  L.gFp = takef(nwarps * dp);
+  int zw = dp > hs ? dp : hs;
+  zw = zw > es ? zw : es;
+  L.zs = takef(nwarps * zw);
+  L.dE = takef(2 * hs);
+  L.dZ3 = takef(hs);
+  L.logit = takef(C < 32 ? 32 : C);
+  L.icol = takei(e1);
+  L.irp = takei(n2 + 1);
+  L.pi = takei(np);
+  L.pj = takei(np);
+  L.ppij = takei(np);
+  L.ppji = takei(np);
+  L.total_words = o;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+#define GX_CUDA_CHECK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      gx_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                   __LINE__);                                                        \
+      return GX_ERR_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+void gx_set_error(const char* fmt, ...);
+
+// kernel launchers (defined in khop.cu / explain_node.cu)
+struct GxSlotWs {
+  uint32_t* bm;     // [slots * W]   membership bitmap (must be all-zero between tasks)
+  int32_t* wpref;   // [slots * (W+1)]
+  uint8_t* dist;    // [slots * N]
+  int32_t* q;       // [slots * (N+1)]
+  int32_t* loc;     // [slots * N]  level-order id by canonical id
+  int32_t* cof;     // [slots * N]  canonical id by level-order id
+  int32_t* pbase;   // [slots * (N+1)]
+  int32_t W;        // words per bitmap
+  int32_t slots;
+};
+
+cudaError_t gx_launch_khop_count(const GxGraphDev& g, const int32_t* nodes_dev, int count, int k,
+                                 int row_lvl, GxSlotWs ws, GxTask* tasks, cudaStream_t s);
+cudaError_t gx_launch_khop_fill(const GxGraphDev& g, int count, int k, GxSlotWs ws, GxPlanArrays plan,
+                                cudaStream_t s);
+cudaError_t gx_launch_hop_rows(const GxGraphDev& g, const int32_t* nodes_dev, int count, int k,
+                               GxSlotWs ws, uint8_t* out_rows, cudaStream_t s);
+
+struct GxExplainLaunch {
+  const int32_t* order;  // [ntasks] task ids of this launch class, most expensive first
+  int32_t ntasks;
+  int32_t* counter;      // device work-queue counter (zeroed)
+  int32_t smem_bytes;    // dynamic shared memory per CTA (0 => global-memory resident variant)
+  int32_t threads;
+  int32_t grid;
+  int32_t idx16;         // 1: 16-bit indices
+  float* gws;            // global workspace for the non-resident variant
+  int64_t gws_stride_words;
+};
+cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
+                              const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
+                              float* out_mask, float* out_feat, cudaStream_t s);
+int gx_explain_max_smem();
+cudaError_t gx_launch_densify(const GxPlanArrays& plan, int count, const int64_t* dense_off,
+                              const float* edge_mask, double* out, cudaStream_t s);

@@ -1,0 +1,416 @@
+// khop.cu -- K1: batched k-hop neighbourhood extraction on CSR (integer, bit-exact).
+//
+// Replaces utils/graph_utils.py:147-158 (neighborhoods: dense (A + A^2 + .. + A^k) > 0) and
+// explainer/explain.py:492-501 (extract_neighborhood: row -> nonzero -> fancy-index) of the
+// reference.  One CTA per explained node; a level-synchronous frontier expansion marks the walk-
+// reachable set in a per-CTA bitmap (the start node is NOT pre-marked: it is a member only if a
+// closed walk of length <= k exists, exactly like the matrix powers), then the CTA emits
+//   * the canonical description the reference API exposes (ascending neighbours, node_idx_new,
+//     induced sub-adjacency as CSR in row-major nonzero order), and
+//   * the internal description the explainer kernel consumes: nodes relabelled in
+//     (distance-from-node, id) order so that every layer's receptive field is a prefix, rows with
+//     columns ascending in that order, the undirected pair list with both directed slots.
+#include "gnnx_internal.cuh"
+
+namespace {
+
+constexpr int KH_THREADS = 256;
+
+struct Slot {
+  uint32_t* bm;
+  int32_t* wpref;
+  uint8_t* dist;
+  int32_t* q;
+  int32_t* loc;
+  int32_t* cof;
+  int32_t* pbase;
+};
+
+__device__ __forceinline__ Slot slot_of(const GxSlotWs& ws, int s, int64_t N) {
+  Slot sl;
+  sl.bm = ws.bm + (int64_t)s * ws.W;
+  sl.wpref = ws.wpref + (int64_t)s * (ws.W + 1);
+  sl.dist = ws.dist + (int64_t)s * N;
+  sl.q = ws.q + (int64_t)s * (N + 1);
+  sl.loc = ws.loc + (int64_t)s * N;
+  sl.cof = ws.cof + (int64_t)s * N;
+  sl.pbase = ws.pbase + (int64_t)s * (N + 1);
+  return sl;
+}
+
+__device__ __forceinline__ bool member(const uint32_t* bm, int v) {
+  return (__ldcg(bm + (v >> 5)) >> (v & 31)) & 1u;
+}
+
+__device__ __forceinline__ int warp_sum_i(int x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// In-place exclusive scan of data[0..len) by the whole CTA; returns the total.  s_w: >= 33 ints.
+__device__ int block_excl_scan(int32_t* data, int len, int* s_w) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < len; base += blockDim.x) {
+    const int idx = base + tid;
+    const int v = idx < len ? data[idx] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = lane < nwarps ? s_w[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_w[lane] = w;
+    }
+    __syncthreads();
+    const int woff = warp > 0 ? s_w[warp - 1] : 0;
+    const int total = s_w[nwarps - 1];
+    if (idx < len) data[idx] = carry + woff + x - v;
+    carry += total;
+    __syncthreads();
+  }
+  return carry;
+}
+
+// Frontier expansion; returns the queue length (q[0] is a pseudo entry holding the start node; the
+// members are q[1..tail)).  s_ctrl: 3 ints of shared memory.
+__device__ int bfs_khop(const GxGraphDev& g, int root, int k, const Slot& sl, int* s_ctrl) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if (tid == 0) {
+    sl.q[0] = root;
+    s_ctrl[0] = 0;
+    s_ctrl[1] = 1;
+    s_ctrl[2] = 1;
+  }
+  __syncthreads();
+  for (int lvl = 0; lvl < k; ++lvl) {
+    const int lo = s_ctrl[0], hi = s_ctrl[1];
+    if (lo == hi) break;
+    for (int idx = lo + warp; idx < hi; idx += nwarps) {
+      const int u = sl.q[idx];
+      const int e1 = g.rowptr[u + 1];
+      for (int e = g.rowptr[u] + lane; e < e1; e += 32) {
+        const int v = g.col[e];
+        const uint32_t bit = 1u << (v & 31);
+        const uint32_t old = atomicOr(sl.bm + (v >> 5), bit);
+        if (!(old & bit)) {
+          const int pos = atomicAdd(&s_ctrl[2], 1);
+          sl.q[pos] = v;
+          sl.dist[v] = (uint8_t)(lvl + 1);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_ctrl[0] = hi;
+      s_ctrl[1] = s_ctrl[2];
+    }
+    __syncthreads();
+  }
+  const int tail = s_ctrl[2];
+  __syncthreads();
+  return tail;
+}
+
+__device__ __forceinline__ void bfs_cleanup(const Slot& sl, int tail) {
+  for (int idx = 1 + threadIdx.x; idx < tail; idx += blockDim.x) sl.bm[sl.q[idx] >> 5] = 0u;
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KH_THREADS)
+khop_count_kernel(GxGraphDev g, const int32_t* __restrict__ nodes, int count, int k, int row_lvl,
+                  GxSlotWs ws, GxTask* __restrict__ tasks) {
+  __shared__ int s_ctrl[3];
+  __shared__ int s_cnt[GX_MAX_LEVELS + 1];
+  __shared__ int s_e[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const Slot sl = slot_of(ws, blockIdx.x, g.N);
+  for (int t = blockIdx.x; t < count; t += gridDim.x) {
+    const int root = nodes[t];
+    const int tail = bfs_khop(g, root, k, sl, s_ctrl);
+    if (tid <= GX_MAX_LEVELS) s_cnt[tid] = 0;
+    if (tid < 2) s_e[tid] = 0;
+    __syncthreads();
+    for (int idx = 1 + warp; idx < tail; idx += nwarps) {
+      const int u = sl.q[idx];
+      const int du = (u == root) ? 0 : (int)sl.dist[u];
+      int cnt = 0;
+      const int e1 = g.rowptr[u + 1];
+      for (int e = g.rowptr[u] + lane; e < e1; e += 32) {
+        const int v = g.col[e];
+        cnt += (v != u && member(sl.bm, v)) ? 1 : 0;
+      }
+      cnt = warp_sum_i(cnt);
+      if (lane == 0) {
+        atomicAdd(&s_cnt[du], 1);
+        atomicAdd(&s_e[0], cnt);
+        if (du <= row_lvl) atomicAdd(&s_e[1], cnt);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      GxTask T;
+      T.node = root;
+      T.n = tail - 1;
+      T.e_d = s_e[0];
+      T.npairs = s_e[0] / 2;
+      T.e1 = s_e[1];
+      T.idx_new = -1;
+      T.gt_label = g.label ? g.label[root] : 0;
+      T.status = member(sl.bm, root) ? 0 : 1;
+      int c = 0;
+      for (int l = 0; l <= GX_MAX_LEVELS; ++l) {
+        c += s_cnt[l];
+        T.cum[l] = c;
+      }
+      T.n2 = T.cum[row_lvl];
+      T.n1 = row_lvl >= 1 ? T.cum[row_lvl - 1] : 0;
+      T.smem_bytes = 0;
+      T.node_off = T.edge_off = T.pair_off = T.rp_off = 0;
+      tasks[t] = T;
+    }
+    __syncthreads();
+    bfs_cleanup(sl, tail);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_i(const int32_t* a, int lo, int hi, int key) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(KH_THREADS)
+khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
+  __shared__ int s_ctrl[3];
+  __shared__ int s_w[33];
+  __shared__ int s_cum[GX_MAX_LEVELS + 2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const Slot sl = slot_of(ws, blockIdx.x, g.N);
+  const int W = ws.W;
+  for (int t = blockIdx.x; t < count; t += gridDim.x) {
+    GxTask* T = P.tasks + t;
+    if (T->status != 0) continue;  // uniform
+    const int root = T->node;
+    const int n = T->n;
+    const int tail = bfs_khop(g, root, k, sl, s_ctrl);
+    int32_t* nbrs = P.nbrs + T->node_off;
+    int32_t* lo2gid = P.lo2gid + T->node_off;
+    int32_t* srp = P.sub_rowptr + T->rp_off;
+    int32_t* irp = P.irowptr + T->rp_off;
+    int32_t* scol = P.sub_col + T->edge_off;
+    int32_t* icol = P.icol + T->edge_off;
+    if (tid <= GX_MAX_LEVELS) s_cum[tid + 1] = T->cum[tid];
+    if (tid == 0) s_cum[0] = 0;
+
+    // (1) word prefix of the membership bitmap -> canonical ranks
+    for (int w = tid; w < W; w += blockDim.x) sl.wpref[w] = __popc(__ldcg(sl.bm + w));
+    __syncthreads();
+    block_excl_scan(sl.wpref, W, s_w);
+    // (2) ascending neighbour list (explain.py:497 np.nonzero)
+    for (int w = tid; w < W; w += blockDim.x) {
+      uint32_t bits = __ldcg(sl.bm + w);
+      int base = sl.wpref[w];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        nbrs[base++] = w * 32 + b;
+        bits &= bits - 1;
+      }
+    }
+    __syncthreads();
+    auto canon = [&](int v) -> int {
+      return sl.wpref[v >> 5] + __popc(__ldcg(sl.bm + (v >> 5)) & ((1u << (v & 31)) - 1u));
+    };
+    if (tid == 0) T->idx_new = canon(root);  // == sum(row[:node_idx]) (explain.py:496)
+    // (3) level order: stable partition of the canonical order by distance from the node
+    int base_lo = 0;
+    for (int lv = 0; lv <= k; ++lv) {
+      for (int c = tid; c < n; c += blockDim.x) {
+        const int v = nbrs[c];
+        const int dv = (v == root) ? 0 : (int)sl.dist[v];
+        sl.pbase[c] = (dv == lv) ? 1 : 0;
+      }
+      __syncthreads();
+      const int tot = block_excl_scan(sl.pbase, n, s_w);
+      for (int c = tid; c < n; c += blockDim.x) {
+        const int v = nbrs[c];
+        const int dv = (v == root) ? 0 : (int)sl.dist[v];
+        if (dv == lv) {
+          const int lo = base_lo + sl.pbase[c];
+          sl.loc[c] = lo;
+          sl.cof[lo] = c;
+          lo2gid[lo] = v;
+        }
+      }
+      base_lo += tot;
+      __syncthreads();
+    }
+    // (4) induced degrees -> canonical and level-order row pointers
+    for (int c = warp; c < n; c += nwarps) {
+      const int u = nbrs[c];
+      int cnt = 0;
+      const int e1 = g.rowptr[u + 1];
+      for (int e = g.rowptr[u] + lane; e < e1; e += 32) {
+        const int v = g.col[e];
+        cnt += (v != u && member(sl.bm, v)) ? 1 : 0;
+      }
+      cnt = warp_sum_i(cnt);
+      if (lane == 0) srp[c] = cnt;
+    }
+    __syncthreads();
+    const int e_tot = block_excl_scan(srp, n, s_w);
+    if (tid == 0) srp[n] = e_tot;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int c = sl.cof[i];
+      irp[i] = srp[c + 1] - srp[c];
+    }
+    __syncthreads();
+    block_excl_scan(irp, n, s_w);
+    if (tid == 0) irp[n] = e_tot;
+    // (5) canonical columns: member neighbours in ascending id order (row-major nonzero order)
+    for (int c = warp; c < n; c += nwarps) {
+      const int u = nbrs[c];
+      int out = srp[c];
+      const int e0 = g.rowptr[u], e1 = g.rowptr[u + 1];
+      for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        int v = -1;
+        bool keep = false;
+        if (e < e1) {
+          v = g.col[e];
+          keep = (v != u) && member(sl.bm, v);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) scol[out + __popc(bal & lt_mask)] = canon(v);
+        out += __popc(bal);
+      }
+    }
+    __syncthreads();
+    // (6) level-order columns: stable partition of each canonical row by level => ascending lo ids
+    for (int i = warp; i < n; i += nwarps) {
+      const int c = sl.cof[i];
+      const int r0 = srp[c], r1 = srp[c + 1];
+      int out = irp[i];
+      for (int lv = 0; lv <= k; ++lv) {
+        const int lo_b = s_cum[lv], lo_e = s_cum[lv + 1];
+        if (lo_b == lo_e) continue;
+        for (int eb = r0; eb < r1; eb += 32) {
+          const int e = eb + lane;
+          int lo = -1;
+          if (e < r1) lo = sl.loc[scol[e]];
+          const bool keep = lo >= lo_b && lo < lo_e;
+          const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) icol[out + __popc(bal & lt_mask)] = lo;
+          out += __popc(bal);
+        }
+      }
+    }
+    __syncthreads();
+    // (7) undirected pairs (i < j) with both directed slots, internal and canonical
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int r0 = irp[i], r1 = irp[i + 1];
+      sl.pbase[i] = r1 - lower_bound_i(icol, r0, r1, i + 1);
+    }
+    __syncthreads();
+    block_excl_scan(sl.pbase, n, s_w);
+    for (int i = warp; i < n; i += nwarps) {
+      const int r0 = irp[i], r1 = irp[i + 1];
+      const int ub = lower_bound_i(icol, r0, r1, i + 1);
+      const int ci = sl.cof[i];
+      for (int kk = ub + lane; kk < r1; kk += 32) {
+        const int j = icol[kk];
+        const int cj = sl.cof[j];
+        const int64_t p = T->pair_off + sl.pbase[i] + (kk - ub);
+        P.pair_i[p] = i;
+        P.pair_j[p] = j;
+        P.pair_pij[p] = kk;
+        P.pair_pji[p] = lower_bound_i(icol, irp[j], irp[j + 1], i);
+        P.pair_oij[p] = lower_bound_i(scol, srp[ci], srp[ci + 1], cj);
+        P.pair_oji[p] = lower_bound_i(scol, srp[cj], srp[cj + 1], ci);
+      }
+    }
+    __syncthreads();
+    bfs_cleanup(sl, tail);
+  }
+}
+
+// graph_utils.neighborhoods rows: out_rows[t*N + v] = 1 for members (out pre-zeroed).
+__global__ void __launch_bounds__(KH_THREADS)
+hop_rows_kernel(GxGraphDev g, const int32_t* __restrict__ nodes, int count, int k, GxSlotWs ws,
+                uint8_t* __restrict__ out_rows) {
+  __shared__ int s_ctrl[3];
+  const Slot sl = slot_of(ws, blockIdx.x, g.N);
+  for (int t = blockIdx.x; t < count; t += gridDim.x) {
+    const int tail = bfs_khop(g, nodes[t], k, sl, s_ctrl);
+    uint8_t* row = out_rows + (int64_t)t * g.N;
+    for (int idx = 1 + threadIdx.x; idx < tail; idx += blockDim.x) row[sl.q[idx]] = 1;
+    __syncthreads();
+    bfs_cleanup(sl, tail);
+  }
+}
+
+// dense (n,n) float64 expansion of packed edge masks (explain.py:209-221 return value)
+__global__ void __launch_bounds__(256)
+densify_kernel(GxPlanArrays P, int count, const int64_t* __restrict__ dense_off,
+               const float* __restrict__ edge_mask, double* __restrict__ out) {
+  for (int t = blockIdx.x; t < count; t += gridDim.x) {
+    const GxTask* T = P.tasks + t;
+    const int n = T->n;
+    double* o = out + dense_off[t];
+    const int64_t nn = (int64_t)n * n;
+    for (int64_t i = threadIdx.x; i < nn; i += blockDim.x) o[i] = 0.0;
+    __syncthreads();
+    const int32_t* srp = P.sub_rowptr + T->rp_off;
+    const int32_t* scol = P.sub_col + T->edge_off;
+    const float* em = edge_mask + T->edge_off;
+    for (int r = threadIdx.x >> 5; r < n; r += blockDim.x >> 5)
+      for (int e = srp[r] + (threadIdx.x & 31); e < srp[r + 1]; e += 32)
+        o[(int64_t)r * n + scol[e]] = (double)em[e];
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+static int khop_grid(int count, const GxSlotWs& ws) { return count < ws.slots ? count : ws.slots; }
+
+cudaError_t gx_launch_khop_count(const GxGraphDev& g, const int32_t* nodes_dev, int count, int k,
+                                 int row_lvl, GxSlotWs ws, GxTask* tasks, cudaStream_t s) {
+  khop_count_kernel<<<khop_grid(count, ws), KH_THREADS, 0, s>>>(g, nodes_dev, count, k, row_lvl, ws, tasks);
+  return cudaGetLastError();
+}
+
+cudaError_t gx_launch_khop_fill(const GxGraphDev& g, int count, int k, GxSlotWs ws, GxPlanArrays plan,
+                                cudaStream_t s) {
+  khop_fill_kernel<<<khop_grid(count, ws), KH_THREADS, 0, s>>>(g, count, k, ws, plan);
+  return cudaGetLastError();
+}
+
+cudaError_t gx_launch_hop_rows(const GxGraphDev& g, const int32_t* nodes_dev, int count, int k,
+                               GxSlotWs ws, uint8_t* out_rows, cudaStream_t s) {
+  hop_rows_kernel<<<khop_grid(count, ws), KH_THREADS, 0, s>>>(g, nodes_dev, count, k, ws, out_rows);
+  return cudaGetLastError();
+}
+
+cudaError_t gx_launch_densify(const GxPlanArrays& plan, int count, const int64_t* dense_off,
+                              const float* edge_mask, double* out, cudaStream_t s) {
+  const int grid = count < 148 * 8 ? count : 148 * 8;
+  densify_kernel<<<grid, 256, 0, s>>>(plan, count, dense_off, edge_mask, out);
+  return cudaGetLastError();
+}

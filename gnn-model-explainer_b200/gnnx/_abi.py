@@ -1,0 +1,77 @@
+"""ctypes binding of libgnnx.so (include/gnnx.h).  No fallback: importing this module without
+the built library raises, and creating an engine without a CUDA device raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgnnx.so")
+
+GX_OK = 0
+GX_HOST, GX_DEVICE = 0, 1
+GX_INIT_M0, GX_INIT_PHILOX = 0, 1
+GX_MODEL_BN = 1
+
+EXPORTS = [
+    "gx_default_hparams", "gx_last_error", "gx_version", "gx_create", "gx_destroy", "gx_set_stream",
+    "gx_sync", "gx_set_model", "gx_set_graph_csr", "gx_neighborhood_rows", "gx_plan_nodes",
+    "gx_plan_fetch", "gx_explain_nodes", "gx_densify", "gx_launch_count",
+]
+
+
+class GxModelDims(C.Structure):
+    _fields_ = [("input_dim", C.c_int32), ("hidden_dim", C.c_int32), ("embed_dim", C.c_int32),
+                ("num_classes", C.c_int32), ("num_layers", C.c_int32), ("flags", C.c_int32)]
+
+
+class GxHparams(C.Structure):
+    _fields_ = [("num_epochs", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("coef_size", C.c_float), ("coef_feat_size", C.c_float),
+                ("coef_ent", C.c_float), ("coef_lap", C.c_float), ("mask_act", C.c_int32),
+                ("mask_bias", C.c_int32), ("init", C.c_int32), ("seed", C.c_uint64)]
+
+
+class GnnxError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("libgnnx status %d: %s" % (status, message))
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libgnnx.so not found at %s -- build it with `python __graft_entry__.py` "
+            "(or gnn-model-explainer_b200/csrc/build.sh); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32p, i64p, f32p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    L.gx_last_error.restype = C.c_char_p
+    L.gx_version.restype = C.c_int
+    L.gx_default_hparams.argtypes = [C.POINTER(GxHparams)]
+    L.gx_default_hparams.restype = None
+    L.gx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.gx_destroy.argtypes = [vp]
+    L.gx_set_stream.argtypes = [vp, vp]
+    L.gx_sync.argtypes = [vp]
+    L.gx_set_model.argtypes = [vp, C.POINTER(GxModelDims), C.POINTER(vp), C.POINTER(vp), f32p, f32p]
+    L.gx_set_graph_csr.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int32, i32p, i32p]
+    L.gx_neighborhood_rows.argtypes = [vp, i32p, C.c_int32, C.c_int32, vp]
+    L.gx_plan_nodes.argtypes = [vp, i32p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.gx_plan_fetch.argtypes = [vp, i64p, i64p, i32p, i32p, i32p, i32p]
+    L.gx_explain_nodes.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, f32p, f32p]
+    L.gx_densify.argtypes = [vp, C.c_int, f32p, vp]
+    L.gx_launch_count.argtypes = [vp]
+    L.gx_launch_count.restype = C.c_int64
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here means the library does not match include/gnnx.h
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != GX_OK:
+        raise GnnxError(status, lib().gx_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,180 @@
+"""Engine: thin host wrapper around one libgnnx handle (one per GPU / host thread).
+
+Numpy arrays are passed as HOST pointers; torch CUDA tensors as DEVICE pointers.  All arithmetic
+happens inside the library's CUDA kernels; this module only marshals buffers."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _f32c(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32c(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Plan:
+    """Canonical (reference-ordered) description of a batch of k-hop subgraphs."""
+
+    def __init__(self, nodes, node_off, edge_off, neighbors, node_idx_new, sub_rowptr, sub_col):
+        self.nodes = nodes
+        self.node_off = node_off
+        self.edge_off = edge_off
+        self.neighbors = neighbors
+        self.node_idx_new = node_idx_new
+        self.sub_rowptr = sub_rowptr
+        self.sub_col = sub_col
+        self.count = len(nodes)
+        self.total_nodes = int(node_off[-1])
+        self.total_edges = int(edge_off[-1])
+
+    def n(self, t):
+        return int(self.node_off[t + 1] - self.node_off[t])
+
+    def neighbors_of(self, t):
+        return self.neighbors[self.node_off[t]:self.node_off[t + 1]]
+
+    def csr_of(self, t):
+        """(rowptr[n+1], col[E_t]) of task t (task-local)."""
+        n = self.n(t)
+        rp = self.sub_rowptr[self.node_off[t] + t: self.node_off[t] + t + n + 1]
+        return rp, self.sub_col[self.edge_off[t]:self.edge_off[t + 1]]
+
+    def rows_cols_of(self, t):
+        rp, col = self.csr_of(t)
+        rows = np.repeat(np.arange(len(rp) - 1, dtype=np.int64), np.diff(rp))
+        return rows, col.astype(np.int64)
+
+    def dense_of(self, t, edge_values, dtype=np.float64):
+        """(n,n) dense array holding edge_values of task t at the sub-adjacency entries."""
+        n = self.n(t)
+        rows, cols = self.rows_cols_of(t)
+        out = np.zeros((n, n), dtype=dtype)
+        out[rows, cols] = edge_values[self.edge_off[t]:self.edge_off[t + 1]]
+        return out
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _abi.lib()
+        h = C.c_void_p()
+        _abi.check(self._lib.gx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.input_dim = None
+        self._plan = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- setup
+    def set_stream(self, cuda_stream_ptr):
+        _abi.check(self._lib.gx_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def sync(self):
+        _abi.check(self._lib.gx_sync(self._h))
+
+    def set_model(self, weights, num_layers=3, bn=False):
+        """weights: dict W1,b1,W2,b2,W3,b3,Wp,bp (numpy; b* may be None)."""
+        Ws = [_f32c(weights["W%d" % (l + 1)]) for l in range(num_layers)]
+        bs = [None if weights.get("b%d" % (l + 1)) is None else _f32c(weights["b%d" % (l + 1)])
+              for l in range(num_layers)]
+        Wp, bp = _f32c(weights["Wp"]), _f32c(weights["bp"])
+        dims = _abi.GxModelDims(Ws[0].shape[0], Ws[0].shape[1], Ws[-1].shape[1], Wp.shape[0], num_layers,
+                                _abi.GX_MODEL_BN if bn else 0)
+        wp = (C.c_void_p * num_layers)(*[w.ctypes.data for w in Ws])
+        bp_arr = (C.c_void_p * num_layers)(*[(b.ctypes.data if b is not None else None) for b in bs])
+        _abi.check(self._lib.gx_set_model(self._h, C.byref(dims), wp, bp_arr, _np_ptr(Wp), _np_ptr(bp)))
+        self.input_dim = int(Ws[0].shape[0])
+        self.num_classes = int(Wp.shape[0])
+
+    def set_graph_csr(self, rowptr, col, feat, label, pred_label):
+        rowptr, col = _i32c(rowptr), _i32c(col)
+        feat = _f32c(feat)
+        N = len(rowptr) - 1
+        assert feat.shape[0] == N
+        label = None if label is None else _i32c(label)
+        pred_label = _i32c(pred_label)
+        _abi.check(self._lib.gx_set_graph_csr(self._h, N, _np_ptr(rowptr), _np_ptr(col), _np_ptr(feat),
+                                              feat.shape[1], _np_ptr(label), _np_ptr(pred_label)))
+        self.num_nodes = N
+
+    def set_graph_csr_structure(self, rowptr, col):
+        """Structure-only upload (for neighbourhood queries): dummy 1-d features / labels."""
+        N = len(rowptr) - 1
+        self.set_graph_csr(rowptr, col, np.zeros((N, 1), np.float32), None, np.zeros(N, np.int32))
+
+    # ---------------------------------------------------------------- k-hop
+    def neighborhood_rows(self, nodes, n_hops):
+        nodes = _i32c(nodes)
+        out = np.zeros((len(nodes), self.num_nodes), dtype=np.uint8)
+        if len(nodes):
+            _abi.check(self._lib.gx_neighborhood_rows(self._h, _np_ptr(nodes), len(nodes), int(n_hops), _np_ptr(out)))
+        return out
+
+    def plan_nodes(self, nodes, n_hops, fetch=True):
+        nodes = _i32c(nodes)
+        tn, te = C.c_int64(), C.c_int64()
+        _abi.check(self._lib.gx_plan_nodes(self._h, _np_ptr(nodes), len(nodes), int(n_hops), C.byref(tn), C.byref(te)))
+        self._plan_sizes = (len(nodes), tn.value, te.value)
+        if not fetch:
+            return None
+        return self.fetch_plan(nodes)
+
+    def fetch_plan(self, nodes):
+        count, tn, te = self._plan_sizes
+        node_off = np.empty(count + 1, np.int64)
+        edge_off = np.empty(count + 1, np.int64)
+        nbrs = np.empty(tn, np.int32)
+        idx_new = np.empty(count, np.int32)
+        srp = np.empty(tn + count, np.int32)
+        scol = np.empty(te, np.int32)
+        _abi.check(self._lib.gx_plan_fetch(self._h, _np_ptr(node_off), _np_ptr(edge_off), _np_ptr(nbrs),
+                                           _np_ptr(idx_new), _np_ptr(srp), _np_ptr(scol)))
+        self._plan = Plan(np.asarray(nodes), node_off, edge_off, nbrs, idx_new, srp, scol)
+        return self._plan
+
+    # ---------------------------------------------------------------- hot path
+    def make_hparams(self, num_epochs=100, lr=0.1, init=_abi.GX_INIT_M0, seed=0, **over):
+        hp = _abi.GxHparams()
+        self._lib.gx_default_hparams(C.byref(hp))
+        hp.num_epochs = int(num_epochs)
+        hp.lr = float(lr)
+        hp.init = int(init)
+        hp.seed = int(seed)
+        for k, v in over.items():
+            setattr(hp, k, v)
+        return hp
+
+    def explain_nodes_host(self, hp, m0_edges, edge_mask_out, feat_mask_out=None):
+        """Host buffers (numpy).  m0_edges may be None with GX_INIT_PHILOX."""
+        _abi.check(self._lib.gx_explain_nodes(self._h, C.byref(hp), _abi.GX_HOST, _np_ptr(m0_edges),
+                                              _np_ptr(edge_mask_out), _np_ptr(feat_mask_out)))
+
+    def explain_nodes_ptr(self, hp, space, m0_ptr, out_ptr, feat_ptr=0):
+        _abi.check(self._lib.gx_explain_nodes(self._h, C.byref(hp), int(space), C.c_void_p(int(m0_ptr) or None),
+                                              C.c_void_p(int(out_ptr)), C.c_void_p(int(feat_ptr) or None)))
+
+    def densify_host(self, edge_mask, total_dense):
+        out = np.empty(total_dense, np.float64)
+        _abi.check(self._lib.gx_densify(self._h, _abi.GX_HOST, _np_ptr(_f32c(edge_mask)), _np_ptr(out)))
+        return out
+
+    def launch_count(self):
+        return int(self._lib.gx_launch_count(self._h))

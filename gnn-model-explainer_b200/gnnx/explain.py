@@ -1,0 +1,205 @@
+"""Drop-in for the reference's explainer/explain.py:Explainer (node-classification path).
+
+Same constructor, same method names/arguments, same return values (dense (n,n) float64 numpy
+arrays, one per node, in input order) and the same .npy side effect
+(explain.py:216-220).  The per-node optimisation is NOT executed in Python: the whole batch of
+nodes goes through libgnnx (k-hop extraction kernel + one persistent CTA per node).
+
+Differences that are deliberate and documented:
+  * explain_nodes() batches all nodes into one launch; it returns the list of masks like the
+    reference (explain.py:234-236,290-292) but does not run the reference's matplotlib/tensorboard
+    post-processing (denoise_graph/align/log_graph, explain.py:238-288: viz, out of scope).
+  * M0 policy (args.gnnx_init, default "torch"): "torch" draws FloatTensor(n,n).normal_(1, std)
+    from torch's global CPU generator per node in call order, exactly the RNG consumption of
+    ExplainModule.construct_edge_mask (explain.py:645-652) -> bit-identical M0 under the same
+    torch.manual_seed; "device" draws N(1, 2/n) with Philox on the GPU (no n^2 host work).
+  * a node outside its own k-hop set (isolated) raises instead of explaining a wrong row.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _abi
+from .engine import Engine
+from . import graph_utils as _gu
+
+
+def gen_prefix(args):
+    """utils/io_utils.py:37-51 (file-name compatibility of the .npy side effect)."""
+    name = args.bmname if getattr(args, "bmname", None) is not None else args.dataset
+    name += "_" + args.method
+    name += "_h" + str(args.hidden_dim) + "_o" + str(args.output_dim)
+    if not args.bias:
+        name += "_nobias"
+    if len(args.name_suffix) > 0:
+        name += "_" + args.name_suffix
+    return name
+
+
+def gen_explainer_prefix(args):
+    """utils/io_utils.py:54-60."""
+    name = gen_prefix(args) + "_explain"
+    if len(args.explainer_suffix) > 0:
+        name += "_" + args.explainer_suffix
+    return name
+
+
+def model_weights(model):
+    """state_dict of a reference (or gnnx) GcnEncoderNode/GcnEncoderGraph -> weight dict.
+    Keys as in the reference checkpoints: conv_first / conv_block.i / conv_last /
+    pred_model."""
+    sd = {k: v.detach().cpu().float().numpy() for k, v in model.state_dict().items()}
+    if "pred_model.weight" not in sd:
+        raise NotImplementedError("pred_hidden_dims != [] (MLP prediction head) is not built")
+    n_block = 0
+    while ("conv_block.%d.weight" % n_block) in sd:
+        n_block += 1
+    names = ["conv_first"] + ["conv_block.%d" % i for i in range(n_block)] + ["conv_last"]
+    w = {}
+    for l, nm in enumerate(names, 1):
+        w["W%d" % l] = sd[nm + ".weight"]
+        w["b%d" % l] = sd.get(nm + ".bias")
+        if (nm + ".self_weight") in sd or (nm + ".att_weight") in sd:
+            raise NotImplementedError("add_self / att GraphConv variants are out of scope")
+    w["Wp"], w["bp"] = sd["pred_model.weight"], sd["pred_model.bias"]
+    return w, len(names)
+
+
+class Explainer:
+    def __init__(self, model, adj, feat, label, pred, train_idx, args, writer=None,
+                 print_training=True, graph_mode=False, graph_idx=False, device=None):
+        self.model = model
+        if hasattr(self.model, "eval"):
+            self.model.eval()
+        self.adj = adj
+        self.feat = feat
+        self.label = label
+        self.pred = pred
+        self.train_idx = train_idx
+        self.n_hops = args.num_gc_layers
+        self.graph_mode = graph_mode
+        self.graph_idx = graph_idx
+        self.args = args
+        self.writer = writer
+        self.print_training = print_training
+        self._neighborhoods = None
+        if graph_mode:
+            raise NotImplementedError("graph-classification mode (explain_graphs) is the next scope row")
+        if getattr(args, "mask_act", "sigmoid") != "sigmoid":
+            raise NotImplementedError("mask_act=%r is not built (default: sigmoid)" % args.mask_act)
+        if getattr(args, "mask_bias", False):
+            raise NotImplementedError("--mask-bias is not built")
+        if getattr(args, "opt", "adam") != "adam" or getattr(args, "opt_scheduler", "none") != "none":
+            raise NotImplementedError("only Adam without scheduler (explainer_main.py defaults) is built")
+        if getattr(model, "bn", False):
+            raise NotImplementedError("--bn models are not built")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() else 0
+        self.engine = Engine(device)
+        weights, num_layers = model_weights(model)
+        self.engine.set_model(weights, num_layers=num_layers)
+        adj_np = np.asarray(adj)
+        if adj_np.ndim != 3 or adj_np.shape[0] != 1:
+            raise NotImplementedError("node mode expects adj of shape (1,N,N) (single graph)")
+        self._rowptr, self._col = _gu.csr_from_dense(adj_np[0])
+        feat_np = np.asarray(feat, dtype=np.float32)[0]
+        label_np = np.asarray(label)[0].astype(np.int32)
+        pred_np = np.asarray(pred)[0]
+        self._pred_label = np.argmax(pred_np, axis=1).astype(np.int32)          # explain.py:105
+        self.engine.set_graph_csr(self._rowptr, self._col, feat_np, label_np, self._pred_label)
+
+    # the reference computes this dense (B,N,N) matrix eagerly in __init__ (explain.py:67); here
+    # it is materialised on demand only (the engine never needs it).
+    @property
+    def neighborhoods(self):
+        if self._neighborhoods is None:
+            N = self.engine.num_nodes
+            rows = self.engine.neighborhood_rows(np.arange(N, dtype=np.int32), self.n_hops)
+            self._neighborhoods = rows.astype(int)[None]
+        return self._neighborhoods
+
+    def extract_neighborhood(self, node_idx, graph_idx=0):
+        """explain.py:492-501: (node_idx_new, sub_adj, sub_feat, sub_label, neighbors)."""
+        plan = self.engine.plan_nodes([int(node_idx)], self.n_hops)
+        nbrs = plan.neighbors_of(0).astype(np.int64)
+        sub_adj = plan.dense_of(0, np.ones(plan.total_edges, dtype=np.float64),
+                                dtype=np.asarray(self.adj).dtype)
+        sub_feat = np.asarray(self.feat)[graph_idx, nbrs]
+        sub_label = np.asarray(self.label)[graph_idx][nbrs]
+        return int(plan.node_idx_new[0]), sub_adj, sub_feat, sub_label, nbrs
+
+    # ---------------------------------------------------------------- internals
+    def _hparams(self):
+        a = self.args
+        init = getattr(a, "gnnx_init", "torch")
+        if init not in ("torch", "device"):
+            raise ValueError("args.gnnx_init must be 'torch' or 'device'")
+        hp = self.engine.make_hparams(
+            num_epochs=a.num_epochs, lr=a.lr,
+            init=_abi.GX_INIT_M0 if init == "torch" else _abi.GX_INIT_PHILOX,
+            seed=int(getattr(a, "gnnx_seed", 0)))
+        return hp, init
+
+    def _draw_m0(self, plan):
+        """Per node, in call order: FloatTensor(n,n).normal_(1, std) (explain.py:645-652), gathered at the
+        directed-edge slots.  Consumes torch's global CPU RNG exactly like the reference."""
+        m0 = np.empty(plan.total_edges, dtype=np.float32)
+        gain = torch.nn.init.calculate_gain("relu")
+        for t in range(plan.count):
+            n = plan.n(t)
+            std = gain * math.sqrt(2.0 / (n + n))
+            M = torch.FloatTensor(n, n).normal_(1.0, std).numpy()
+            rows, cols = plan.rows_cols_of(t)
+            m0[plan.edge_off[t]:plan.edge_off[t + 1]] = M[rows, cols]
+        return m0
+
+    def _explain_batch(self, node_indices, graph_idx=0, model="exp", unconstrained=False):
+        if model != "exp":
+            raise NotImplementedError("model=%r ('grad' baseline / att) is not built" % model)
+        if unconstrained:
+            raise NotImplementedError("unconstrained=True is not built")
+        if graph_idx not in (0, -1):
+            raise NotImplementedError("multi-graph node tasks (graph_idx != 0) are not built")
+        nodes = [int(i) for i in node_indices]
+        plan = self.engine.plan_nodes(nodes, self.n_hops)
+        hp, init = self._hparams()
+        m0 = self._draw_m0(plan) if init == "torch" else None
+        edge_mask = np.empty(plan.total_edges, dtype=np.float32)
+        self.engine.explain_nodes_host(hp, m0, edge_mask)
+        return plan, edge_mask
+
+    def _save(self, masked_adj, node_idx):
+        fname = "masked_adj_" + gen_explainer_prefix(self.args) + (
+            "node_idx_" + str(node_idx) + "graph_idx_" + str(self.graph_idx) + ".npy")
+        os.makedirs(self.args.logdir, exist_ok=True)
+        with open(os.path.join(self.args.logdir, fname), "wb") as outfile:
+            np.save(outfile, np.asarray(masked_adj.copy()))
+        return fname
+
+    # ---------------------------------------------------------------- public API
+    def explain(self, node_idx, graph_idx=0, graph_mode=False, unconstrained=False, model="exp"):
+        """explain.py:74-221 -> (n,n) float64 masked adjacency of the node's k-hop subgraph."""
+        if graph_mode:
+            raise NotImplementedError("graph-classification mode is the next scope row")
+        plan, edge_mask = self._explain_batch([node_idx], graph_idx, model, unconstrained)
+        masked_adj = plan.dense_of(0, edge_mask, dtype=np.float64)
+        fname = self._save(masked_adj, node_idx)
+        if self.print_training:
+            print("Saved adjacency matrix to ", fname)
+        return masked_adj
+
+    def explain_nodes(self, node_indices, args=None, graph_idx=0, save=True):
+        """explain.py:225-292 -> list of masked adjacencies in input order (one batched launch)."""
+        plan, edge_mask = self._explain_batch(node_indices, graph_idx)
+        out = [plan.dense_of(t, edge_mask, dtype=np.float64) for t in range(plan.count)]
+        if save:
+            for t, node in enumerate(node_indices):
+                self._save(out[t], int(node))
+        return out
+
+    def explain_nodes_packed(self, node_indices, graph_idx=0):
+        """Same computation, returning (plan, edge_mask) without densifying: edge_mask[edge_off[t]:
+        edge_off[t+1]] are the masked_adj entries of node t at plan.csr_of(t) (row-major order)."""
+        return self._explain_batch(node_indices, graph_idx)

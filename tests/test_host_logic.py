@@ -1,0 +1,70 @@
+"""CPU: host-side marshalling logic of the drop-in package (no GPU needed)."""
+import types
+
+import numpy as np
+import pytest
+
+import gnnx
+from gnnx import explain as gx_explain
+from gnnx import graph_utils as gx_gu
+from gnnx.dist import shard_indices
+from gnnx.engine import Plan
+import gnnx_oracle as O
+
+
+def test_csr_from_dense_matches_oracle():
+    rng = np.random.default_rng(0)
+    A = (rng.random((40, 40)) < 0.1).astype(float)
+    A = np.maximum(A, A.T)
+    np.fill_diagonal(A, 0)
+    rp, col = gx_gu.csr_from_dense(A)
+    rp2, col2 = O.csr_from_dense(A)
+    assert np.array_equal(rp, rp2) and np.array_equal(col, col2)
+    with pytest.raises(NotImplementedError):
+        gx_gu.csr_from_dense(A * 0.5)
+
+
+def test_plan_densify_roundtrip():
+    # two tasks: a triangle and a path
+    node_off = np.array([0, 3, 6]); edge_off = np.array([0, 6, 10])
+    srp = np.array([0, 2, 4, 6, 0, 1, 3, 4], np.int32)
+    scol = np.array([1, 2, 0, 2, 0, 1, 1, 0, 2, 1], np.int32)
+    plan = Plan(np.array([5, 9]), node_off, edge_off, np.arange(6, dtype=np.int32), np.array([0, 1], np.int32), srp, scol)
+    vals = np.arange(1, 11, dtype=np.float32)
+    d0, d1 = plan.dense_of(0, vals), plan.dense_of(1, vals)
+    assert d0.dtype == np.float64 and d0.shape == (3, 3) and d0[0, 1] == 1 and d0[2, 1] == 6 and d0[0, 0] == 0
+    assert d1[0, 1] == 7 and d1[1, 0] == 8 and d1[1, 2] == 9 and d1[2, 1] == 10 and d1.sum() == 34
+
+
+def test_explainer_prefix_matches_reference_naming():
+    args = types.SimpleNamespace(bmname=None, dataset="syn1", method="base", hidden_dim=20, output_dim=20,
+                                 bias=True, name_suffix="", explainer_suffix="")
+    assert gx_explain.gen_explainer_prefix(args) == "syn1_base_h20_o20_explain"   # io_utils.py:37-60
+    args.bias = False; args.name_suffix = "x"; args.explainer_suffix = "y"
+    assert gx_explain.gen_explainer_prefix(args) == "syn1_base_h20_o20_nobias_x_explain_y"
+
+
+def test_model_state_dict_keys_match_reference_checkpoints():
+    args = types.SimpleNamespace(gpu=False, bias=True, method="base")
+    m = gnnx.models.GcnEncoderNode(10, 20, 20, 4, 3, bn=False, args=args)
+    keys = set(m.state_dict().keys())
+    assert keys == {"conv_first.weight", "conv_first.bias", "conv_block.0.weight", "conv_block.0.bias",
+                    "conv_last.weight", "conv_last.bias", "pred_model.weight", "pred_model.bias"}
+    w, L = gx_explain.model_weights(m)
+    assert L == 3 and w["W1"].shape == (10, 20) and w["Wp"].shape == (4, 60)
+    # forward agrees with the oracle's statement of the architecture
+    import torch
+    x = torch.randn(1, 7, 10); adj = (torch.rand(1, 7, 7) < 0.4).float()
+    adj = ((adj + adj.transpose(1, 2)) > 0).float()
+    y, _ = m(x, adj)
+    y2 = O._gcn_forward_torch(x, adj, O.weights_to_torch(w, False), False)
+    assert torch.allclose(y, y2, atol=1e-6)
+
+
+def test_shard_indices_partition():
+    for world in (1, 2, 3, 8):
+        costs = np.random.default_rng(1).integers(1, 100, 37)
+        seen = np.concatenate([shard_indices(37, world, r, costs) for r in range(world)])
+        assert sorted(seen) == list(range(37))
+        loads = [costs[shard_indices(37, world, r, costs)].sum() for r in range(world)]
+        assert max(loads) - min(loads) <= costs.max()

@@ -1,0 +1,112 @@
+"""CPU: pins the oracle (oracle/gnnx_oracle.py) against the golden vectors produced by the
+UNMODIFIED reference (oracle/gen_golden.py).  Sized to run in about a minute."""
+import numpy as np
+import pytest
+
+import gnnx_oracle as O
+import util
+
+
+@pytest.fixture(scope="module", params=["rand", "syn4", "syn1"])
+def fx(request):
+    return util.load_fixture(request.param)
+
+
+def _sample(fx, k):
+    return fx.nodes if len(fx.nodes) <= k else [fx.nodes[i] for i in np.linspace(0, len(fx.nodes) - 1, k).astype(int)]
+
+
+def test_khop_set_matches_reference(fx):
+    # Explainer.extract_neighborhood (explain.py:492-501): neighbours, node_idx_new, edge count
+    for node in fx.nodes:
+        idx, srp, scol, _, _, nbrs = O.extract_neighborhood(fx.rowptr, fx.col, fx.feat, fx.label, node, 3)
+        assert np.array_equal(nbrs, fx.gold["n%d_nbrs" % node])
+        assert idx == int(fx.gold["n%d_idx_new" % node])
+        assert len(scol) == len(fx.gold["n%d_mask" % node])
+
+
+@pytest.mark.parametrize("name", ["syn1", "syn4"])
+def test_dense_neighborhoods_match_reference_hop_matrix(name):
+    # graph_utils.neighborhoods (graph_utils.py:147-158): full (N,N) matrix, bit-exact
+    fx = util.load_fixture(name)
+    hops = np.load(util.GOLDEN + "/%s_hops.npz" % name)
+    A = O.dense_from_csr(fx.rowptr, fx.col)
+    hop = O.neighborhoods_dense(A[None], 3)[0]
+    ref = np.unpackbits(hops["hop_bits"], axis=1)[:, : fx.N]
+    assert np.array_equal(hop.astype(np.uint8), ref)
+    assert np.array_equal(hop.sum(1), hops["hop_rowsum"])
+    # and the CSR frontier expansion defines the same sets
+    for node in range(0, fx.N, 37):
+        assert np.array_equal(O.khop_walk_set(fx.rowptr, fx.col, node, 3), np.nonzero(ref[node])[0])
+
+
+def _inputs(fx, node):
+    idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(fx.rowptr, fx.col, fx.feat, fx.label, node, 3)
+    n = len(nbrs)
+    A = O.dense_from_csr(srp, scol)
+    ei, ej = np.nonzero(A)
+    M0 = np.zeros((n, n), np.float32)
+    M0[ei, ej] = fx.gold["n%d_m0" % node]
+    ref = np.zeros((n, n))
+    ref[ei, ej] = fx.gold["n%d_mask" % node]
+    return A, sfeat, slabel[idx], fx.pred_label[nbrs], idx, M0, ref
+
+
+def test_line_by_line_port_is_bit_exact(fx):
+    # same ops in the same order as the reference => identical floats (off-edge M0 entries are
+    # irrelevant to the result: they are zero here, random in the reference)
+    nodes = [n for n in _sample(fx, 6) if len(fx.gold["n%d_nbrs" % n]) <= 200][:4] or fx.nodes[:1]
+    for node in nodes:
+        A, sfeat, gt, pl, idx, M0, ref = _inputs(fx, node)
+        out = O.explain_dense_torch(A, sfeat, gt, pl, idx, fx.weights, M0)
+        assert O.rel_l2(out, ref) <= 1e-6, "node %d" % node
+
+
+def test_closed_form_matches_reference(fx):
+    cond = np.load(util.GOLDEN + "/%s_cond.npz" % fx.name)
+    tol_of = {int(n): max(1e-4, 3 * max(a, b)) for n, a, b in zip(cond["nodes"], cond["err_closed64"], cond["err_closed32"])}
+    for node in _sample(fx, 8):
+        A, sfeat, gt, pl, idx, M0, ref = _inputs(fx, node)
+        out = O.explain_closed_form(A, sfeat, gt, pl, idx, fx.weights, M0, dtype=np.float32)
+        assert O.rel_l2(out, ref) <= tol_of[node], "node %d" % node
+
+
+def test_one_epoch_returns_initial_mask():
+    # num_epochs=1: the returned mask is A * sym(sigmoid(M0)) -- the last Adam step is never observed
+    fx = util.load_fixture("rand")
+    A, sfeat, gt, pl, idx, M0, _ = _inputs(fx, fx.nodes[-1])
+    S = 1 / (1 + np.exp(-M0.astype(np.float64)))
+    exp = A * (S + S.T) / 2
+    for fn in (O.explain_dense_torch, O.explain_closed_form):
+        out = fn(A, sfeat, gt, pl, idx, fx.weights, M0, hp=O.default_hparams(num_epochs=1))
+        assert np.abs(out - exp).max() < 1e-6
+
+
+def test_gradients_match_autograd():
+    # hand-derived dL/dM, dL/dF of the closed form against torch autograd on the dense port's loss
+    import torch
+    fx = util.load_fixture("rand")
+    A, sfeat, gt, pl, idx, M0, _ = _inputs(fx, 149)
+    _, st = O.explain_closed_form(A, sfeat, gt, pl, idx, fx.weights, M0, hp=O.default_hparams(num_epochs=1),
+                                  return_state=True)
+    W = O.weights_to_torch(fx.weights, requires_grad=False)
+    n = A.shape[0]
+    adj = torch.tensor(A[None], dtype=torch.double)
+    x = torch.tensor(sfeat[None], dtype=torch.double)
+    Wd = dict(conv_w=[w.double() for w in W["conv_w"]], conv_b=[b.double() for b in W["conv_b"]],
+              pred_w=W["pred_w"].double(), pred_b=W["pred_b"].double())
+    mask = torch.tensor(M0, dtype=torch.double, requires_grad=True)
+    fmask = torch.zeros(x.size(-1), dtype=torch.double, requires_grad=True)
+    sym = torch.sigmoid(mask); sym = (sym + sym.t()) / 2
+    madj = adj * sym * (torch.ones(n, n, dtype=torch.double) - torch.eye(n, dtype=torch.double))
+    yp = O._gcn_forward_torch(x * torch.sigmoid(fmask), madj, Wd, False)
+    res = torch.softmax(yp[-1, idx, :], 0)
+    m = torch.sigmoid(mask)
+    plt = torch.tensor(pl, dtype=torch.double)
+    loss = (-torch.log(res[int(gt)]) + 0.005 * m.sum() + torch.sigmoid(fmask).mean()
+            + (-m * torch.log(m) - (1 - m) * torch.log(1 - m)).mean()
+            + plt @ (torch.diag(madj[0].sum(0)) - madj[0]) @ plt / adj.numel())
+    loss.backward()
+    ei, ej = np.nonzero(A)
+    assert O.rel_l2(st["gM"][ei, ej], mask.grad.numpy()[ei, ej]) < 1e-9
+    assert O.rel_l2(st["gF"], fmask.grad.numpy()) < 1e-9

@@ -1,0 +1,47 @@
+"""Shared helpers for the tests: fixture loading and engine construction."""
+import os
+import types
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WKEYS = ["W1", "b1", "W2", "b2", "W3", "b3", "Wp", "bp"]
+
+
+def load_fixture(name):
+    """-> namespace(N, edges, feat, label, pred, weights, rowptr, col, pred_label, gold)"""
+    import gnnx_oracle as O
+    g = np.load(os.path.join(GOLDEN, name + "_graph.npz"))
+    gold = np.load(os.path.join(GOLDEN, name + "_golden.npz"))
+    N = int(g["N"])
+    rowptr, col = O.csr_from_edges(N, g["edges"])
+    return types.SimpleNamespace(
+        name=name, N=N, edges=g["edges"], feat=g["feat"], label=g["label"], pred=g["pred"],
+        weights={k: g[k] for k in WKEYS}, rowptr=rowptr, col=col,
+        pred_label=np.argmax(g["pred"], axis=1).astype(np.int32), gold=gold,
+        nodes=[int(x) for x in gold["nodes"]])
+
+
+def make_engine(fx, device=0):
+    import gnnx
+    eng = gnnx.Engine(device)
+    eng.set_model(fx.weights)
+    eng.set_graph_csr(fx.rowptr, fx.col, fx.feat, fx.label, fx.pred_label)
+    return eng
+
+
+def golden_m0(fx, plan):
+    """Concatenate the golden M0 edge entries in plan order (checks the edge counts on the way)."""
+    m0 = np.empty(plan.total_edges, np.float32)
+    for t, node in enumerate(plan.nodes):
+        g = fx.gold["n%d_m0" % node]
+        assert len(g) == plan.edge_off[t + 1] - plan.edge_off[t], "directed edge count differs from the reference"
+        m0[plan.edge_off[t]:plan.edge_off[t + 1]] = g
+    return m0
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
