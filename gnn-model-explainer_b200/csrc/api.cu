@@ -65,6 +65,8 @@ struct gx_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t side[kNumStreams] = {};
   cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool timed = false;
   cudaEvent_t ev_join[kNumStreams] = {};
   int64_t launches = 0;
 
@@ -197,6 +199,8 @@ int gx_create(int device, gx_handle** out) {
     GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
   }
   GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  GX_CUDA_CHECK(cudaEventCreate(&h->ev_t0));
+  GX_CUDA_CHECK(cudaEventCreate(&h->ev_t1));
   *out = h;
   return GX_OK;
 }
@@ -215,6 +219,8 @@ int gx_destroy(gx_handle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   delete h;
   return GX_OK;
 }
@@ -233,6 +239,15 @@ int gx_sync(gx_handle* h) {
 }
 
 int64_t gx_launch_count(gx_handle* h) { return h ? h->launches : 0; }
+
+int gx_last_explain_ms(gx_handle* h, float* ms) {
+  if (!h || !ms) { gx_set_error("gx_last_explain_ms: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->timed) { gx_set_error("gx_last_explain_ms: no gx_explain_nodes call yet"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  GX_CUDA_CHECK(cudaEventSynchronize(h->ev_t1));
+  GX_CUDA_CHECK(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return GX_OK;
+}
 
 int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* conv_w,
                  const float* const* conv_b, const float* pred_w, const float* pred_b) {
@@ -511,6 +526,7 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
     last_grid = std::min<int>((int)last.size(), h->num_sms);
     GX_CUDA_CHECK(h->d_gws.reserve((size_t)last_grid * h->gws_stride_words * 4));
   }
+  GX_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->stream));
   GX_CUDA_CHECK(cudaEventRecord(h->ev_fork, h->stream));
   int off = 0;
   std::vector<int> used;
@@ -544,6 +560,8 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
     used.push_back(c);
   }
   for (int c : used) GX_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_join[c], 0));
+  GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
+  h->timed = true;
   if (space == GX_HOST) {
     GX_CUDA_CHECK(cudaMemcpyAsync(edge_mask, out_dev, (size_t)te * 4, cudaMemcpyDeviceToHost, h->stream));
     if (feat_mask) GX_CUDA_CHECK(cudaMemcpyAsync(feat_mask, feat_dev, (size_t)count * h->m.d * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -14,7 +14,7 @@ GX_MODEL_BN = 1
 EXPORTS = [
     "gx_default_hparams", "gx_last_error", "gx_version", "gx_create", "gx_destroy", "gx_set_stream",
     "gx_sync", "gx_set_model", "gx_set_graph_csr", "gx_neighborhood_rows", "gx_plan_nodes",
-    "gx_plan_fetch", "gx_explain_nodes", "gx_densify", "gx_launch_count",
+    "gx_plan_fetch", "gx_explain_nodes", "gx_densify", "gx_launch_count", "gx_last_explain_ms",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.gx_densify.argtypes = [vp, C.c_int, f32p, vp]
     L.gx_launch_count.argtypes = [vp]
     L.gx_launch_count.restype = C.c_int64
+    L.gx_last_explain_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here means the library does not match include/gnnx.h
     _lib = L

@@ -178,3 +178,8 @@ class Engine:
 
     def launch_count(self):
         return int(self._lib.gx_launch_count(self._h))
+
+    def last_explain_ms(self):
+        ms = C.c_float()
+        _abi.check(self._lib.gx_last_explain_ms(self._h, C.byref(ms)))
+        return float(ms.value)

@@ -137,8 +137,10 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
  * (explain.py:209-221), task after task, into out (sum_t n_t^2 doubles, `space`). */
 int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* out);
 
-/* Counters for bench.py: number of kernels this handle has launched so far. */
+/* Counters for bench.py: number of kernels this handle has launched so far, and the device time
+ * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);
+int gx_last_explain_ms(gx_handle* h, float* ms);
 
 #ifdef __cplusplus
 }
