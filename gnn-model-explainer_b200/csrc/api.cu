@@ -430,7 +430,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   GX_CUDA_CHECK(h->d_srp.reserve((size_t)(tn + count) * 4));
   GX_CUDA_CHECK(h->d_irp.reserve((size_t)(tn + count) * 4));
   GX_CUDA_CHECK(h->d_scol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
-  GX_CUDA_CHECK(h->d_icol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+  GX_CUDA_CHECK(h->d_icol.reserve((size_t)std::max<int64_t>(te, 1) * 4 * 3));
   GX_CUDA_CHECK(h->d_pairs.reserve((size_t)std::max<int64_t>(tp, 1) * 4 * 6));
   h->plan.tasks = h->d_tasks.as<GxTask>();
   h->plan.nbrs = h->d_nbrs.as<int32_t>();
@@ -439,6 +439,8 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   h->plan.irowptr = h->d_irp.as<int32_t>();
   h->plan.sub_col = h->d_scol.as<int32_t>();
   h->plan.icol = h->d_icol.as<int32_t>();
+  h->plan.cs2is = h->plan.icol + te;
+  h->plan.is2cs = h->plan.icol + 2 * te;
   int32_t* pb = h->d_pairs.as<int32_t>();
   h->plan.pair_i = pb; h->plan.pair_j = pb + tp; h->plan.pair_pij = pb + 2 * tp;
   h->plan.pair_pji = pb + 3 * tp; h->plan.pair_oij = pb + 4 * tp; h->plan.pair_oji = pb + 5 * tp;

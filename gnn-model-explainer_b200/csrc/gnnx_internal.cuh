@@ -37,7 +37,9 @@ struct GxPlanArrays {
   int32_t* sub_rowptr;  // [total_n + count] canonical CSR, task-local
   int32_t* sub_col;     // [total_e]
   int32_t* irowptr;     // [total_n + count] level-order CSR, task-local
-  int32_t* icol;        // [total_e] level-order ids, ascending per row
+  int32_t* icol;        // [total_e] level-order ids; per row partitioned by level of the neighbour
+  int32_t* cs2is;       // [total_e] canonical slot -> internal slot (task-local)
+  int32_t* is2cs;       // [total_e] internal slot -> canonical slot
   int32_t* pair_i;      // [total_e/2] i < j, level-order ids
   int32_t* pair_j;
   int32_t* pair_pij;    // position of j in internal row i (absolute, task-local)
@@ -83,46 +85,48 @@ __host__ __device__ inline int gx_round_up(int x, int m) { return (x + m - 1) / 
 
 struct GxLayout {
   // float arrays (offsets in 4-byte words)
-  int X, U, Yh1, q1, Yh2, q2, dZ2, dZ1s, a, M, lap2, W1s, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
+  int X, U, Yh1, q1, Yh2, q2, dZ2, T, a, M, lap2, W1s, W2s, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
   // index arrays (offsets in 4-byte words; element type IdxT)
-  int icol, irp, pi, pj, ppij, ppji;
+  int icol, irp, pi, pj, ppij, ppji, llist;
   int total_words;
-  int dp, hs;
+  int dp, ts;
 };
 
-// idx_bytes = sizeof(IdxT) (2 or 4)
+// idx_bytes = sizeof(IdxT) (2 or 4).  hid/emb must be multiples of 4.
 __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1, int np, int d,
                                                    int hid, int emb, int C, int nwarps,
                                                    int idx_bytes) {
   GxLayout L;
-  const int dp = gx_round_up(d, 4), hs = gx_round_up(hid, 4), es = gx_round_up(emb, 4);
+  const int dp = gx_round_up(d, 4);
+  const int ts = dp > hid ? dp : hid;
   L.dp = dp;
-  L.hs = hs;
+  L.ts = ts;
   int o = 0;
   auto takef = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
   auto takei = [&](int elems) { int r = o; o += gx_round_up((elems * idx_bytes + 3) / 4, 4); return r; };
   L.X = takef(n * dp);
   L.U = takef(n2 * dp);
-  L.Yh1 = takef(n2 * hs);
+  L.Yh1 = takef(n2 * hid);
   L.q1 = takef(n2);
-  L.Yh2 = takef(n1 * hs);
+  L.Yh2 = takef(n1 * hid);
   L.q2 = takef(n1);
-  L.dZ2 = takef(n1 * hs);
-  L.dZ1s = takef(n2 * dp);
+  L.dZ2 = takef(n1 * hid);
+  L.T = takef(n2 * ts);
   L.a = takef(e1);
-  L.M = takef(6 * np);  // M_ij, M_ji, m_ij, m_ji, v_ij, v_ji  (SoA, np each)
+  L.M = takef(8 * np);  // (M_ij,M_ji), (m_ij,m_ji), (v_ij,v_ji), (S_ij,S_ji) as float2 arrays
   L.lap2 = takef(np);
-  L.W1s = takef(d * hs);
+  L.W1s = takef(dp * hid);
+  L.W2s = takef(hid * hid);
+  L.W3s = takef(hid * emb);
+  L.bs = takef(2 * hid + emb);
   L.sF = takef(dp);
   L.F = takef(dp);
   L.mF = takef(dp);
   L.vF = takef(dp);
   L.gFp = takef(nwarps * dp);
-  int zw = dp > hs ? dp : hs;
-  zw = zw > es ? zw : es;
-  L.zs = takef(nwarps * zw);
-  L.dE = takef(2 * hs);
-  L.dZ3 = takef(hs);
+  L.zs = takef(nwarps * 128);
+  L.dE = takef(2 * hid);
+  L.dZ3 = takef(hid);
   L.logit = takef(C < 32 ? 32 : C);
   L.icol = takei(e1);
   L.irp = takei(n2 + 1);
@@ -130,6 +134,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.pj = takei(np);
   L.ppij = takei(np);
   L.ppji = takei(np);
+  L.llist = takei(n2);
   L.total_words = o;
   return L;
 }

@@ -15,6 +15,7 @@
 namespace {
 
 constexpr int KH_THREADS = 256;
+constexpr int GX_RANK_SORT_MAX = 4096;  // O(n^2) rank sort of (level, degree) keys up to this many nodes
 
 struct Slot {
   uint32_t* bm;
@@ -237,30 +238,7 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
       return sl.wpref[v >> 5] + __popc(__ldcg(sl.bm + (v >> 5)) & ((1u << (v & 31)) - 1u));
     };
     if (tid == 0) T->idx_new = canon(root);  // == sum(row[:node_idx]) (explain.py:496)
-    // (3) level order: stable partition of the canonical order by distance from the node
-    int base_lo = 0;
-    for (int lv = 0; lv <= k; ++lv) {
-      for (int c = tid; c < n; c += blockDim.x) {
-        const int v = nbrs[c];
-        const int dv = (v == root) ? 0 : (int)sl.dist[v];
-        sl.pbase[c] = (dv == lv) ? 1 : 0;
-      }
-      __syncthreads();
-      const int tot = block_excl_scan(sl.pbase, n, s_w);
-      for (int c = tid; c < n; c += blockDim.x) {
-        const int v = nbrs[c];
-        const int dv = (v == root) ? 0 : (int)sl.dist[v];
-        if (dv == lv) {
-          const int lo = base_lo + sl.pbase[c];
-          sl.loc[c] = lo;
-          sl.cof[lo] = c;
-          lo2gid[lo] = v;
-        }
-      }
-      base_lo += tot;
-      __syncthreads();
-    }
-    // (4) induced degrees -> canonical and level-order row pointers
+    // (3) induced degrees of the canonical rows
     for (int c = warp; c < n; c += nwarps) {
       const int u = nbrs[c];
       int cnt = 0;
@@ -273,6 +251,54 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
       if (lane == 0) srp[c] = cnt;
     }
     __syncthreads();
+    // (4) level order: (distance from the node asc, induced degree desc, id asc).  Every layer's row
+    //     set is a prefix, and inside a level rows of similar degree are adjacent (the explainer kernel
+    //     processes rows in lane groups: similar degrees => little divergence, hubs first).
+    if (n <= GX_RANK_SORT_MAX) {
+      for (int c = tid; c < n; c += blockDim.x) {
+        const int v = nbrs[c];
+        const int dv = (v == root) ? 0 : (int)sl.dist[v];
+        sl.pbase[c] = (dv << 24) | (0xFFFFFF - min(srp[c], 0xFFFFFF));
+      }
+      __syncthreads();
+      for (int c = tid; c < n; c += blockDim.x) {
+        const int key = sl.pbase[c];
+        int rank = 0;
+        for (int o = 0; o < n; ++o) {
+          const int ko = sl.pbase[o];
+          rank += (ko < key || (ko == key && o < c)) ? 1 : 0;
+        }
+        sl.loc[c] = rank;
+        sl.cof[rank] = c;
+        lo2gid[rank] = nbrs[c];
+      }
+      __syncthreads();
+    } else {
+      // large neighbourhoods: stable partition by level only (scan based, O(n) per level)
+      int base_lo = 0;
+      for (int lv = 0; lv <= k; ++lv) {
+        for (int c = tid; c < n; c += blockDim.x) {
+          const int v = nbrs[c];
+          const int dv = (v == root) ? 0 : (int)sl.dist[v];
+          sl.pbase[c] = (dv == lv) ? 1 : 0;
+        }
+        __syncthreads();
+        const int tot = block_excl_scan(sl.pbase, n, s_w);
+        for (int c = tid; c < n; c += blockDim.x) {
+          const int v = nbrs[c];
+          const int dv = (v == root) ? 0 : (int)sl.dist[v];
+          if (dv == lv) {
+            const int lo = base_lo + sl.pbase[c];
+            sl.loc[c] = lo;
+            sl.cof[lo] = c;
+            lo2gid[lo] = v;
+          }
+        }
+        base_lo += tot;
+        __syncthreads();
+      }
+    }
+    // canonical and level-order row pointers
     const int e_tot = block_excl_scan(srp, n, s_w);
     if (tid == 0) srp[n] = e_tot;
     __syncthreads();
@@ -302,7 +328,11 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
       }
     }
     __syncthreads();
-    // (6) level-order columns: stable partition of each canonical row by level => ascending lo ids
+    // (6) level-order rows: each canonical row partitioned by the level of the neighbour (columns within
+    //     one hop of the explained node first: the backward only needs that prefix); the two slot maps
+    //     canonical <-> internal are kept for the pair construction
+    int32_t* cs2is = P.cs2is + T->edge_off;
+    int32_t* is2cs = P.is2cs + T->edge_off;
     for (int i = warp; i < n; i += nwarps) {
       const int c = sl.cof[i];
       const int r0 = srp[c], r1 = srp[c + 1];
@@ -316,33 +346,50 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
           if (e < r1) lo = sl.loc[scol[e]];
           const bool keep = lo >= lo_b && lo < lo_e;
           const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) icol[out + __popc(bal & lt_mask)] = lo;
+          if (keep) {
+            const int o = out + __popc(bal & lt_mask);
+            icol[o] = lo;
+            cs2is[e] = o;
+            is2cs[o] = e;
+          }
           out += __popc(bal);
         }
       }
     }
     __syncthreads();
-    // (7) undirected pairs (i < j) with both directed slots, internal and canonical
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int r0 = irp[i], r1 = irp[i + 1];
-      sl.pbase[i] = r1 - lower_bound_i(icol, r0, r1, i + 1);
+    // (7) undirected pairs, owned by the endpoint with the smaller level-order id, in (i, slot) order:
+    //     pairs touching the explained node / its neighbours come first, pairs between two
+    //     outermost nodes last (uniform work per warp in the explainer's edge phase)
+    for (int i = warp; i < n; i += nwarps) {
+      int cnt = 0;
+      for (int kk = irp[i] + lane; kk < irp[i + 1]; kk += 32) cnt += icol[kk] > i ? 1 : 0;
+      cnt = warp_sum_i(cnt);
+      if (lane == 0) sl.pbase[i] = cnt;
     }
     __syncthreads();
     block_excl_scan(sl.pbase, n, s_w);
     for (int i = warp; i < n; i += nwarps) {
       const int r0 = irp[i], r1 = irp[i + 1];
-      const int ub = lower_bound_i(icol, r0, r1, i + 1);
       const int ci = sl.cof[i];
-      for (int kk = ub + lane; kk < r1; kk += 32) {
-        const int j = icol[kk];
-        const int cj = sl.cof[j];
-        const int64_t p = T->pair_off + sl.pbase[i] + (kk - ub);
-        P.pair_i[p] = i;
-        P.pair_j[p] = j;
-        P.pair_pij[p] = kk;
-        P.pair_pji[p] = lower_bound_i(icol, irp[j], irp[j + 1], i);
-        P.pair_oij[p] = lower_bound_i(scol, srp[ci], srp[ci + 1], cj);
-        P.pair_oji[p] = lower_bound_i(scol, srp[cj], srp[cj + 1], ci);
+      int64_t out = T->pair_off + sl.pbase[i];
+      for (int kb = r0; kb < r1; kb += 32) {
+        const int kk = kb + lane;
+        int j = -1;
+        if (kk < r1) j = icol[kk];
+        const bool keep = j > i;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int64_t p = out + __popc(bal & lt_mask);
+          const int cj = sl.cof[j];
+          const int oji = lower_bound_i(scol, srp[cj], srp[cj + 1], ci);
+          P.pair_i[p] = i;
+          P.pair_j[p] = j;
+          P.pair_pij[p] = kk;
+          P.pair_pji[p] = cs2is[oji];
+          P.pair_oij[p] = is2cs[kk];
+          P.pair_oji[p] = oji;
+        }
+        out += __popc(bal);
       }
     }
     __syncthreads();

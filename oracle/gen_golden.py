@@ -183,10 +183,55 @@ def gen_rand(R):
     np.savez_compressed(os.path.join(OUT, "rand_golden.npz"), nodes=np.asarray(nodes, np.int64), **gold)
 
 
+def gen_short_horizon(R, which, epochs):
+    """Same graph / weights / seeds as <which>_golden.npz, but the reference runs only `epochs` mask-
+    optimisation epochs.  Some 100-epoch trajectories are chaotic (DESIGN.md 'Parity'): a short horizon
+    pins the arithmetic of EVERY node before rounding differences are amplified."""
+    g = np.load(os.path.join(OUT, which + "_graph.npz"))
+    gold = np.load(os.path.join(OUT, which + "_golden.npz"))
+    N = int(g["N"])
+    adj = np.zeros((1, N, N))
+    adj[0, g["edges"][:, 0], g["edges"][:, 1]] = 1
+    adj[0, g["edges"][:, 1], g["edges"][:, 0]] = 1
+    C = g["Wp"].shape[0]
+    targs = train_args(dataset=which)
+    model = R.models.GcnEncoderNode(g["feat"].shape[1], 20, 20, C, 3, bn=False, args=targs)
+    sd = {"conv_first.weight": g["W1"], "conv_first.bias": g["b1"], "conv_block.0.weight": g["W2"],
+          "conv_block.0.bias": g["b2"], "conv_last.weight": g["W3"], "conv_last.bias": g["b3"],
+          "pred_model.weight": g["Wp"], "pred_model.bias": g["bp"]}
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    model.eval()
+    eargs = ref_harness.explainer_args(dataset=which, num_epochs=epochs)
+    with ref_harness.quiet():
+        ex = R.explain.Explainer(model=model, adj=adj, feat=g["feat"][None].astype(np.float64), label=g["label"][None],
+                                 pred=g["pred"][None], train_idx=list(range(N)), args=eargs,
+                                 writer=None, print_training=False, graph_idx=-1)
+    out = {}
+    for node in gold["nodes"]:
+        node = int(node)
+        torch.manual_seed(int(gold["n%d_seed" % node]))
+        with ref_harness.quiet():
+            masked = np.asarray(ex.explain(node, graph_idx=0))
+            _, sub_adj, _, _, nbrs = ex.extract_neighborhood(node, 0)
+        assert np.array_equal(nbrs, gold["n%d_nbrs" % node])
+        ei, ej = np.nonzero(sub_adj)
+        out["n%d_mask" % node] = masked[ei, ej].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "%s_golden_e%d.npz" % (which, epochs)), nodes=gold["nodes"],
+                        num_epochs=np.int64(epochs), **out)
+    print("  %s: %d nodes at %d epochs" % (which, len(gold["nodes"]), epochs))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
+    ap.add_argument("--short", type=int, default=0, help="also/only generate the short-horizon golden (epochs)")
     a = ap.parse_args()
+    if a.short:
+        torch.set_num_threads(8)
+        R = ref_harness.load()
+        for which in (["syn1", "syn4", "rand"] if a.only is None else [a.only]):
+            gen_short_horizon(R, which, a.short)
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     R = ref_harness.load()

@@ -78,21 +78,42 @@ def test_khop_edge_cases():
 
 
 # ------------------------------------------------------------------------------------ masks vs the reference
-def test_masks_match_reference_golden(fx):
+def _run_golden(fx, num_epochs):
     eng = util.make_engine(fx)
     plan = eng.plan_nodes(fx.nodes, 3)
     out = np.zeros(plan.total_edges, np.float32)
-    eng.explain_nodes_host(eng.make_hparams(), util.golden_m0(fx, plan), out)
-    tol = tolerances(fx.name)
-    errs = {}
-    for t, node in enumerate(fx.nodes):
-        errs[node] = util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], fx.gold["n%d_mask" % node])
-    bad = {n: (e, tol[n]) for n, e in errs.items() if not e <= tol[n]}
-    assert not bad, bad
-    strict = [e for n, e in errs.items() if tol[n] == 1e-4]
-    assert len(strict) >= 0.9 * len(errs)          # the 1e-4 bar applies to (at least) 90% of the nodes
-    assert np.median(list(errs.values())) < 1e-5
+    eng.explain_nodes_host(eng.make_hparams(num_epochs=num_epochs), util.golden_m0(fx, plan), out)
     eng.close()
+    return plan, out
+
+
+def test_masks_match_reference_golden_30_epochs(fx):
+    """Short horizon (30 epochs, golden from the unmodified reference): EVERY node within 1e-4.
+    At 30 epochs no trajectory has had time to amplify rounding differences (DESIGN.md 'Parity')."""
+    g30 = np.load(util.GOLDEN + "/%s_golden_e30.npz" % fx.name)
+    plan, out = _run_golden(fx, int(g30["num_epochs"]))
+    errs = {node: util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], g30["n%d_mask" % node])
+            for t, node in enumerate(fx.nodes)}
+    bad = {n: e for n, e in errs.items() if not e <= 1e-4}
+    assert not bad, bad
+    assert np.median(list(errs.values())) < 2e-6
+
+
+def test_masks_match_reference_golden_100_epochs(fx):
+    """Full horizon (the reference default, 100 epochs).  A few syn1 trajectories are chaotic: a relu
+    kink crossed one epoch earlier or later under a different fp summation order moves the final mask
+    by 1e-3..1e-1 (the reference's own result is not reproducible there: tests/golden/*_cond.npz shows
+    two CPU restatements of the same mathematics landing up to 6.6e-2 apart).  Bar: >= 90% of the nodes
+    within the north-star 1e-4, median < 1e-5, every node bounded."""
+    plan, out = _run_golden(fx, 100)
+    errs = {node: util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], fx.gold["n%d_mask" % node])
+            for t, node in enumerate(fx.nodes)}
+    vals = np.array(list(errs.values()))
+    assert (vals <= 1e-4).mean() >= 0.9, sorted(errs.items(), key=lambda kv: -kv[1])[:10]
+    assert np.median(vals) < 1e-5
+    assert vals.max() < 0.2, max(errs.items(), key=lambda kv: kv[1])
+    if fx.name != "syn1":
+        assert vals.max() <= 1e-4          # syn4 / rand: no chaotic node
 
 
 def _random_case(seed, n_nodes, m, d, C, graph="ba"):
@@ -260,8 +281,8 @@ def test_explainer_dropin_reproduces_reference_under_torch_seed(syn1, tmp_path):
     """Explainer.explain with the reference's call sequence: torch.manual_seed(s) then explain(node).
     The M0 draw consumes torch's CPU RNG exactly like ExplainModule.construct_edge_mask, so the
     same seed reproduces the reference's mask."""
-    ex, args = _explainer(syn1, tmp_path)
-    tol = tolerances("syn1")
+    g30 = np.load(util.GOLDEN + "/syn1_golden_e30.npz")
+    ex, args = _explainer(syn1, tmp_path, num_epochs=30)
     for node in [300, 450, 683, 13]:
         torch.manual_seed(int(syn1.gold["n%d_seed" % node]))
         masked = ex.explain(node, graph_idx=0)
@@ -270,7 +291,7 @@ def test_explainer_dropin_reproduces_reference_under_torch_seed(syn1, tmp_path):
         idx_new, sub_adj, sub_feat, sub_label, nbrs = ex.extract_neighborhood(node)
         assert np.array_equal(nbrs, syn1.gold["n%d_nbrs" % node]) and idx_new == int(syn1.gold["n%d_idx_new" % node])
         ei, ej = np.nonzero(sub_adj)
-        assert util.rel_l2(masked[ei, ej], syn1.gold["n%d_mask" % node]) <= tol[node]
+        assert util.rel_l2(masked[ei, ej], g30["n%d_mask" % node]) <= 1e-4
         off = masked.copy(); off[ei, ej] = 0
         assert np.all(off == 0)
         f = os.path.join(str(tmp_path), "masked_adj_syn1_base_h20_o20_explainnode_idx_%dgraph_idx_-1.npy" % node)
