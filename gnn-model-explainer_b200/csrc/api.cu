@@ -67,6 +67,7 @@ struct gx_handle {
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   bool timed = false;
+  float* dbg = nullptr;
   cudaEvent_t ev_join[kNumStreams] = {};
   int64_t launches = 0;
 
@@ -239,6 +240,9 @@ int gx_sync(gx_handle* h) {
 }
 
 int64_t gx_launch_count(gx_handle* h) { return h ? h->launches : 0; }
+
+/* debug only (not in gnnx.h): device buffer receiving the shared-memory slab of the first task of each class */
+int gx_debug_set_dump(gx_handle* h, float* dev_buf) { if (!h) return GX_ERR_INVALID; h->dbg = dev_buf; return GX_OK; }
 
 int gx_last_explain_ms(gx_handle* h, float* ms) {
   if (!h || !ms) { gx_set_error("gx_last_explain_ms: NULL argument"); return GX_ERR_INVALID; }
@@ -547,6 +551,7 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
     cfg.idx16 = h->class_idx16[c];
     cfg.gws = h->d_gws.as<float>();
     cfg.gws_stride_words = h->gws_stride_words;
+    cfg.dbg = h->dbg;
     if (c == kNumClasses - 1) cfg.grid = last_grid;
     else {
       // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)

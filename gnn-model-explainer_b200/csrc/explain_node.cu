@@ -19,12 +19,14 @@
 //   * The returned mask is the one built in the forward of the LAST epoch (explain.py:694,209),
 //     i.e. after num_epochs-1 updates; the last backward/Adam step is unobservable and skipped.
 //
-// Work mapping (v2, driven by the ncu profile of v1 in profiles/r01a_v1_kernel_summary.md):
-//   * sparse aggregations: a warp is cut into groups of W/4 lanes; each group owns ONE row and
-//     walks its edges with float4 shared-memory loads (rows of similar degree are adjacent thanks
-//     to the plan's ordering); rows longer than kLongRow edges are split across the whole warp.
-//   * dense 20x20 / dx20 products, row normalisation and their backward: ONE THREAD PER ROW,
-//     accumulators in registers, weight rows broadcast from shared memory as float4.
+// Work mapping (v3; v1 was issue bound with lane=feature rows, v2's one-thread-per-row dense left most
+// warps waiting at barriers -- profiles/r01a_*, r01b_*):
+//   * a warp is cut into groups of GW = max(d,20)/4 lanes; a group owns ONE row from start to finish:
+//     it walks the row's edges with float4 shared-memory loads (lane q holds features 4q..4q+3),
+//     exchanges the aggregate through a per-warp scratch row, and each lane then produces one float4
+//     of the dense product (weights as float4 from shared memory), the row norm being a GW-lane
+//     shuffle sum.  Rows are dealt cyclically over the warps in chunks of 32/GW, so every phase keeps
+//     all warps busy; rows with more than kLongRow edges are split across a whole warp first.
 //   * edge phase: one thread per undirected edge (both directions), sigmoid cached between epochs.
 // Phases per epoch (one __syncthreads each): F1 | F2 | S (row r: layer 3 + readout + softmax +
 // layer-3 backward, one warp) | B2 | B1 | P.
@@ -111,67 +113,84 @@ struct ExplainArgs {
   const float* m0;
   float* out_mask;
   float* out_feat;
+  float* dbg;  // optional debug dump of the shared-memory arrays of task 0 after the backward of epoch 1
 };
 
 // ---------------------------------------------------------------------------------------------
-// Sparse aggregation  dst[i] = sum_{e in row i (, col < col_limit)} a[e] * f(src[col[e]])  for the rows
-// [row_b, row_e) of a warp's block.  W4 = row width in float4 (<= 32), lanes are cut into groups of W4.
-//   kRelu   : f = relu
-//   mode    : 0 = only rows with <= kLongRow edges (row per lane group)
-//             1 = only rows with  > kLongRow edges, rows dealt across warps (edges across groups)
+// Lane-group primitives.  A warp = epi groups of GW lanes; lane = grp*GW + q.
 // ---------------------------------------------------------------------------------------------
-template <typename IdxT, bool kRelu>
-__device__ __forceinline__ void gather_short_rows(int row_b, int row_e, int W4, int lane,
-                                                  const IdxT* __restrict__ irp, const IdxT* __restrict__ icol,
-                                                  const float* a, const float* src, int src_stride,
-                                                  float* dst, int dst_stride, int col_limit) {
-  const int grp = lane / W4, q = lane - grp * W4;
-  const int epi = 32 / W4;
-  if (grp >= epi) return;
-  for (int i = row_b + grp; i < row_e; i += epi) {
-    const int r0 = irp[i], r1 = irp[i + 1];
-    if (r1 - r0 > kLongRow) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = r0; e < r1; ++e) {
-      const int c = icol[e];
-      if (c >= col_limit) break;
-      float4 v = ld4(src + c * src_stride + 4 * q);
-      if (kRelu) v = relu4(v);
-      fma4(acc, a[e], v);
-    }
-    st4(dst + i * dst_stride + 4 * q, acc);
-  }
+struct Grp {
+  int GW, epi, grp, q, gbase, lane;
+};
+
+// sum of v over the GW lanes of the caller's group (every lane of the warp must call this)
+__device__ __forceinline__ float group_sum(float v, const Grp& G) {
+  float s = 0.f;
+  for (int k = 0; k < G.GW; ++k) s += __shfl_sync(0xffffffffu, v, min(G.gbase + k, 31));
+  return s;
 }
 
+// out4 = init + sum_{f < 4*F4} z[f] * W[f][4q .. 4q+3]   (z: F4 float4 in the group's scratch row)
+__device__ __forceinline__ float4 group_dense(const float* zrow, int F4, const float* W, int ldw, int q, float4 acc) {
+  for (int f4 = 0; f4 < F4; ++f4) {
+    const float4 z = ld4(zrow + 4 * f4);
+    const float* w = W + (4 * f4) * ldw + 4 * q;
+    fma4(acc, z.x, ld4(w));
+    fma4(acc, z.y, ld4(w + ldw));
+    fma4(acc, z.z, ld4(w + 2 * ldw));
+    fma4(acc, z.w, ld4(w + 3 * ldw));
+  }
+  return acc;
+}
+
+// this lane's float4 slice of  sum_{e in row i, col < col_limit} a[e] * f(src[col[e]])
 template <typename IdxT, bool kRelu>
-__device__ __forceinline__ void gather_long_row(int i, int W4, int lane, const IdxT* __restrict__ irp,
-                                                const IdxT* __restrict__ icol, const float* a,
-                                                const float* src, int src_stride, float* dst, int dst_stride,
-                                                int col_limit, float* scratch /* >= 128 floats per warp */) {
-  const int grp = lane / W4, q = lane - grp * W4;
-  const int epi = 32 / W4;
-  const int r0 = irp[i], r1 = irp[i + 1];
+__device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const IdxT* icol, const float* a,
+                                             const float* src, int src_stride, int q, int col_limit) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (grp < epi) {
-    for (int e = r0 + grp; e < r1; e += epi) {
-      const int c = icol[e];
-      if (c >= col_limit) break;  // columns are partitioned by level: once past the limit, all later ones are too
-      float4 v = ld4(src + c * src_stride + 4 * q);
-      if (kRelu) v = relu4(v);
-      fma4(acc, a[e], v);
-    }
-    st4(scratch + lane * 4, acc);
+  for (int e = r0; e < r1; e += estep) {
+    const int c = icol[e];
+    if (c >= col_limit) break;  // columns are partitioned by level: past the limit, all later ones are too
+    float4 v = ld4(src + c * src_stride + 4 * q);
+    if (kRelu) v = relu4(v);
+    fma4(acc, a[e], v);
   }
-  __syncwarp();
-  if (grp == 0) {
-    float4 t = acc;
-    for (int g2 = 1; g2 < epi; ++g2) {
-      const float4 o = ld4(scratch + (g2 * W4 + q) * 4);
-      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+  return acc;
+}
+
+// A "row task" of a phase: either one long row taken by the whole warp (edges split across the groups,
+// partial sums reduced into group 0 through the scratch) or a chunk of epi short rows, one per group.
+// Returns the row id (or -1) and this lane's float4 of the aggregate; W4 = source width in float4.
+template <typename IdxT, bool kRelu>
+__device__ __forceinline__ int row_task_gather(int t, int nlong, const IdxT* llist, int R, const Grp& G, int W4,
+                                               const IdxT* irp, const IdxT* icol, const float* a,
+                                               const float* src, int src_stride, int col_limit, float* zs,
+                                               float4& z) {
+  z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < nlong) {
+    const int i = llist[t];
+    const int r0 = irp[i], r1 = irp[i + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (G.grp < G.epi && G.q < W4)
+      acc = gather_row<IdxT, kRelu>(r0 + G.grp, r1, G.epi, icol, a, src, src_stride, G.q, col_limit);
+    st4(zs + G.lane * 4, acc);
+    __syncwarp();
+    if (G.grp == 0 && G.q < W4) {
+      z = acc;
+      for (int g2 = 1; g2 < G.epi; ++g2) {
+        const float4 o = ld4(zs + (g2 * G.GW + G.q) * 4);
+        z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w;
+      }
     }
-    st4(dst + i * dst_stride + 4 * q, t);
+    __syncwarp();
+    return G.grp == 0 ? i : -1;
   }
-  __syncwarp();
+  const int i = (t - nlong) * G.epi + G.grp;
+  if (G.grp >= G.epi || i >= R) return -1;
+  const int r0 = irp[i], r1 = irp[i + 1];
+  if (nlong > 0 && r1 - r0 > kLongRow) return -1;  // taken by a whole warp above
+  if (G.q < W4) z = gather_row<IdxT, kRelu>(r0, r1, 1, icol, a, src, src_stride, G.q, col_limit);
+  return i;
 }
 
 template <bool kShared, typename IdxT, int HID, int EMB, int NT>
@@ -205,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     const int64_t node_off = Tp->node_off, rp_off = Tp->rp_off, edge_off = Tp->edge_off, pair_off = Tp->pair_off;
     if (tid == 0) sL = gx_make_layout(n, n1, n2, e1, np, d, HID, EMB, C, nwarps, (int)sizeof(IdxT));
     __syncthreads();
-    const int dp = sL.dp, D4 = dp / 4, TS = sL.ts;
+    const int dp = sL.dp, D4 = dp / 4;
     const int32_t* __restrict__ lo2gid = A.plan.lo2gid + node_off;
     const float nn = (float)n * (float)n;
     const float ent_over_nn = hp.c_ent / nn;
@@ -229,6 +248,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       W1s[idx] = f < d ? __ldg(m.W[0] + f * HID + c) : 0.f;
     }
     for (int idx = tid; idx < HID * HS; idx += nthreads) W2s[idx] = __ldg(m.W[1] + idx);
+    {
+      float* const W1t = base + sL.W1t; float* const W2t = base + sL.W2t;
+      for (int idx = tid; idx < HID * dp; idx += nthreads) {   // W1t[c][f] = W1[f][c], zero for f >= d
+        const int c = idx / dp, f = idx - c * dp;
+        W1t[idx] = f < d ? __ldg(m.Wt[0] + c * d + f) : 0.f;
+      }
+      for (int idx = tid; idx < HID * HID; idx += nthreads) W2t[idx] = __ldg(m.Wt[1] + idx);
+    }
     for (int idx = tid; idx < HID * EMB; idx += nthreads) W3s[idx] = __ldg(m.W[2] + idx);
     for (int idx = tid; idx < HID; idx += nthreads) { bs[idx] = __ldg(m.b[0] + idx); bs[HID + idx] = __ldg(m.b[1] + idx); }
     for (int idx = tid; idx < EMB; idx += nthreads) bs[2 * HID + idx] = __ldg(m.b[2] + idx);
@@ -293,139 +320,90 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     const int nlongF1 = s_long[0];  // long rows among [0,n2)
     const int nlongF2 = s_long[1];  // long rows among [0,n1) (a prefix of the list)
 
+    // lane groups: GW lanes per row
+    Grp G;
+    {
+      int gw = D4 > H4 ? D4 : H4;
+      gw = gw > (EMB / 4) ? gw : (EMB / 4);
+      G.GW = gw; G.epi = 32 / gw; G.lane = lane; G.grp = lane / gw; G.q = lane - G.grp * gw; G.gbase = G.grp * gw;
+    }
+    const int epi = G.epi, q = G.q;
+
     // ------------------------------------------------------------------ epochs
     for (int it = 1; it <= hp.iters; ++it) {
-      // ---- F1: rows [0,n2): U = A_m X ; Y1 = (U . sF) W1 + b1 ; normalise           (models.py:70-78)
+      // ---- F1: rows [0,n2): U = A_m X ; Y1 = (U . sF) W1 + b1 ; row normalise            (models.py:70-78)
       {
-      const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
-      const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
-      float* const a = base + sL.a;
-      float* const X = base + sL.X;
-      float* const U = base + sL.U;
-      float* const zs = base + sL.zs + warp * 128;
-      float* const bs = base + sL.bs;
-      float* const sF = base + sL.sF;
-      float* const W1s = base + sL.W1s;
-      float* const Yh1 = base + sL.Yh1;
-      float* const q1 = base + sL.q1;
-      const IdxT* const llist = reinterpret_cast<const IdxT*>(base + sL.llist);
-      if (nlongF1 > 0) {
-        for (int k = warp; k < nlongF1; k += nwarps)
-          gather_long_row<IdxT, false>((int)llist[k], D4, lane, irp, icol, a, X, dp, U, dp, n, zs);
-        __syncthreads();
-      }
-      for (int rb = warp * 32; rb < n2; rb += nwarps * 32) {
-        const int re = min(rb + 32, n2);
-        gather_short_rows<IdxT, false>(rb, re, D4, lane, irp, icol, a, X, dp, U, dp, n);
-        __syncwarp();
-        const int i = rb + lane;
-        if (i < re) {
-          float acc[HID];
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4) {
-            const float4 b = ld4(bs + 4 * c4);
-            acc[4 * c4] = b.x; acc[4 * c4 + 1] = b.y; acc[4 * c4 + 2] = b.z; acc[4 * c4 + 3] = b.w;
+        const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
+        const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
+        const IdxT* const llist = reinterpret_cast<const IdxT*>(base + sL.llist);
+        const float* const a = base + sL.a; const float* const X = base + sL.X; float* const U = base + sL.U;
+        float* const zs = base + sL.zs + warp * 128; const float* const bs = base + sL.bs;
+        const float* const sF = base + sL.sF; const float* const W1s = base + sL.W1s;
+        float* const Yh1 = base + sL.Yh1; float* const q1 = base + sL.q1;
+        const int ntask = nlongF1 + (n2 + epi - 1) / epi;
+        for (int t = warp; t < ntask; t += nwarps) {
+          float4 z;
+          const int i = row_task_gather<IdxT, false>(t, nlongF1, llist, n2, G, D4, irp, icol, a, X, dp, n, zs, z);
+          const bool act = i >= 0;
+          if (act && q < D4) {
+            st4(U + i * dp + 4 * q, z);
+            const float4 s4 = ld4(sF + 4 * q);   // x * sigmoid(feat_mask) (explain.py:707), linear in x
+            st4(zs + lane * 4, make_float4(z.x * s4.x, z.y * s4.y, z.z * s4.z, z.w * s4.w));
           }
-          for (int f4 = 0; f4 < D4; ++f4) {
-            const float4 u = ld4(U + i * dp + 4 * f4);
-            const float4 s = ld4(sF + 4 * f4);
-            const float z[4] = {u.x * s.x, u.y * s.y, u.z * s.z, u.w * s.w};  // x * sigmoid(feat_mask) (explain.py:707)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float* wr = W1s + (4 * f4 + k) * HS;
-#pragma unroll
-              for (int c4 = 0; c4 < H4; ++c4) {
-                const float4 w = ld4(wr + 4 * c4);
-                acc[4 * c4] = fmaf(z[k], w.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(z[k], w.y, acc[4 * c4 + 1]);
-                acc[4 * c4 + 2] = fmaf(z[k], w.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(z[k], w.w, acc[4 * c4 + 3]);
-              }
-            }
-          }
-          float ss = 0.f;
-#pragma unroll
-          for (int c = 0; c < HID; ++c) ss = fmaf(acc[c], acc[c], ss);
-          const float q = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(p=2, dim=2), eps 1e-12
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4)
-            st4(Yh1 + i * HS + 4 * c4, make_float4(acc[4 * c4] / q, acc[4 * c4 + 1] / q, acc[4 * c4 + 2] / q, acc[4 * c4 + 3] / q));
-          q1[i] = q;
+          __syncwarp();
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (act && q < H4) y = group_dense(zs + G.gbase * 4, D4, W1s, HS, q, ld4(bs + 4 * q));
+          const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
+          const float qn = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(p=2, dim=2), eps 1e-12
+          if (act && q < H4) st4(Yh1 + i * HS + 4 * q, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
+          if (act && q == 0) q1[i] = qn;
+          __syncwarp();
         }
-      }
       }
       __syncthreads();
-      // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; normalise (aggregate lands in Yh2[i], then in place)
+      // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
       {
-      const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
-      const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
-      float* const a = base + sL.a;
-      float* const Yh1 = base + sL.Yh1;
-      float* const Yh2 = base + sL.Yh2;
-      float* const zs = base + sL.zs + warp * 128;
-      float* const bs = base + sL.bs;
-      float* const W2s = base + sL.W2s;
-      float* const q2 = base + sL.q2;
-      const IdxT* const llist = reinterpret_cast<const IdxT*>(base + sL.llist);
-      if (nlongF2 > 0) {
-        for (int k = warp; k < nlongF2; k += nwarps)
-          gather_long_row<IdxT, true>((int)llist[k], H4, lane, irp, icol, a, Yh1, HS, Yh2, HS, n, zs);
-        __syncthreads();
-      }
-      for (int rb = warp * 32; rb < n1; rb += nwarps * 32) {
-        const int re = min(rb + 32, n1);
-        gather_short_rows<IdxT, true>(rb, re, H4, lane, irp, icol, a, Yh1, HS, Yh2, HS, n);
-        __syncwarp();
-        const int i = rb + lane;
-        if (i < re) {
-          float acc[HID];
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4) {
-            const float4 b = ld4(bs + HID + 4 * c4);
-            acc[4 * c4] = b.x; acc[4 * c4 + 1] = b.y; acc[4 * c4 + 2] = b.z; acc[4 * c4 + 3] = b.w;
-          }
-#pragma unroll
-          for (int f4 = 0; f4 < H4; ++f4) {
-            const float4 u = ld4(Yh2 + i * HS + 4 * f4);
-            const float z[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float* wr = W2s + (4 * f4 + k) * HS;
-#pragma unroll
-              for (int c4 = 0; c4 < H4; ++c4) {
-                const float4 w = ld4(wr + 4 * c4);
-                acc[4 * c4] = fmaf(z[k], w.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(z[k], w.y, acc[4 * c4 + 1]);
-                acc[4 * c4 + 2] = fmaf(z[k], w.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(z[k], w.w, acc[4 * c4 + 3]);
-              }
-            }
-          }
-          float ss = 0.f;
-#pragma unroll
-          for (int c = 0; c < HID; ++c) ss = fmaf(acc[c], acc[c], ss);
-          const float q = fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4)
-            st4(Yh2 + i * HS + 4 * c4, make_float4(acc[4 * c4] / q, acc[4 * c4 + 1] / q, acc[4 * c4 + 2] / q, acc[4 * c4 + 3] / q));
-          q2[i] = q;
+        const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
+        const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
+        const IdxT* const llist = reinterpret_cast<const IdxT*>(base + sL.llist);
+        const float* const a = base + sL.a; const float* const Yh1 = base + sL.Yh1;
+        float* const zs = base + sL.zs + warp * 128; const float* const bs = base + sL.bs;
+        const float* const W2s = base + sL.W2s; float* const Yh2 = base + sL.Yh2; float* const q2 = base + sL.q2;
+        const int ntask = nlongF2 + (n1 + epi - 1) / epi;
+        for (int t = warp; t < ntask; t += nwarps) {
+          float4 z;
+          const int i = row_task_gather<IdxT, true>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, n, zs, z);
+          const bool act = i >= 0;
+          if (act && q < H4) st4(zs + lane * 4, z);
+          __syncwarp();
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (act && q < H4) y = group_dense(zs + G.gbase * 4, H4, W2s, HS, q, ld4(bs + HID + 4 * q));
+          const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
+          const float qn = fmaxf(sqrtf(ss), 1e-12f);
+          if (act && q < H4) st4(Yh2 + i * HS + 4 * q, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
+          if (act && q == 0) q2[i] = qn;
+          __syncwarp();
         }
-      }
       }
       __syncthreads();
       // ---- S: row r (= level-order id 0): layer 3, readout, softmax, -log p[gt], layer-3 backward
       if (warp == 0) {
         const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
         const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
-        float* const a = base + sL.a;
-        float* const Yh1 = base + sL.Yh1;
-        float* const Yh2 = base + sL.Yh2;
-        float* const zs = base + sL.zs + warp * 128;
-        float* const bs = base + sL.bs;
-        float* const W3s = base + sL.W3s;
-        float* const logit = base + sL.logit;
-        float* const dE = base + sL.dE;
-        float* const dZ3 = base + sL.dZ3;
-        const int r0 = irp[0], r1 = irp[1];
+        const float* const a = base + sL.a; const float* const Yh1 = base + sL.Yh1; const float* const Yh2 = base + sL.Yh2;
+        float* const zs = base + sL.zs; const float* const bs = base + sL.bs; const float* const W3s = base + sL.W3s;
+        float* const logit = base + sL.logit; float* const dE = base + sL.dE; float* const dZ3 = base + sL.dZ3;
+        {  // aggregate of row 0 with its edges split across the lane groups
+          const int r0 = irp[0], r1 = irp[1];
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (G.grp < epi && q < H4) acc = gather_row<IdxT, true>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q, n);
+          st4(zs + lane * 4, acc);
+        }
+        __syncwarp();
         float z = 0.f;
         if (lane < HID)
-          for (int e = r0; e < r1; ++e) z = fmaf(a[e], fmaxf(Yh2[(int)icol[e] * HS + lane], 0.f), z);
+          for (int g2 = 0; g2 < epi; ++g2) z += zs[(g2 * G.GW + (lane >> 2)) * 4 + (lane & 3)];
+        __syncwarp();
         if (lane < HID) zs[lane] = z;
         __syncwarp();
         float y3 = lane < EMB ? bs[2 * HID + lane] : 0.f;
@@ -473,161 +451,112 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         if (lane < HID) dZ3[lane] = dot_v4(zs, W3s + lane * EMB, EMB / 4);
       }
       __syncthreads();
-      // ---- B2: rows {r} U N(r) (one thread per row): dYh2 = dEmb2 (row r) + a[r,j] dZ3 (j in N(r)),
-      //          relu', normalise', dZ2 = dY2 W2^T
+      // ---- B2: rows {r} U N(r): dYh2 = dEmb2 (row r) + a[r,j] dZ3 (j in N(r)), relu', normalise', dZ2 = dY2 W2^T
       {
         const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
         const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
-        float* const a = base + sL.a;
-        float* const dE = base + sL.dE;
-        float* const dZ3 = base + sL.dZ3;
-        float* const Yh2 = base + sL.Yh2;
-        float* const q2 = base + sL.q2;
-        float* const W2s = base + sL.W2s;
-        float* const dZ2 = base + sL.dZ2;
+        const float* const a = base + sL.a; const float* const dE = base + sL.dE; const float* const dZ3 = base + sL.dZ3;
+        const float* const Yh2 = base + sL.Yh2; const float* const q2 = base + sL.q2; const float* const W2t = base + sL.W2t;
+        float* const dZ2 = base + sL.dZ2; float* const zs = base + sL.zs + warp * 128;
         const int r0 = irp[0];
         const int items = 1 + (int)irp[1] - r0;
-        for (int item = tid; item < items; item += nthreads) {
+        const int ntask = (items + epi - 1) / epi;
+        for (int t = warp; t < ntask; t += nwarps) {
+          const int item = t * epi + G.grp;
+          const bool act = G.grp < epi && item < items;
           int j = 0;
           float coef = 1.f;
           const float* dsrc = dE + HS;
-          if (item > 0) {
+          if (act && item > 0) {
             const int e = r0 + item - 1;
             j = icol[e];
             coef = a[e];
             dsrc = dZ3;
           }
-          const float* yr = Yh2 + j * HS;
-          float dy[HID];
-          float s = 0.f;
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4) {
-            const float4 yh = ld4(yr + 4 * c4);
-            const float4 g4 = ld4(dsrc + 4 * c4);
-            dy[4 * c4] = yh.x > 0.f ? coef * g4.x : 0.f;      // relu backward: grad where input > 0
-            dy[4 * c4 + 1] = yh.y > 0.f ? coef * g4.y : 0.f;
-            dy[4 * c4 + 2] = yh.z > 0.f ? coef * g4.z : 0.f;
-            dy[4 * c4 + 3] = yh.w > 0.f ? coef * g4.w : 0.f;
-            s = fmaf(yh.x, dy[4 * c4], s); s = fmaf(yh.y, dy[4 * c4 + 1], s);
-            s = fmaf(yh.z, dy[4 * c4 + 2], s); s = fmaf(yh.w, dy[4 * c4 + 3], s);
+          float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
+          if (act && q < H4) {
+            yh = ld4(Yh2 + j * HS + 4 * q);
+            const float4 g4 = ld4(dsrc + 4 * q);
+            dy.x = yh.x > 0.f ? coef * g4.x : 0.f;   // relu backward: grad where input > 0
+            dy.y = yh.y > 0.f ? coef * g4.y : 0.f;
+            dy.z = yh.z > 0.f ? coef * g4.z : 0.f;
+            dy.w = yh.w > 0.f ? coef * g4.w : 0.f;
           }
-          const float q = q2[j];
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4) {
-            const float4 yh = ld4(yr + 4 * c4);
-            dy[4 * c4] = (dy[4 * c4] - yh.x * s) / q; dy[4 * c4 + 1] = (dy[4 * c4 + 1] - yh.y * s) / q;
-            dy[4 * c4 + 2] = (dy[4 * c4 + 2] - yh.z * s) / q; dy[4 * c4 + 3] = (dy[4 * c4 + 3] - yh.w * s) / q;
+          const float sdot = group_sum(yh.x * dy.x + yh.y * dy.y + yh.z * dy.z + yh.w * dy.w, G);
+          if (act && q < H4) {
+            const float qn = q2[j];
+            st4(zs + lane * 4, make_float4((dy.x - yh.x * sdot) / qn, (dy.y - yh.y * sdot) / qn,
+                                           (dy.z - yh.z * sdot) / qn, (dy.w - yh.w * sdot) / qn));
           }
-#pragma unroll
-          for (int f4 = 0; f4 < H4; ++f4) {
-            float o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float* wr = W2s + (4 * f4 + k) * HS;
-              float t = 0.f;
-#pragma unroll
-              for (int c4 = 0; c4 < H4; ++c4) {
-                const float4 w = ld4(wr + 4 * c4);
-                t = fmaf(dy[4 * c4], w.x, t); t = fmaf(dy[4 * c4 + 1], w.y, t);
-                t = fmaf(dy[4 * c4 + 2], w.z, t); t = fmaf(dy[4 * c4 + 3], w.w, t);
-              }
-              o[k] = t;
-            }
-            st4(dZ2 + j * HS + 4 * f4, make_float4(o[0], o[1], o[2], o[3]));
-          }
+          __syncwarp();
+          if (act && q < H4)
+            st4(dZ2 + j * HS + 4 * q, group_dense(zs + G.gbase * 4, H4, W2t, HS, q, make_float4(0.f, 0.f, 0.f, 0.f)));
+          __syncwarp();
         }
       }
       __syncthreads();
-      // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient) lands in T[i]; then one
-      //          thread per row: relu', normalise', dZ1 = dY1 W1^T, dL/dsF partial, T[i] = dZ1 (.) sF
+      // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise',
+      //          dZ1 = dY1 W1^T, dL/dsF partial, dZ1 (.) sF kept for the edge dots
       {
-      const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
-      const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
-      float* const a = base + sL.a;
-      float* const dZ2 = base + sL.dZ2;
-      float* const Tb = base + sL.T;
-      float* const Yh1 = base + sL.Yh1;
-      float* const dE = base + sL.dE;
-      float* const q1 = base + sL.q1;
-      float* const W1s = base + sL.W1s;
-      float* const U = base + sL.U;
-      float* const sF = base + sL.sF;
-      float* const gFp = base + sL.gFp;
-      for (int rb = warp * 32; rb < n2; rb += nwarps * 32) {
-        const int re = min(rb + 32, n2);
-        {  // all rows by lane groups: at most n1 columns per row carry gradient
-          const int grp = lane / H4, q = lane - grp * H4;
-          const int epi = 32 / H4;
-          if (grp < epi) {
-            for (int i = rb + grp; i < re; i += epi) {
-              const int r0 = irp[i], r1 = irp[i + 1];
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int e = r0; e < r1; ++e) {
-                const int c = icol[e];
-                if (c >= n1) break;
-                fma4(acc, a[e], ld4(dZ2 + c * HS + 4 * q));
-              }
-              st4(Tb + i * TS + 4 * q, acc);
-            }
+        const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
+        const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
+        const float* const a = base + sL.a; const float* const dZ2 = base + sL.dZ2; const float* const dE = base + sL.dE;
+        const float* const Yh1 = base + sL.Yh1; const float* const q1 = base + sL.q1; const float* const W1t = base + sL.W1t;
+        const float* const U = base + sL.U; const float* const sF = base + sL.sF;
+        float* const dZ1s = base + sL.dZ1s; float* const gFp = base + sL.gFp; float* const zs = base + sL.zs + warp * 128;
+        float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ntask = (n2 + epi - 1) / epi;
+        for (int t = warp; t < ntask; t += nwarps) {
+          float4 dh;
+          const int i = row_task_gather<IdxT, false>(t, 0, (const IdxT*)nullptr, n2, G, H4, irp, icol, a, dZ2, HS, n1, zs, dh);
+          const bool act = i >= 0;
+          float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
+          if (act && q < H4) {
+            yh = ld4(Yh1 + i * HS + 4 * q);
+            if (i == 0) { const float4 e4 = ld4(dE + 4 * q); dh.x += e4.x; dh.y += e4.y; dh.z += e4.z; dh.w += e4.w; }
+            dy.x = yh.x > 0.f ? dh.x : 0.f; dy.y = yh.y > 0.f ? dh.y : 0.f;
+            dy.z = yh.z > 0.f ? dh.z : 0.f; dy.w = yh.w > 0.f ? dh.w : 0.f;
           }
+          const float sdot = group_sum(yh.x * dy.x + yh.y * dy.y + yh.z * dy.z + yh.w * dy.w, G);
+          if (act && q < H4) {
+            const float qn = q1[i];
+            st4(zs + lane * 4, make_float4((dy.x - yh.x * sdot) / qn, (dy.y - yh.y * sdot) / qn,
+                                           (dy.z - yh.z * sdot) / qn, (dy.w - yh.w * sdot) / qn));
+          }
+          __syncwarp();
+          if (act && q < D4) {
+            const float4 o = group_dense(zs + G.gbase * 4, H4, W1t, dp, q, make_float4(0.f, 0.f, 0.f, 0.f));
+            const float4 u = ld4(U + i * dp + 4 * q);
+            const float4 s4 = ld4(sF + 4 * q);
+            gacc.x = fmaf(o.x, u.x, gacc.x); gacc.y = fmaf(o.y, u.y, gacc.y);
+            gacc.z = fmaf(o.z, u.z, gacc.z); gacc.w = fmaf(o.w, u.w, gacc.w);
+            st4(dZ1s + i * dp + 4 * q, make_float4(o.x * s4.x, o.y * s4.y, o.z * s4.z, o.w * s4.w));
+          }
+          __syncwarp();
+        }
+        // per-warp dL/dsF partial: sum the groups' accumulators (fixed order => deterministic)
+        st4(zs + lane * 4, gacc);
+        __syncwarp();
+        if (G.grp == 0 && q < D4) {
+          float4 tsum = gacc;
+          for (int g2 = 1; g2 < epi; ++g2) {
+            const float4 o = ld4(zs + (g2 * G.GW + q) * 4);
+            tsum.x += o.x; tsum.y += o.y; tsum.z += o.z; tsum.w += o.w;
+          }
+          st4(gFp + warp * dp + 4 * q, tsum);
         }
         __syncwarp();
-        const int i = rb + lane;
-        const bool valid = i < re;
-        float dy[HID];
-        {
-          const float* yr = Yh1 + (valid ? i : 0) * HS;
-          const float* tr = Tb + (valid ? i : 0) * TS;
-          float s = 0.f;
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4) {
-            const float4 yh = ld4(yr + 4 * c4);
-            float4 g4 = ld4(tr + 4 * c4);
-            if (i == 0) { const float4 e4 = ld4(dE + 4 * c4); g4.x += e4.x; g4.y += e4.y; g4.z += e4.z; g4.w += e4.w; }
-            dy[4 * c4] = yh.x > 0.f ? g4.x : 0.f; dy[4 * c4 + 1] = yh.y > 0.f ? g4.y : 0.f;
-            dy[4 * c4 + 2] = yh.z > 0.f ? g4.z : 0.f; dy[4 * c4 + 3] = yh.w > 0.f ? g4.w : 0.f;
-            s = fmaf(yh.x, dy[4 * c4], s); s = fmaf(yh.y, dy[4 * c4 + 1], s);
-            s = fmaf(yh.z, dy[4 * c4 + 2], s); s = fmaf(yh.w, dy[4 * c4 + 3], s);
-          }
-          const float q = valid ? q1[i] : 1.f;
-#pragma unroll
-          for (int c4 = 0; c4 < H4; ++c4) {
-            const float4 yh = ld4(yr + 4 * c4);
-            dy[4 * c4] = (dy[4 * c4] - yh.x * s) / q; dy[4 * c4 + 1] = (dy[4 * c4 + 1] - yh.y * s) / q;
-            dy[4 * c4 + 2] = (dy[4 * c4 + 2] - yh.z * s) / q; dy[4 * c4 + 3] = (dy[4 * c4 + 3] - yh.w * s) / q;
-          }
-        }
-        for (int f4 = 0; f4 < D4; ++f4) {
-          float o[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float* wr = W1s + (4 * f4 + k) * HS;
-            float t = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < H4; ++c4) {
-              const float4 w = ld4(wr + 4 * c4);
-              t = fmaf(dy[4 * c4], w.x, t); t = fmaf(dy[4 * c4 + 1], w.y, t);
-              t = fmaf(dy[4 * c4 + 2], w.z, t); t = fmaf(dy[4 * c4 + 3], w.w, t);
-            }
-            o[k] = t;
-          }
-          float4 pu = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) {
-            const float4 u = ld4(U + i * dp + 4 * f4);
-            const float4 s4 = ld4(sF + 4 * f4);
-            pu = make_float4(o[0] * u.x, o[1] * u.y, o[2] * u.z, o[3] * u.w);
-            st4(Tb + i * TS + 4 * f4, make_float4(o[0] * s4.x, o[1] * s4.y, o[2] * s4.z, o[3] * s4.w));
-          }
-          pu.x = warp_sum(pu.x); pu.y = warp_sum(pu.y); pu.z = warp_sum(pu.z); pu.w = warp_sum(pu.w);
-          if (lane == 0) {
-            float4 g4 = ld4(gFp + warp * dp + 4 * f4);
-            g4.x += pu.x; g4.y += pu.y; g4.z += pu.z; g4.w += pu.w;
-            st4(gFp + warp * dp + 4 * f4, g4);
-          }
-        }
-      }
       }
       __syncthreads();
+      if (A.dbg != nullptr && it == 1 && qi == 0) {   // debug: [header 16 floats][whole task slab]
+        if (tid == 0) {
+          A.dbg[0] = (float)sL.total_words; A.dbg[1] = (float)sL.X; A.dbg[2] = (float)sL.U; A.dbg[3] = (float)sL.Yh1;
+          A.dbg[4] = (float)sL.q1; A.dbg[5] = (float)sL.Yh2; A.dbg[6] = (float)sL.q2; A.dbg[7] = (float)sL.dZ2;
+          A.dbg[8] = (float)sL.dZ1s; A.dbg[9] = (float)sL.gFp; A.dbg[10] = (float)sL.dE; A.dbg[11] = (float)sL.dZ3;
+          A.dbg[12] = (float)sL.logit; A.dbg[13] = (float)sL.a; A.dbg[14] = (float)dp; A.dbg[15] = (float)nwarps;
+        }
+        for (int w = tid; w < sL.total_words; w += nthreads) A.dbg[16 + w] = base[w];
+      }
       // ---- P: per undirected edge: dA_ij, dA_ji, symmetrise, regularisers, Adam, next mask value
       {
         float* const gFp = base + sL.gFp;
@@ -636,7 +565,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const IdxT* const pi = reinterpret_cast<const IdxT*>(base + sL.pi); const IdxT* const pj = reinterpret_cast<const IdxT*>(base + sL.pj);
         const IdxT* const ppij = reinterpret_cast<const IdxT*>(base + sL.ppij); const IdxT* const ppji = reinterpret_cast<const IdxT*>(base + sL.ppji);
         float* const lap2 = base + sL.lap2;
-        float* const Tb = base + sL.T;
+        float* const dZ1s = base + sL.dZ1s;
         float* const X = base + sL.X;
         float* const dZ2 = base + sL.dZ2;
         float* const Yh1 = base + sL.Yh1;
@@ -650,7 +579,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         // feature mask: dL/dF = sF(1-sF) (sum_i dZ1[i] U[i] + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
         for (int f = tid; f < d; f += nthreads) {
           float gsum = 0.f;
-          for (int w = 0; w < nwarps; ++w) { gsum += gFp[w * dp + f]; gFp[w * dp + f] = 0.f; }
+          for (int w = 0; w < nwarps; ++w) gsum += gFp[w * dp + f];
           const float s = sF[f];
           const float g = s * (1.f - s) * (gsum + hp.c_feat_size / (float)d);
           float mf = mF[f], vf = vF[f], Fv = Fm[f];
@@ -662,18 +591,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
         for (int p = tid; p < np; p += nthreads) {
           const int i = pi[p], j = pj[p];
-          float G = lap2[p];
-          if (i < n2) G += dot_v4(Tb + i * TS, X + j * dp, D4);
-          if (j < n2) G += dot_v4(Tb + j * TS, X + i * dp, D4);
-          if (i < n1) G += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
-          if (j < n1) G += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
-          if (i == 0) G += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
-          G *= 0.5f;  // sym_mask = (S + S^T)/2 (explain.py:671)
+          float Gd = lap2[p];
+          if (i < n2) Gd += dot_v4(dZ1s + i * dp, X + j * dp, D4);
+          if (j < n2) Gd += dot_v4(dZ1s + j * dp, X + i * dp, D4);
+          if (i < n1) Gd += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
+          if (j < n1) Gd += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
+          if (i == 0) Gd += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
+          Gd *= 0.5f;  // sym_mask = (S + S^T)/2 (explain.py:671)
           float2 Mv = MM[p];
           const float2 Sv = SS[p];
           // size: coeff*sum(S) ; entropy: mean over n^2 of H(S), dH/dM = -M S(1-S) (explain.py:755-770)
-          const float gi = Sv.x * (1.f - Sv.x) * (G + hp.c_size - ent_over_nn * Mv.x);
-          const float gj = Sv.y * (1.f - Sv.y) * (G + hp.c_size - ent_over_nn * Mv.y);
+          const float gi = Sv.x * (1.f - Sv.x) * (Gd + hp.c_size - ent_over_nn * Mv.x);
+          const float gj = Sv.y * (1.f - Sv.y) * (Gd + hp.c_size - ent_over_nn * Mv.y);
           float2 m2 = mm[p], v2 = vv[p];
           m2.x = m2.x + (gi - m2.x) * hp.one_minus_b1;
           m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
@@ -734,7 +663,7 @@ cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, c
   args.order = cfg.order; args.ntasks = cfg.ntasks; args.counter = cfg.counter;
   args.gws = cfg.gws; args.gws_stride_words = cfg.gws_stride_words;
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
-  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat;
+  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg;
   if (m.hid == 20 && m.emb == 20) return launch_dims<20, 20>(cfg, args, s);
   return cudaErrorInvalidValue;  // gx_set_model rejects other widths before this point
 }

@@ -85,11 +85,11 @@ __host__ __device__ inline int gx_round_up(int x, int m) { return (x + m - 1) / 
 
 struct GxLayout {
   // float arrays (offsets in 4-byte words)
-  int X, U, Yh1, q1, Yh2, q2, dZ2, T, a, M, lap2, W1s, W2s, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
+  int X, U, Yh1, q1, Yh2, q2, dZ2, dZ1s, a, M, lap2, W1s, W1t, W2s, W2t, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
   // index arrays (offsets in 4-byte words; element type IdxT)
   int icol, irp, pi, pj, ppij, ppji, llist;
   int total_words;
-  int dp, ts;
+  int dp;
 };
 
 // idx_bytes = sizeof(IdxT) (2 or 4).  hid/emb must be multiples of 4.
@@ -98,9 +98,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
                                                    int idx_bytes) {
   GxLayout L;
   const int dp = gx_round_up(d, 4);
-  const int ts = dp > hid ? dp : hid;
   L.dp = dp;
-  L.ts = ts;
   int o = 0;
   auto takef = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
   auto takei = [&](int elems) { int r = o; o += gx_round_up((elems * idx_bytes + 3) / 4, 4); return r; };
@@ -111,12 +109,14 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.Yh2 = takef(n1 * hid);
   L.q2 = takef(n1);
   L.dZ2 = takef(n1 * hid);
-  L.T = takef(n2 * ts);
+  L.dZ1s = takef(n2 * dp);
   L.a = takef(e1);
   L.M = takef(8 * np);  // (M_ij,M_ji), (m_ij,m_ji), (v_ij,v_ji), (S_ij,S_ji) as float2 arrays
   L.lap2 = takef(np);
-  L.W1s = takef(dp * hid);
+  L.W1s = takef(dp * hid);   // [dp][hid]   rows >= d are zero
+  L.W1t = takef(hid * dp);   // [hid][dp]   transposed
   L.W2s = takef(hid * hid);
+  L.W2t = takef(hid * hid);
   L.W3s = takef(hid * emb);
   L.bs = takef(2 * hid + emb);
   L.sF = takef(dp);
@@ -182,6 +182,7 @@ struct GxExplainLaunch {
   int32_t idx16;         // 1: 16-bit indices
   float* gws;            // global workspace for the non-resident variant
   int64_t gws_stride_words;
+  float* dbg;            // debug dump buffer (device) or NULL
 };
 cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                               const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
