@@ -88,7 +88,7 @@ struct gx_handle {
   std::vector<int> class_idx16;
   int64_t gws_stride_words = 0;
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
-  DevBuf d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
+  DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
   GxPlanArrays plan{};
   // slot workspace
   DevBuf ws_buf;
@@ -135,7 +135,7 @@ int task_smem_class(const GxTask& T, const GxModelDev& m, int* bytes_out, int* i
   const bool small_idx = T.n < 65535 && T.e1 < 65535;
   for (int c = 0; small_idx && c < kNumClasses - 1; ++c) {
     const int nwarps = kClasses[c].threads / 32;
-    const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs, m.d, m.hid, m.emb, m.C, nwarps, 2);
+    const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, m.d, m.hid, m.emb, m.C, nwarps, 2);
     const int64_t bytes = (int64_t)L.total_words * 4;
     if (bytes <= kClasses[c].cap_bytes) {
       *bytes_out = (int)bytes;
@@ -143,7 +143,7 @@ int task_smem_class(const GxTask& T, const GxModelDev& m, int* bytes_out, int* i
       return c;
     }
   }
-  const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs, m.d, m.hid, m.emb, m.C,
+  const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, m.d, m.hid, m.emb, m.C,
                                     kClasses[kNumClasses - 1].threads / 32, 4);
   *bytes_out = L.total_words;  // words (may exceed int bytes range for huge tasks)
   *idx16_out = 0;
@@ -212,7 +212,7 @@ int gx_destroy(gx_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&h->g_rowptr, &h->g_col, &h->g_feat, &h->g_label, &h->g_pred, &h->m_buf, &h->d_nodes,
                     &h->d_tasks, &h->d_nbrs, &h->d_lo2gid, &h->d_srp, &h->d_scol, &h->d_irp, &h->d_icol,
-                    &h->d_pairs, &h->d_order, &h->d_counters, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
+                    &h->d_pairs, &h->d_order, &h->d_counters, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
                     &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < kNumStreams; ++i) {
@@ -526,11 +526,26 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
   hd.init = hp->init;
   hd.seed = hp->seed;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
-  const auto& last = h->class_order[kNumClasses - 1];
-  int last_grid = 0;
-  if (!last.empty()) {
-    last_grid = std::min<int>((int)last.size(), h->num_sms);
+  if (!h->class_order[kNumClasses - 1].empty()) {
+    const int last_grid = std::min<int>((int)h->class_order[kNumClasses - 1].size(), h->num_sms);
     GX_CUDA_CHECK(h->d_gws.reserve((size_t)last_grid * h->gws_stride_words * 4));
+  }
+  // per-CTA pair-state slabs (one region per launch class, 8 floats per inner pair of its largest task)
+  int64_t pws_off[kNumClasses + 1], pws_stride[kNumClasses];
+  int grids[kNumClasses];
+  {
+    int64_t acc_words = 0;
+    for (int c = 0; c < kNumClasses; ++c) {
+      const int nt = (int)h->class_order[c].size();
+      int maxnp = 0;
+      for (int32_t t : h->class_order[c]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
+      pws_stride[c] = ((int64_t)maxnp * 8 + 3) / 4 * 4;
+      grids[c] = c == kNumClasses - 1 ? std::min<int>(nt, h->num_sms) : std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
+      pws_off[c] = acc_words;
+      acc_words += pws_stride[c] * std::max(grids[c], 0);
+    }
+    pws_off[kNumClasses] = acc_words;
+    GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(acc_words, 4) * 4));
   }
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->stream));
   GX_CUDA_CHECK(cudaEventRecord(h->ev_fork, h->stream));
@@ -552,13 +567,14 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
     cfg.gws = h->d_gws.as<float>();
     cfg.gws_stride_words = h->gws_stride_words;
     cfg.dbg = h->dbg;
-    if (c == kNumClasses - 1) cfg.grid = last_grid;
-    else {
+    cfg.pws = h->d_pws.as<float>() + pws_off[c];
+    cfg.pws_stride_words = pws_stride[c];
+    cfg.grid = grids[c];
+    if (c != kNumClasses - 1) {
       // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)
       int need = 0;
       for (int32_t t : h->class_order[c]) need = std::max(need, h->tasks[t].smem_bytes);
       cfg.smem_bytes = std::max(need, 1024);
-      cfg.grid = std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
     GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
@@ -566,6 +582,9 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
     GX_CUDA_CHECK(cudaEventRecord(h->ev_join[c], h->side[c]));
     used.push_back(c);
   }
+  // pairs between two outermost nodes: independent scalar recurrences, whole batch in one launch
+  GX_CUDA_CHECK(gx_launch_outer_pairs(hd, h->g, h->plan, count, m0_dev, out_dev, h->stream));
+  h->launches += 1;
   for (int c : used) GX_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_join[c], 0));
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
   h->timed = true;

@@ -106,6 +106,8 @@ struct ExplainArgs {
   int32_t* counter;
   float* gws;
   int64_t gws_stride_words;
+  float* pws;
+  int64_t pws_stride_words;
   GxGraphDev g;
   GxModelDev m;
   GxHparamsDev hp;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     if (qi >= A.ntasks) break;
     const int task_id = A.order[qi];
     const GxTask* __restrict__ Tp = A.plan.tasks + task_id;
-    const int n = Tp->n, n1 = Tp->n1, n2 = Tp->n2, e1 = Tp->e1, np = Tp->npairs;
+    const int n = Tp->n, n1 = Tp->n1, n2 = Tp->n2, e1 = Tp->e1, np = Tp->npairs_in;  // inner pairs only
     const int gt = Tp->gt_label;
     const int64_t node_off = Tp->node_off, rp_off = Tp->rp_off, edge_off = Tp->edge_off, pair_off = Tp->pair_off;
     if (tid == 0) sL = gx_make_layout(n, n1, n2, e1, np, d, HID, EMB, C, nwarps, (int)sizeof(IdxT));
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     {
       float* const X = base + sL.X; float* const W1s = base + sL.W1s; float* const W2s = base + sL.W2s; float* const W3s = base + sL.W3s;
       float* const bs = base + sL.bs; float* const sF = base + sL.sF; float* const Fm = base + sL.F; float* const mF = base + sL.mF;
-      float* const vF = base + sL.vF; float* const gFp = base + sL.gFp; float* const a = base + sL.a; float* const lap2 = base + sL.lap2;
-      float2* const MM = reinterpret_cast<float2*>(base + sL.M); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
+      float* const vF = base + sL.vF; float* const gFp = base + sL.gFp; float* const a = base + sL.a; float* const yv = base + sL.y;
+      float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)blockIdx.x * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
       IdxT* const icol = reinterpret_cast<IdxT*>(base + sL.icol); IdxT* const irp = reinterpret_cast<IdxT*>(base + sL.irp);
       IdxT* const pi = reinterpret_cast<IdxT*>(base + sL.pi); IdxT* const pj = reinterpret_cast<IdxT*>(base + sL.pj);
       IdxT* const ppij = reinterpret_cast<IdxT*>(base + sL.ppij); IdxT* const ppji = reinterpret_cast<IdxT*>(base + sL.ppji);
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     for (int idx = tid; idx < EMB; idx += nthreads) bs[2 * HID + idx] = __ldg(m.b[2] + idx);
     for (int e = tid; e < e1; e += nthreads) icol[e] = (IdxT)A.plan.icol[edge_off + e];
     for (int i = tid; i <= n2; i += nthreads) irp[i] = (IdxT)A.plan.irowptr[rp_off + i];
+    for (int i = tid; i < n; i += nthreads) yv[i] = (float)__ldg(A.g.pred_label + lo2gid[i]);
     for (int f = tid; f < dp; f += nthreads) {
       sF[f] = 0.5f;  // sigmoid(0): feat_mask is initialised to 0 (explain.py:633-643)
       Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f;
@@ -287,9 +290,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       vv[p] = make_float2(0.f, 0.f);
       const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
       SS[p] = make_float2(Si, Sj);
-      const float yi = (float)__ldg(A.g.pred_label + lo2gid[i]);
-      const float yj = (float)__ldg(A.g.pred_label + lo2gid[j]);
-      lap2[p] = lap_over_nn * (yi - yj) * (yi - yj);  // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2
       const float a0 = 0.5f * (Si + Sj);  // explain.py:665-678
       if (i < n2) a[pij] = a0;
       if (j < n2) a[pji] = a0;
@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const a = base + sL.a; const float* const dZ2 = base + sL.dZ2; const float* const dE = base + sL.dE;
         const float* const Yh1 = base + sL.Yh1; const float* const q1 = base + sL.q1; const float* const W1t = base + sL.W1t;
         const float* const U = base + sL.U; const float* const sF = base + sL.sF;
-        float* const dZ1s = base + sL.dZ1s; float* const gFp = base + sL.gFp; float* const zs = base + sL.zs + warp * 128;
+        float* const dZ1s = base + sL.U;  // row i of U is consumed (dL/dsF) right before dZ1[i] (.) sF overwrites it
+        float* const gFp = base + sL.gFp; float* const zs = base + sL.zs + warp * 128;
         float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int ntask = (n2 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         if (tid == 0) {
           A.dbg[0] = (float)sL.total_words; A.dbg[1] = (float)sL.X; A.dbg[2] = (float)sL.U; A.dbg[3] = (float)sL.Yh1;
           A.dbg[4] = (float)sL.q1; A.dbg[5] = (float)sL.Yh2; A.dbg[6] = (float)sL.q2; A.dbg[7] = (float)sL.dZ2;
-          A.dbg[8] = (float)sL.dZ1s; A.dbg[9] = (float)sL.gFp; A.dbg[10] = (float)sL.dE; A.dbg[11] = (float)sL.dZ3;
+          A.dbg[8] = (float)sL.U; A.dbg[9] = (float)sL.gFp; A.dbg[10] = (float)sL.dE; A.dbg[11] = (float)sL.dZ3;
           A.dbg[12] = (float)sL.logit; A.dbg[13] = (float)sL.a; A.dbg[14] = (float)dp; A.dbg[15] = (float)nwarps;
         }
         for (int w = tid; w < sL.total_words; w += nthreads) A.dbg[16 + w] = base[w];
@@ -564,14 +565,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float* const Fm = base + sL.F; float* const mF = base + sL.mF; float* const vF = base + sL.vF;
         const IdxT* const pi = reinterpret_cast<const IdxT*>(base + sL.pi); const IdxT* const pj = reinterpret_cast<const IdxT*>(base + sL.pj);
         const IdxT* const ppij = reinterpret_cast<const IdxT*>(base + sL.ppij); const IdxT* const ppji = reinterpret_cast<const IdxT*>(base + sL.ppji);
-        float* const lap2 = base + sL.lap2;
-        float* const dZ1s = base + sL.dZ1s;
+        const float* const yv = base + sL.y;
+        const float* const dZ1s = base + sL.U;
         float* const X = base + sL.X;
         float* const dZ2 = base + sL.dZ2;
         float* const Yh1 = base + sL.Yh1;
         float* const dZ3 = base + sL.dZ3;
         float* const Yh2 = base + sL.Yh2;
-        float2* const MM = reinterpret_cast<float2*>(base + sL.M); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
+        float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)blockIdx.x * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
         float* const a = base + sL.a;
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
         const float step = tab.x, bc2s = tab.y;
@@ -591,7 +592,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
         for (int p = tid; p < np; p += nthreads) {
           const int i = pi[p], j = pj[p];
-          float Gd = lap2[p];
+          const float yd = yv[i] - yv[j];
+          float Gd = lap_over_nn * yd * yd;  // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2 (explain.py:780-793)
           if (i < n2) Gd += dot_v4(dZ1s + i * dp, X + j * dp, D4);
           if (j < n2) Gd += dot_v4(dZ1s + j * dp, X + i * dp, D4);
           if (i < n1) Gd += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
@@ -632,6 +634,56 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
   }
 }
 
+
+// Pairs between two outermost nodes (both endpoints outside every row the forward computes): their
+// masked-adjacency value never enters the GCN, so dL/dM is regulariser-only and the whole Adam
+// trajectory is a private scalar recurrence -- one thread per pair, state in registers, no barriers.
+__global__ void __launch_bounds__(256)
+outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays plan, int count,
+                   const float* __restrict__ m0, float* __restrict__ out_mask) {
+  for (int t = blockIdx.x; t < count; t += gridDim.x) {
+    const GxTask* __restrict__ Tp = plan.tasks + t;
+    const int np = Tp->npairs, np_in = Tp->npairs_in, n = Tp->n;
+    const int64_t edge_off = Tp->edge_off, pair_off = Tp->pair_off;
+    const int32_t* __restrict__ lo2gid = plan.lo2gid + Tp->node_off;
+    const float nn = (float)n * (float)n;
+    const float ent_over_nn = hp.c_ent / nn, lap_over_nn = hp.c_lap / nn;
+    const float m0_std = sqrtf(2.0f / (float)n);
+    for (int p = np_in + threadIdx.x; p < np; p += blockDim.x) {
+      const int i = plan.pair_i[pair_off + p], j = plan.pair_j[pair_off + p];
+      const int oij = plan.pair_oij[pair_off + p], oji = plan.pair_oji[pair_off + p];
+      float Mi, Mj;
+      if (hp.init == GX_INIT_M0) {
+        Mi = __ldg(m0 + edge_off + oij);
+        Mj = __ldg(m0 + edge_off + oji);
+      } else {
+        Mi = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oij);
+        Mj = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oji);
+      }
+      const float yd = (float)__ldg(g.pred_label + lo2gid[i]) - (float)__ldg(g.pred_label + lo2gid[j]);
+      const float Gd = 0.5f * (lap_over_nn * yd * yd);
+      float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
+      float mi = 0.f, mj = 0.f, vi = 0.f, vj = 0.f;
+      for (int it = 1; it <= hp.iters; ++it) {
+        const float2 tab = __ldg(hp.adam_tab + (it - 1));
+        const float gi = Si * (1.f - Si) * (Gd + hp.c_size - ent_over_nn * Mi);
+        const float gj = Sj * (1.f - Sj) * (Gd + hp.c_size - ent_over_nn * Mj);
+        mi = mi + (gi - mi) * hp.one_minus_b1;
+        mj = mj + (gj - mj) * hp.one_minus_b1;
+        vi = vi * hp.b2 + hp.one_minus_b2 * gi * gi;
+        vj = vj * hp.b2 + hp.one_minus_b2 * gj * gj;
+        Mi = Mi - tab.x * (mi / (sqrtf(vi) / tab.y + hp.eps));
+        Mj = Mj - tab.x * (mj / (sqrtf(vj) / tab.y + hp.eps));
+        Si = sigmoid_f(Mi);
+        Sj = sigmoid_f(Mj);
+      }
+      const float an = 0.5f * (Si + Sj);
+      out_mask[edge_off + oij] = an;
+      out_mask[edge_off + oji] = an;
+    }
+  }
+}
+
 template <bool kShared, typename IdxT, int HID, int EMB, int NT>
 cudaError_t launch_one(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
   auto kern = explain_node_kernel<kShared, IdxT, HID, EMB, NT>;
@@ -656,12 +708,19 @@ cudaError_t launch_dims(const GxExplainLaunch& cfg, const ExplainArgs& args, cud
 
 int gx_explain_max_smem() { return 227 * 1024; }
 
+cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
+                                  const float* m0, float* out_mask, cudaStream_t s) {
+  outer_pairs_kernel<<<count < 148 * 8 ? count : 148 * 8, 256, 0, s>>>(hp, g, plan, count, m0, out_mask);
+  return cudaGetLastError();
+}
+
 cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                               const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                               float* out_mask, float* out_feat, cudaStream_t s) {
   ExplainArgs args;
   args.order = cfg.order; args.ntasks = cfg.ntasks; args.counter = cfg.counter;
   args.gws = cfg.gws; args.gws_stride_words = cfg.gws_stride_words;
+  args.pws = cfg.pws; args.pws_stride_words = cfg.pws_stride_words;
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
   args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg;
   if (m.hid == 20 && m.emb == 20) return launch_dims<20, 20>(cfg, args, s);

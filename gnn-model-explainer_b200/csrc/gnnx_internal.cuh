@@ -16,6 +16,7 @@ struct GxTask {
   int32_t n;        // |k-hop set|
   int32_t e_d;      // directed entries of the induced sub-adjacency (self loops dropped)
   int32_t npairs;   // e_d / 2 undirected edges
+  int32_t npairs_in;  // pairs with at least one endpoint in a row the forward computes (< n2): listed first
   int32_t idx_new;  // rank of `node` among its ascending neighbours (explain.py:496)
   int32_t gt_label; // label[node]
   int32_t n1, n2;   // level-order prefix sizes: |dist<=L-2|, |dist<=L-1| for L=3 -> |dist<=1|, |dist<=2|
@@ -85,15 +86,18 @@ __host__ __device__ inline int gx_round_up(int x, int m) { return (x + m - 1) / 
 
 struct GxLayout {
   // float arrays (offsets in 4-byte words)
-  int X, U, Yh1, q1, Yh2, q2, dZ2, dZ1s, a, M, lap2, W1s, W1t, W2s, W2t, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
+  int X, U, Yh1, q1, Yh2, q2, dZ2, a, y, W1s, W1t, W2s, W2t, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
   // index arrays (offsets in 4-byte words; element type IdxT)
   int icol, irp, pi, pj, ppij, ppji, llist;
   int total_words;
   int dp;
 };
 
+// Shared-memory footprint of one task.  np_in = pairs with an endpoint in rows < n2 (their indices live in
+// shared memory, their optimiser state in a per-CTA global slab that stays in L2); pairs between two
+// outermost nodes never touch the forward and are optimised by a separate elementwise kernel.
 // idx_bytes = sizeof(IdxT) (2 or 4).  hid/emb must be multiples of 4.
-__host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1, int np, int d,
+__host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1, int np_in, int d,
                                                    int hid, int emb, int C, int nwarps,
                                                    int idx_bytes) {
   GxLayout L;
@@ -103,16 +107,14 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   auto takef = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
   auto takei = [&](int elems) { int r = o; o += gx_round_up((elems * idx_bytes + 3) / 4, 4); return r; };
   L.X = takef(n * dp);
-  L.U = takef(n2 * dp);
+  L.U = takef(n2 * dp);      // A_m X in the forward; overwritten row by row with dZ1 (.) sF in the backward
   L.Yh1 = takef(n2 * hid);
   L.q1 = takef(n2);
   L.Yh2 = takef(n1 * hid);
   L.q2 = takef(n1);
   L.dZ2 = takef(n1 * hid);
-  L.dZ1s = takef(n2 * dp);
   L.a = takef(e1);
-  L.M = takef(8 * np);  // (M_ij,M_ji), (m_ij,m_ji), (v_ij,v_ji), (S_ij,S_ji) as float2 arrays
-  L.lap2 = takef(np);
+  L.y = takef(n);            // float(pred_label) per node (Laplacian regulariser)
   L.W1s = takef(dp * hid);   // [dp][hid]   rows >= d are zero
   L.W1t = takef(hid * dp);   // [hid][dp]   transposed
   L.W2s = takef(hid * hid);
@@ -130,10 +132,10 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.logit = takef(C < 32 ? 32 : C);
   L.icol = takei(e1);
   L.irp = takei(n2 + 1);
-  L.pi = takei(np);
-  L.pj = takei(np);
-  L.ppij = takei(np);
-  L.ppji = takei(np);
+  L.pi = takei(np_in);
+  L.pj = takei(np_in);
+  L.ppij = takei(np_in);
+  L.ppji = takei(np_in);
   L.llist = takei(n2);
   L.total_words = o;
   return L;
@@ -182,11 +184,15 @@ struct GxExplainLaunch {
   int32_t idx16;         // 1: 16-bit indices
   float* gws;            // global workspace for the non-resident variant
   int64_t gws_stride_words;
+  float* pws;            // per-CTA pair-state slab: 8 floats per inner pair (M,m,v,S of both directions)
+  int64_t pws_stride_words;
   float* dbg;            // debug dump buffer (device) or NULL
 };
 cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                               const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                               float* out_mask, float* out_feat, cudaStream_t s);
 int gx_explain_max_smem();
+cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
+                                  const float* m0, float* out_mask, cudaStream_t s);
 cudaError_t gx_launch_densify(const GxPlanArrays& plan, int count, const int64_t* dense_off,
                               const float* edge_mask, double* out, cudaStream_t s);

@@ -134,29 +134,34 @@ khop_count_kernel(GxGraphDev g, const int32_t* __restrict__ nodes, int count, in
                   GxSlotWs ws, GxTask* __restrict__ tasks) {
   __shared__ int s_ctrl[3];
   __shared__ int s_cnt[GX_MAX_LEVELS + 1];
-  __shared__ int s_e[2];
+  __shared__ int s_e[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const Slot sl = slot_of(ws, blockIdx.x, g.N);
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
     const int root = nodes[t];
     const int tail = bfs_khop(g, root, k, sl, s_ctrl);
     if (tid <= GX_MAX_LEVELS) s_cnt[tid] = 0;
-    if (tid < 2) s_e[tid] = 0;
+    if (tid < 3) s_e[tid] = 0;
     __syncthreads();
     for (int idx = 1 + warp; idx < tail; idx += nwarps) {
       const int u = sl.q[idx];
       const int du = (u == root) ? 0 : (int)sl.dist[u];
-      int cnt = 0;
+      int cnt = 0, cnt_out = 0;
       const int e1 = g.rowptr[u + 1];
       for (int e = g.rowptr[u] + lane; e < e1; e += 32) {
         const int v = g.col[e];
-        cnt += (v != u && member(sl.bm, v)) ? 1 : 0;
+        if (v != u && member(sl.bm, v)) {
+          ++cnt;
+          const int dv = (v == root) ? 0 : (int)sl.dist[v];
+          cnt_out += dv > row_lvl ? 1 : 0;
+        }
       }
       cnt = warp_sum_i(cnt);
+      cnt_out = warp_sum_i(cnt_out);
       if (lane == 0) {
         atomicAdd(&s_cnt[du], 1);
         atomicAdd(&s_e[0], cnt);
-        if (du <= row_lvl) atomicAdd(&s_e[1], cnt);
+        if (du <= row_lvl) { atomicAdd(&s_e[1], cnt); atomicAdd(&s_e[2], cnt_out); }
       }
     }
     __syncthreads();
@@ -167,6 +172,7 @@ khop_count_kernel(GxGraphDev g, const int32_t* __restrict__ nodes, int count, in
       T.e_d = s_e[0];
       T.npairs = s_e[0] / 2;
       T.e1 = s_e[1];
+      T.npairs_in = (s_e[1] - s_e[2]) / 2 + s_e[2];  // inner-inner pairs are seen from both ends
       T.idx_new = -1;
       T.gt_label = g.label ? g.label[root] : 0;
       T.status = member(sl.bm, root) ? 0 : 1;
