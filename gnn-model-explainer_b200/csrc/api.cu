@@ -4,6 +4,7 @@
 // algorithmic step is a kernel in khop.cu / explain_node.cu.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,7 +52,7 @@ struct LaunchClass {
   int ctas_per_sm;
 };
 // k CTAs per SM share 227 KB (1 KB per CTA is reserved by the system)
-static const LaunchClass kClasses[] = {
+static LaunchClass kClasses[] = {
     {13 * 1024, 128, 16}, {27 * 1024, 256, 8}, {55 * 1024, 256, 4},
     {112 * 1024, 512, 2}, {226 * 1024, 512, 1}, {0, 512, 1}};
 constexpr int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
@@ -100,7 +101,7 @@ namespace {
 int ensure_slot_ws(gx_handle* h) {
   const int64_t N = h->g.N;
   const int W = (int)((N + 31) / 32);
-  int slots = h->num_sms * 4;
+  int slots = h->num_sms * 8;
   const size_t per_slot = (size_t)W * 4 + (size_t)(W + 1) * 4 + (size_t)N + (size_t)(N + 1) * 4 * 2 + (size_t)N * 4 * 2 + 64;
   const size_t budget = (size_t)4 << 30;
   while (slots > 1 && per_slot * slots > budget) slots /= 2;
@@ -191,6 +192,12 @@ int gx_create(int device, gx_handle** out) {
   if (prop.major < 10) {
     gx_set_error("gx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     return GX_ERR_CUDA;
+  }
+  if (const char* env = getenv("GNNX_CLASS_THREADS")) {   // tuning knob: threads per launch class, comma separated
+    int v[kNumClasses], k = 0;
+    const char* p = env;
+    while (*p && k < kNumClasses) { v[k++] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    for (int c = 0; c < k; ++c) if (v[c] >= 32 && v[c] <= 512 && v[c] % 32 == 0) kClasses[c].threads = v[c];
   }
   gx_handle* h = new gx_handle();
   h->device = device;
@@ -422,6 +429,29 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   for (int c = 0; c < kNumClasses; ++c) {
     auto& v = h->class_order[c];
     std::stable_sort(v.begin(), v.end(), [&](int32_t x, int32_t y) { return cost(x) > cost(y); });
+  }
+  {
+    // The batch makespan is the latency of its most expensive tasks (one wave; a 512-thread task is ~15 % slower
+    // when it shares the SM with a second one: profiles/r01d_timeline.md).  The top-K tasks of the 2-per-SM
+    // class therefore run alone on an SM (moved to the 1-per-SM class, which requests the whole shared memory).
+    static int topk = -1;
+    if (topk < 0) { const char* e = getenv("GNNX_EXCLUSIVE_TOPK"); topk = e ? atoi(e) : 12; }
+    auto& two = h->class_order[kNumClasses - 3];
+    auto& one = h->class_order[kNumClasses - 2];
+    // only when the 2-per-SM class really pairs up tasks, and the exclusive SMs still leave everything in one wave
+    int k = 0;
+    if ((int)two.size() > h->num_sms) {
+      k = topk;
+      while (k > 0 && (int)one.size() + k + ((int)two.size() - k + 1) / 2 > (h->num_sms * 17) / 20) --k;
+    }
+    if (k > 0 && (int)two.size() > k) {
+      one.insert(one.end(), two.begin(), two.begin() + k);
+      two.erase(two.begin(), two.begin() + k);
+      std::stable_sort(one.begin(), one.end(), [&](int32_t x, int32_t y) { return cost(x) > cost(y); });
+    }
+  }
+  for (int c = 0; c < kNumClasses; ++c) {
+    auto& v = h->class_order[c];
     order_all.insert(order_all.end(), v.begin(), v.end());
   }
   h->count = count; h->n_hops = n_hops; h->total_n = tn; h->total_e = te;
@@ -574,7 +604,7 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
       // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)
       int need = 0;
       for (int32_t t : h->class_order[c]) need = std::max(need, h->tasks[t].smem_bytes);
-      cfg.smem_bytes = std::max(need, 1024);
+      cfg.smem_bytes = c == kNumClasses - 2 ? kClasses[c].cap_bytes : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
     GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));

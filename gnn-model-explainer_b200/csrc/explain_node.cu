@@ -47,6 +47,14 @@ __device__ __forceinline__ float warp_max(float x) {
   return x;
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Edge-phase arithmetic (2 sigmoids, 2 square roots, 4 divisions per undirected edge and epoch) uses the
+// hardware approximations (ex2/rcp/rsqrt, <= 2 ulp): the phase is instruction-issue bound and IEEE
+// division/sqrt sequences were a third of its instructions.  The row-normalised forward/backward keeps
+// IEEE arithmetic.  Effect on parity: none measurable (tests/test_gpu_parity.py thresholds unchanged).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float adam_delta_fast(float m, float v, float step, float bc2s_inv, float eps) {
+  return step * __fdividef(m, fmaf(__fsqrt_rn(v), bc2s_inv, eps));
+}
 
 // Philox4x32-10 (Salmon et al. 2011), used only for GX_INIT_PHILOX.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -145,15 +153,25 @@ __device__ __forceinline__ float4 group_dense(const float* zrow, int F4, const f
   return acc;
 }
 
-// this lane's float4 slice of  sum_{e in row i, col < col_limit} a[e] * f(src[col[e]])
-template <typename IdxT, bool kRelu>
+// this lane's float4 slice of  sum_{e = r0, r0+estep, .. < r1} a[e] * f(src[col[e]]).  Four edges are kept in
+// flight: the loop is a chain of two dependent shared-memory loads per edge, so without this a lane
+// group waits ~2 LDS latencies per edge (hub rows: thousands of cycles).
+template <typename IdxT, bool kRelu, bool kUnroll>
 __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const IdxT* icol, const float* a,
-                                             const float* src, int src_stride, int q, int col_limit) {
+                                             const float* src, int src_stride, int q) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int e = r0; e < r1; e += estep) {
-    const int c = icol[e];
-    if (c >= col_limit) break;  // columns are partitioned by level: past the limit, all later ones are too
-    float4 v = ld4(src + c * src_stride + 4 * q);
+  int e = r0;
+  if (kUnroll)
+  for (; e + 3 * estep < r1; e += 4 * estep) {
+    const int c0 = icol[e], c1 = icol[e + estep], c2 = icol[e + 2 * estep], c3 = icol[e + 3 * estep];
+    const float a0 = a[e], a1 = a[e + estep], a2 = a[e + 2 * estep], a3 = a[e + 3 * estep];
+    float4 v0 = ld4(src + c0 * src_stride + 4 * q), v1 = ld4(src + c1 * src_stride + 4 * q);
+    float4 v2 = ld4(src + c2 * src_stride + 4 * q), v3 = ld4(src + c3 * src_stride + 4 * q);
+    if (kRelu) { v0 = relu4(v0); v1 = relu4(v1); v2 = relu4(v2); v3 = relu4(v3); }
+    fma4(acc, a0, v0); fma4(acc, a1, v1); fma4(acc, a2, v2); fma4(acc, a3, v3);
+  }
+  for (; e < r1; e += estep) {
+    float4 v = ld4(src + (int)icol[e] * src_stride + 4 * q);
     if (kRelu) v = relu4(v);
     fma4(acc, a[e], v);
   }
@@ -163,18 +181,18 @@ __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const Id
 // A "row task" of a phase: either one long row taken by the whole warp (edges split across the groups,
 // partial sums reduced into group 0 through the scratch) or a chunk of epi short rows, one per group.
 // Returns the row id (or -1) and this lane's float4 of the aggregate; W4 = source width in float4.
-template <typename IdxT, bool kRelu>
+template <typename IdxT, bool kRelu, bool kUnrollShort>
 __device__ __forceinline__ int row_task_gather(int t, int nlong, const IdxT* llist, int R, const Grp& G, int W4,
                                                const IdxT* irp, const IdxT* icol, const float* a,
-                                               const float* src, int src_stride, int col_limit, float* zs,
+                                               const float* src, int src_stride, const IdxT* cnt, float* zs,
                                                float4& z) {
   z = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t < nlong) {
     const int i = llist[t];
-    const int r0 = irp[i], r1 = irp[i + 1];
+    const int r0 = irp[i], r1 = cnt != nullptr ? r0 + (int)cnt[i] : (int)irp[i + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (G.grp < G.epi && G.q < W4)
-      acc = gather_row<IdxT, kRelu>(r0 + G.grp, r1, G.epi, icol, a, src, src_stride, G.q, col_limit);
+      acc = gather_row<IdxT, kRelu, true>(r0 + G.grp, r1, G.epi, icol, a, src, src_stride, G.q);
     st4(zs + G.lane * 4, acc);
     __syncwarp();
     if (G.grp == 0 && G.q < W4) {
@@ -189,9 +207,9 @@ __device__ __forceinline__ int row_task_gather(int t, int nlong, const IdxT* lli
   }
   const int i = (t - nlong) * G.epi + G.grp;
   if (G.grp >= G.epi || i >= R) return -1;
-  const int r0 = irp[i], r1 = irp[i + 1];
+  const int r0 = irp[i], r1 = cnt != nullptr ? r0 + (int)cnt[i] : (int)irp[i + 1];
   if (nlong > 0 && r1 - r0 > kLongRow) return -1;  // taken by a whole warp above
-  if (G.q < W4) z = gather_row<IdxT, kRelu>(r0, r1, 1, icol, a, src, src_stride, G.q, col_limit);
+  if (G.q < W4) z = gather_row<IdxT, kRelu, kUnrollShort>(r0, r1, 1, icol, a, src, src_stride, G.q);
   return i;
 }
 
@@ -200,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ int s_task;
   __shared__ GxLayout sL;
-  __shared__ int s_long[2];  // number of long rows among [0,n2) and among [0,n1)
+  __shared__ int s_long[3];  // number of long rows among [0,n2), among [0,n1), and rows with a long < n1 prefix
   static_assert(HID % 4 == 0 && EMB % 4 == 0, "hidden widths must be multiples of 4");
   constexpr IdxT kNone = IdxTraits<IdxT>::kNone;
   constexpr int HS = HID;            // row stride of the hidden-width arrays
@@ -220,6 +238,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     __syncthreads();
     if (qi >= A.ntasks) break;
     const int task_id = A.order[qi];
+    unsigned long long t_start_ns = 0;
+    if (A.dbg != nullptr && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
     const GxTask* __restrict__ Tp = A.plan.tasks + task_id;
     const int n = Tp->n, n1 = Tp->n1, n2 = Tp->n2, e1 = Tp->e1, np = Tp->npairs_in;  // inner pairs only
     const int gt = Tp->gt_label;
@@ -261,6 +281,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     for (int idx = tid; idx < HID * EMB; idx += nthreads) W3s[idx] = __ldg(m.W[2] + idx);
     for (int idx = tid; idx < HID; idx += nthreads) { bs[idx] = __ldg(m.b[0] + idx); bs[HID + idx] = __ldg(m.b[1] + idx); }
     for (int idx = tid; idx < EMB; idx += nthreads) bs[2 * HID + idx] = __ldg(m.b[2] + idx);
+    if (C * (PD + 1) <= GX_WP_SMEM_MAX) {
+      float* const Wps = base + sL.Wp;
+      for (int idx = tid; idx < C * PD; idx += nthreads) Wps[idx] = __ldg(m.Wp + idx);
+      for (int idx = tid; idx < C; idx += nthreads) Wps[C * PD + idx] = __ldg(m.bp + idx);
+    }
     for (int e = tid; e < e1; e += nthreads) icol[e] = (IdxT)A.plan.icol[edge_off + e];
     for (int i = tid; i <= n2; i += nthreads) irp[i] = (IdxT)A.plan.irowptr[rp_off + i];
     for (int i = tid; i < n; i += nthreads) yv[i] = (float)__ldg(A.g.pred_label + lo2gid[i]);
@@ -317,6 +342,33 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       if (lane == 0) { s_long[0] = cnt; s_long[1] = cnt1; }
     }
     __syncthreads();
+    {  // per row: how many leading columns are < n1 (rows are partitioned by the level of the neighbour)
+      const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
+      const IdxT* const icol = reinterpret_cast<const IdxT*>(base + sL.icol);
+      IdxT* const cnt1 = reinterpret_cast<IdxT*>(base + sL.cnt1);
+      for (int i = tid; i < n2; i += nthreads) {
+        const int r0 = irp[i], r1 = irp[i + 1];
+        int c = 0;
+        while (r0 + c < r1 && (int)icol[r0 + c] < n1) ++c;
+        cnt1[i] = (IdxT)c;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {   // rows whose gradient-carrying prefix is long (hub-adjacent rows)
+      const IdxT* const cnt1 = reinterpret_cast<const IdxT*>(base + sL.cnt1);
+      IdxT* const llistB = reinterpret_cast<IdxT*>(base + sL.llistB);
+      int cnt = 0;
+      for (int b0 = 0; b0 < n2; b0 += 32) {
+        const int i = b0 + lane;
+        const bool lg = i < n2 && (int)cnt1[i] > kLongRow;
+        const uint32_t bal = __ballot_sync(0xffffffffu, lg);
+        if (lg) llistB[cnt + __popc(bal & ((1u << lane) - 1u))] = (IdxT)i;
+        cnt += __popc(bal);
+      }
+      if (lane == 0) s_long[2] = cnt;
+    }
+    __syncthreads();
+    const int nlongB1 = s_long[2];
     const int nlongF1 = s_long[0];  // long rows among [0,n2)
     const int nlongF2 = s_long[1];  // long rows among [0,n1) (a prefix of the list)
 
@@ -330,6 +382,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     const int epi = G.epi, q = G.q;
 
     // ------------------------------------------------------------------ epochs
+    long long tF1 = 0, tF2 = 0, tS = 0, tB2 = 0, tB1 = 0, tP = 0, tl = clock64();
+#define GX_MARK(acc) if (A.dbg != nullptr && warp == 0) { const long long c_ = clock64(); acc += c_ - tl; tl = c_; }
     for (int it = 1; it <= hp.iters; ++it) {
       // ---- F1: rows [0,n2): U = A_m X ; Y1 = (U . sF) W1 + b1 ; row normalise            (models.py:70-78)
       {
@@ -343,7 +397,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const int ntask = nlongF1 + (n2 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
           float4 z;
-          const int i = row_task_gather<IdxT, false>(t, nlongF1, llist, n2, G, D4, irp, icol, a, X, dp, n, zs, z);
+          const int i = row_task_gather<IdxT, false, (NT >= 512)>(t, nlongF1, llist, n2, G, D4, irp, icol, a, X, dp, (const IdxT*)nullptr, zs, z);
           const bool act = i >= 0;
           if (act && q < D4) {
             st4(U + i * dp + 4 * q, z);
@@ -361,6 +415,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
       }
       __syncthreads();
+      GX_MARK(tF1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
       {
         const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
@@ -372,7 +427,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const int ntask = nlongF2 + (n1 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
           float4 z;
-          const int i = row_task_gather<IdxT, true>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, n, zs, z);
+          const int i = row_task_gather<IdxT, true, (NT >= 512)>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, (const IdxT*)nullptr, zs, z);
           const bool act = i >= 0;
           if (act && q < H4) st4(zs + lane * 4, z);
           __syncwarp();
@@ -386,6 +441,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
       }
       __syncthreads();
+      GX_MARK(tF2)
       // ---- S: row r (= level-order id 0): layer 3, readout, softmax, -log p[gt], layer-3 backward
       if (warp == 0) {
         const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
@@ -393,10 +449,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const a = base + sL.a; const float* const Yh1 = base + sL.Yh1; const float* const Yh2 = base + sL.Yh2;
         float* const zs = base + sL.zs; const float* const bs = base + sL.bs; const float* const W3s = base + sL.W3s;
         float* const logit = base + sL.logit; float* const dE = base + sL.dE; float* const dZ3 = base + sL.dZ3;
+        const bool wp_smem = C * (PD + 1) <= GX_WP_SMEM_MAX;
+        const float* const Wpp = wp_smem ? base + sL.Wp : m.Wp;        // pred_model.weight (C, 2h+e)
+        const float* const bpp = wp_smem ? base + sL.Wp + C * PD : m.bp;  // pred_model.bias
         {  // aggregate of row 0 with its edges split across the lane groups
           const int r0 = irp[0], r1 = irp[1];
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (G.grp < epi && q < H4) acc = gather_row<IdxT, true>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q, n);
+          if (G.grp < epi && q < H4) acc = gather_row<IdxT, true, true>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q);
           st4(zs + lane * 4, acc);
         }
         __syncwarp();
@@ -416,12 +475,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float e2v = lane < HID ? fmaxf(Yh2[lane], 0.f) : 0.f;  // row 0 of H2
         // logits = pred_model(concat) (models.py:260,375), softmax over classes (explain.py:714)
         for (int c = 0; c < C; ++c) {
-          const float* wp = m.Wp + c * PD;
+          const float* wp = Wpp + c * PD;
           float t = 0.f;
-          if (lane < HID) t = fmaf(e1v, __ldg(wp + lane), fmaf(e2v, __ldg(wp + HID + lane), t));
-          if (lane < EMB) t = fmaf(yh3, __ldg(wp + 2 * HID + lane), t);
+          if (lane < HID) t = fmaf(e1v, wp[lane], fmaf(e2v, wp[HID + lane], t));
+          if (lane < EMB) t = fmaf(yh3, wp[2 * HID + lane], t);
           t = warp_sum(t);
-          if (lane == 0) logit[c] = t + __ldg(m.bp + c);
+          if (lane == 0) logit[c] = t + bpp[c];
         }
         __syncwarp();
         float mx = -INFINITY;
@@ -437,9 +496,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float d1 = 0.f, d2 = 0.f, d3 = 0.f;
         for (int c = 0; c < C; ++c) {
           const float gc = logit[c];
-          const float* wp = m.Wp + c * PD;
-          if (lane < HID) { d1 = fmaf(gc, __ldg(wp + lane), d1); d2 = fmaf(gc, __ldg(wp + HID + lane), d2); }
-          if (lane < EMB) d3 = fmaf(gc, __ldg(wp + 2 * HID + lane), d3);
+          const float* wp = Wpp + c * PD;
+          if (lane < HID) { d1 = fmaf(gc, wp[lane], d1); d2 = fmaf(gc, wp[HID + lane], d2); }
+          if (lane < EMB) d3 = fmaf(gc, wp[2 * HID + lane], d3);
         }
         if (lane < HID) { dE[lane] = d1; dE[HS + lane] = d2; }
         // backward of y/max(|y|,eps): dY = (dYh - Yh <Yh,dYh>)/q ; dZ3 = dY3 W3^T
@@ -451,6 +510,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         if (lane < HID) dZ3[lane] = dot_v4(zs, W3s + lane * EMB, EMB / 4);
       }
       __syncthreads();
+      GX_MARK(tS)
       // ---- B2: rows {r} U N(r): dYh2 = dEmb2 (row r) + a[r,j] dZ3 (j in N(r)), relu', normalise', dZ2 = dY2 W2^T
       {
         const IdxT* const irp = reinterpret_cast<const IdxT*>(base + sL.irp);
@@ -495,6 +555,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
       }
       __syncthreads();
+      GX_MARK(tB2)
       // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise',
       //          dZ1 = dY1 W1^T, dL/dsF partial, dZ1 (.) sF kept for the edge dots
       {
@@ -503,13 +564,15 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const a = base + sL.a; const float* const dZ2 = base + sL.dZ2; const float* const dE = base + sL.dE;
         const float* const Yh1 = base + sL.Yh1; const float* const q1 = base + sL.q1; const float* const W1t = base + sL.W1t;
         const float* const U = base + sL.U; const float* const sF = base + sL.sF;
+        const IdxT* const cnt1 = reinterpret_cast<const IdxT*>(base + sL.cnt1);
+        const IdxT* const llistB = reinterpret_cast<const IdxT*>(base + sL.llistB);
         float* const dZ1s = base + sL.U;  // row i of U is consumed (dL/dsF) right before dZ1[i] (.) sF overwrites it
         float* const gFp = base + sL.gFp; float* const zs = base + sL.zs + warp * 128;
         float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int ntask = (n2 + epi - 1) / epi;
+        const int ntask = nlongB1 + (n2 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
           float4 dh;
-          const int i = row_task_gather<IdxT, false>(t, 0, (const IdxT*)nullptr, n2, G, H4, irp, icol, a, dZ2, HS, n1, zs, dh);
+          const int i = row_task_gather<IdxT, false, false>(t, nlongB1, llistB, n2, G, H4, irp, icol, a, dZ2, HS, cnt1, zs, dh);
           const bool act = i >= 0;
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
           if (act && q < H4) {
@@ -549,6 +612,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         __syncwarp();
       }
       __syncthreads();
+      GX_MARK(tB1)
       if (A.dbg != nullptr && it == 1 && qi == 0) {   // debug: [header 16 floats][whole task slab]
         if (tid == 0) {
           A.dbg[0] = (float)sL.total_words; A.dbg[1] = (float)sL.X; A.dbg[2] = (float)sL.U; A.dbg[3] = (float)sL.Yh1;
@@ -575,7 +639,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)blockIdx.x * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
         float* const a = base + sL.a;
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
-        const float step = tab.x, bc2s = tab.y;
+        const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
         const bool last = (it == hp.iters);
         // feature mask: dL/dF = sF(1-sF) (sum_i dZ1[i] U[i] + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
         for (int f = tid; f < d; f += nthreads) {
@@ -610,9 +674,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
           v2.x = v2.x * hp.b2 + hp.one_minus_b2 * gi * gi;
           v2.y = v2.y * hp.b2 + hp.one_minus_b2 * gj * gj;
-          Mv.x = Mv.x - step * (m2.x / (sqrtf(v2.x) / bc2s + hp.eps));
-          Mv.y = Mv.y - step * (m2.y / (sqrtf(v2.y) / bc2s + hp.eps));
-          const float2 Sn = make_float2(sigmoid_f(Mv.x), sigmoid_f(Mv.y));
+          Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s_inv, hp.eps);
+          Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s_inv, hp.eps);
+          const float2 Sn = make_float2(sigmoid_fast(Mv.x), sigmoid_fast(Mv.y));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
           const IdxT pa = ppij[p], pb = ppji[p];
@@ -625,6 +689,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
       }
       __syncthreads();
+      GX_MARK(tP)
+    }
+    if (A.dbg != nullptr && tid == 0 && qi == 0) {
+      float* o = A.dbg + (1 << 19);
+      o[0] = (float)tF1; o[1] = (float)tF2; o[2] = (float)tS; o[3] = (float)tB2; o[4] = (float)tB1; o[5] = (float)tP;
+      o[6] = (float)n; o[7] = (float)n1; o[8] = (float)n2; o[9] = (float)np; o[10] = (float)e1; o[11] = (float)nthreads;
+    }
+    if (A.dbg != nullptr && tid == 0) {
+      unsigned long long t_end_ns; unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* tl64 = reinterpret_cast<unsigned long long*>(A.dbg + (1 << 19) + 64);
+      tl64[3 * task_id + 0] = t_start_ns; tl64[3 * task_id + 1] = t_end_ns; tl64[3 * task_id + 2] = ((unsigned long long)smid << 32) | (unsigned)nthreads;
     }
     if (A.out_feat != nullptr) {
       const float* const sF = base + sL.sF;
@@ -672,10 +749,11 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
         mj = mj + (gj - mj) * hp.one_minus_b1;
         vi = vi * hp.b2 + hp.one_minus_b2 * gi * gi;
         vj = vj * hp.b2 + hp.one_minus_b2 * gj * gj;
-        Mi = Mi - tab.x * (mi / (sqrtf(vi) / tab.y + hp.eps));
-        Mj = Mj - tab.x * (mj / (sqrtf(vj) / tab.y + hp.eps));
-        Si = sigmoid_f(Mi);
-        Sj = sigmoid_f(Mj);
+        const float bc2s_inv = 1.0f / tab.y;
+        Mi = Mi - adam_delta_fast(mi, vi, tab.x, bc2s_inv, hp.eps);
+        Mj = Mj - adam_delta_fast(mj, vj, tab.x, bc2s_inv, hp.eps);
+        Si = sigmoid_fast(Mi);
+        Sj = sigmoid_fast(Mj);
       }
       const float an = 0.5f * (Si + Sj);
       out_mask[edge_off + oij] = an;

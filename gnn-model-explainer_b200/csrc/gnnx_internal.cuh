@@ -8,6 +8,7 @@
 
 #define GX_MAX_LEVELS 8  // n_hops <= 7
 #define GX_NONE16 0xFFFFu
+#define GX_WP_SMEM_MAX 2048  // floats: pred_model (C x (2h+e) + C) is kept in shared memory up to this size
 
 // One explained node ("task").  Counts are produced by khop_count_kernel, offsets by the host
 // prefix sums, the packed arrays by khop_fill_kernel.
@@ -86,9 +87,9 @@ __host__ __device__ inline int gx_round_up(int x, int m) { return (x + m - 1) / 
 
 struct GxLayout {
   // float arrays (offsets in 4-byte words)
-  int X, U, Yh1, q1, Yh2, q2, dZ2, a, y, W1s, W1t, W2s, W2t, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit;
+  int X, U, Yh1, q1, Yh2, q2, dZ2, a, y, W1s, W1t, W2s, W2t, W3s, bs, sF, F, mF, vF, gFp, zs, dE, dZ3, logit, Wp;
   // index arrays (offsets in 4-byte words; element type IdxT)
-  int icol, irp, pi, pj, ppij, ppji, llist;
+  int icol, irp, pi, pj, ppij, ppji, llist, cnt1, llistB;
   int total_words;
   int dp;
 };
@@ -130,6 +131,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.dE = takef(2 * hid);
   L.dZ3 = takef(hid);
   L.logit = takef(C < 32 ? 32 : C);
+  L.Wp = takef(C * (2 * hid + emb + 1) <= GX_WP_SMEM_MAX ? C * (2 * hid + emb + 1) : 0);  // pred_model weights + bias when small
   L.icol = takei(e1);
   L.irp = takei(n2 + 1);
   L.pi = takei(np_in);
@@ -137,6 +139,8 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.ppij = takei(np_in);
   L.ppji = takei(np_in);
   L.llist = takei(n2);
+  L.cnt1 = takei(n2);        // per row: number of leading columns < n1 (the only ones that carry dZ2)
+  L.llistB = takei(n2);      // rows whose < n1 prefix is long (split across a whole warp in the backward)
   L.total_words = o;
   return L;
 }
