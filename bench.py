@@ -295,11 +295,16 @@ def main_ours(a):
             peaks = json.load(open(pk))
             peak_hbm, peak_src = float(peaks.get("hbm_gbs", 6650.0)), "measured"
         achieved = algo_bytes_step / (kern_ms / 1e3) / 1e9
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram__bytes_read+write of the explainer kernels of one step (ncu)
+        if os.path.exists(tj):
+            traffic = float(json.load(open(tj))["traffic_bytes_per_step"])
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak_hbm, "unit": "GB/s", "frac": achieved / peak_hbm,
-                "traffic": None, "peak_source": peak_src, "kernel": "explain_node_kernel (5 size classes, concurrent streams)",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "explain_node_kernel (one launch per size class, concurrent streams) + outer_pairs_kernel",
                 "kernel_ms_per_step": kern_ms, "algorithmic_bytes_per_step": algo_bytes_step,
-                "note": "shared-memory-resident kernel: the algorithmic bytes (SURVEY 8d: 84*E_d+8*n*d per node-epoch) are "
-                        "served from SMEM, not HBM; compulsory HBM traffic is ~one read of the subgraph + one write of the mask"}
+                "note": "shared-memory-resident kernel: the algorithmic bytes (SURVEY 8d: 84*E_d+8*n*d per node-epoch, x100 epochs, "
+                        "summed over the 700 nodes) are served from SMEM; measured DRAM traffic (ncu) is the compulsory one-time read of "
+                        "the subgraphs; the kernel is latency bound (DESIGN.md 6)"}
         cpu = None
         if world == 1 and not a.no_cpu:
             # separate process: the CPU pool must fork before torch/CUDA exist in the parent
