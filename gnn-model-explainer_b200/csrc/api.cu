@@ -91,6 +91,14 @@ struct gx_handle {
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
   GxPlanArrays plan{};
+  // graph-classification mode
+  bool has_batch = false, has_gplan = false;
+  GxGraphBatchDev gb{};
+  DevBuf gb_rowptr, gb_col, gb_feat, gb_label;
+  std::vector<int32_t> gb_h_rowptr, gb_h_label;
+  int g_count = 0;
+  int64_t g_total_e = 0;
+  int g_max_smem = 0, g_max_np = 0;
   // slot workspace
   DevBuf ws_buf;
   GxSlotWs ws{};
@@ -219,7 +227,7 @@ int gx_destroy(gx_handle* h) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&h->g_rowptr, &h->g_col, &h->g_feat, &h->g_label, &h->g_pred, &h->m_buf, &h->d_nodes,
                     &h->d_tasks, &h->d_nbrs, &h->d_lo2gid, &h->d_srp, &h->d_scol, &h->d_irp, &h->d_icol,
-                    &h->d_pairs, &h->d_order, &h->d_counters, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
+                    &h->d_pairs, &h->d_order, &h->d_counters, &h->gb_rowptr, &h->gb_col, &h->gb_feat, &h->gb_label, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
                     &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < kNumStreams; ++i) {
@@ -391,6 +399,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     if (nodes[t] < 0 || nodes[t] >= h->g.N) { gx_set_error("gx_plan_nodes: node %d out of range [0,%lld)", nodes[t], (long long)h->g.N); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   h->has_plan = false;
+  h->has_gplan = false;
   int rc = ensure_slot_ws(h);
   if (rc != GX_OK) return rc;
   GX_CUDA_CHECK(h->d_nodes.reserve((size_t)count * 4));
@@ -616,6 +625,164 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
   GX_CUDA_CHECK(gx_launch_outer_pairs(hd, h->g, h->plan, count, m0_dev, out_dev, h->stream));
   h->launches += 1;
   for (int c : used) GX_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_join[c], 0));
+  GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
+  h->timed = true;
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(edge_mask, out_dev, (size_t)te * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (feat_mask) GX_CUDA_CHECK(cudaMemcpyAsync(feat_mask, feat_dev, (size_t)count * h->m.d * 4, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return GX_OK;
+}
+
+int gx_set_graph_batch_csr(gx_handle* h, int32_t G, int32_t max_nodes, const int32_t* rowptr, const int32_t* col,
+                           const float* feat, int32_t d, const int32_t* label) {
+  if (!h || !rowptr || !col || !feat || !label) { gx_set_error("gx_set_graph_batch_csr: NULL argument"); return GX_ERR_INVALID; }
+  if (G < 1 || max_nodes < 1 || max_nodes > 4096) { gx_set_error("gx_set_graph_batch_csr: num_graphs/max_nodes out of range (max_nodes <= 4096)"); return GX_ERR_INVALID; }
+  const int64_t R = (int64_t)G * max_nodes;
+  if (rowptr[0] != 0) { gx_set_error("gx_set_graph_batch_csr: rowptr[0] != 0"); return GX_ERR_INVALID; }
+  for (int64_t r = 0; r < R; ++r) {
+    if (rowptr[r + 1] < rowptr[r]) { gx_set_error("gx_set_graph_batch_csr: rowptr not monotone"); return GX_ERR_INVALID; }
+    const int64_t g0 = r / max_nodes * max_nodes;
+    const int32_t i = (int32_t)(r - g0);
+    for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+      const int32_t j = col[e];
+      if (j < 0 || j >= max_nodes) { gx_set_error("gx_set_graph_batch_csr: col out of range"); return GX_ERR_INVALID; }
+      if (e > rowptr[r] && col[e] <= col[e - 1]) { gx_set_error("gx_set_graph_batch_csr: columns not strictly ascending"); return GX_ERR_INVALID; }
+      if (j == i) { gx_set_error("gx_set_graph_batch_csr: self loops are not supported in graph mode"); return GX_ERR_UNSUPPORTED; }
+      if (!std::binary_search(col + rowptr[g0 + j], col + rowptr[g0 + j + 1], i)) { gx_set_error("gx_set_graph_batch_csr: adjacency not symmetric"); return GX_ERR_UNSUPPORTED; }
+    }
+  }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int64_t nnz = rowptr[R];
+  GX_CUDA_CHECK(h->gb_rowptr.reserve((size_t)(R + 1) * 4));
+  GX_CUDA_CHECK(h->gb_col.reserve((size_t)std::max<int64_t>(nnz, 1) * 4));
+  GX_CUDA_CHECK(h->gb_feat.reserve((size_t)R * d * 4));
+  GX_CUDA_CHECK(h->gb_label.reserve((size_t)G * 4));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->gb_rowptr.p, rowptr, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->gb_col.p, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->gb_feat.p, feat, (size_t)R * d * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->gb_label.p, label, (size_t)G * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->gb_h_rowptr.assign(rowptr, rowptr + R + 1);
+  h->gb_h_label.assign(label, label + G);
+  h->gb.num_graphs = G; h->gb.max_nodes = max_nodes; h->gb.d = d;
+  h->gb.rowptr = h->gb_rowptr.as<int32_t>(); h->gb.col = h->gb_col.as<int32_t>();
+  h->gb.feat = h->gb_feat.as<float>(); h->gb.label = h->gb_label.as<int32_t>();
+  h->has_batch = true; h->has_gplan = false;
+  return GX_OK;
+}
+
+int gx_plan_graphs(gx_handle* h, const int32_t* graph_ids, int32_t count, int64_t* edge_off, int64_t* total_edges) {
+  if (!h || !graph_ids) { gx_set_error("gx_plan_graphs: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_batch || !h->has_model) { gx_set_error("gx_plan_graphs: call gx_set_model and gx_set_graph_batch_csr first"); return GX_ERR_INVALID; }
+  if (h->gb.d != h->m.d) { gx_set_error("gx_plan_graphs: feat_dim %d != model input_dim %d", h->gb.d, h->m.d); return GX_ERR_INVALID; }
+  if (count <= 0) { gx_set_error("gx_plan_graphs: count <= 0"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  h->has_gplan = false; h->has_plan = false;
+  const int nf = h->gb.max_nodes;
+  h->tasks.assign(count, GxTask());
+  int64_t tn = 0, te = 0, tp = 0;
+  int max_smem = 0, max_np = 0;
+  const int nwarps = 128 / 32;
+  for (int t = 0; t < count; ++t) {
+    const int g = graph_ids[t];
+    if (g < 0 || g >= h->gb.num_graphs) { gx_set_error("gx_plan_graphs: graph %d out of range", g); return GX_ERR_INVALID; }
+    const int32_t* rp = h->gb_h_rowptr.data() + (int64_t)g * nf;
+    GxTask& T = h->tasks[t];
+    memset(&T, 0, sizeof(T));
+    int na = 0;
+    for (int i = 0; i < nf; ++i) na += rp[i + 1] > rp[i] ? 1 : 0;
+    T.node = g; T.n = na; T.n1 = na; T.n2 = na;
+    T.e_d = rp[nf] - rp[0]; T.e1 = T.e_d; T.npairs = T.e_d / 2; T.npairs_in = T.npairs;
+    T.gt_label = h->gb_h_label[g]; T.n_norm = nf; T.flags = na < nf ? 1 : 0;
+    T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
+    if (na >= 65535 || T.e_d >= 65535) { gx_set_error("gx_plan_graphs: graph %d too large for the shared-memory kernel", g); return GX_ERR_UNSUPPORTED; }
+    const GxLayoutG L = gx_make_layout_graph(na, T.e_d, T.npairs, h->m.d, h->m.hid, h->m.emb, h->m.C, nwarps);
+    T.smem_bytes = L.total_words * 4;
+    if (T.smem_bytes > 226 * 1024) { gx_set_error("gx_plan_graphs: graph %d needs %d bytes of shared memory", g, T.smem_bytes); return GX_ERR_UNSUPPORTED; }
+    max_smem = std::max(max_smem, T.smem_bytes); max_np = std::max(max_np, T.npairs);
+    tn += na; te += T.e_d; tp += T.npairs;
+  }
+  std::vector<int32_t> order(count);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h->tasks[x].e_d + 4 * h->tasks[x].n > h->tasks[y].e_d + 4 * h->tasks[y].n; });
+  GX_CUDA_CHECK(h->d_tasks.reserve((size_t)count * sizeof(GxTask)));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), (size_t)count * sizeof(GxTask), cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(h->d_order.reserve((size_t)count * 4));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_order.p, order.data(), (size_t)count * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(h->d_counters.reserve(kNumClasses * 4));
+  GX_CUDA_CHECK(h->d_lo2gid.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
+  GX_CUDA_CHECK(h->d_irp.reserve((size_t)(tn + count) * 4));
+  GX_CUDA_CHECK(h->d_icol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+  GX_CUDA_CHECK(h->d_pairs.reserve((size_t)std::max<int64_t>(tp, 1) * 4 * 6));
+  h->plan = GxPlanArrays();
+  h->plan.tasks = h->d_tasks.as<GxTask>();
+  h->plan.lo2gid = h->d_lo2gid.as<int32_t>();
+  h->plan.irowptr = h->d_irp.as<int32_t>();
+  h->plan.icol = h->d_icol.as<int32_t>();
+  int32_t* pb = h->d_pairs.as<int32_t>();
+  h->plan.pair_i = pb; h->plan.pair_j = pb + tp; h->plan.pair_pij = pb + 2 * tp;
+  h->plan.pair_pji = pb + 3 * tp; h->plan.pair_oij = pb + 4 * tp; h->plan.pair_oji = pb + 5 * tp;
+  GX_CUDA_CHECK(gx_launch_graph_plan(h->gb, count, h->plan, h->stream));
+  h->launches += 1;
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->g_count = count; h->g_total_e = te; h->g_max_smem = max_smem; h->g_max_np = max_np;
+  h->count = count; h->total_e = te;
+  h->has_gplan = true;
+  if (edge_off) { for (int t = 0; t < count; ++t) edge_off[t] = h->tasks[t].edge_off; edge_off[count] = te; }
+  if (total_edges) *total_edges = te;
+  return GX_OK;
+}
+
+int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
+                      float* edge_mask, float* feat_mask) {
+  if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_graphs: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_gplan) { gx_set_error("gx_explain_graphs: no plan (call gx_plan_graphs)"); return GX_ERR_INVALID; }
+  if (hp->mask_act != 0 || hp->mask_bias != 0) { gx_set_error("gx_explain_graphs: mask_act/mask_bias variants are not built"); return GX_ERR_UNSUPPORTED; }
+  if (hp->num_epochs < 1) { gx_set_error("gx_explain_graphs: num_epochs < 1"); return GX_ERR_INVALID; }
+  if (hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_graphs: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int count = h->g_count;
+  const int64_t te = h->g_total_e;
+  const int iters = hp->num_epochs - 1;
+  std::vector<float2> tab(std::max(iters, 1));
+  for (int t = 1; t <= iters; ++t) {
+    tab[t - 1].x = (float)((double)hp->lr / (1.0 - std::pow((double)hp->beta1, (double)t)));
+    tab[t - 1].y = (float)std::sqrt(1.0 - std::pow((double)hp->beta2, (double)t));
+  }
+  GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_adam.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  const float* m0_dev = nullptr; float* out_dev = nullptr; float* feat_dev = nullptr;
+  if (space == GX_DEVICE) { m0_dev = m0_edges; out_dev = edge_mask; feat_dev = feat_mask; }
+  else {
+    if (hp->init == GX_INIT_M0) {
+      GX_CUDA_CHECK(h->d_m0.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+      GX_CUDA_CHECK(cudaMemcpyAsync(h->d_m0.p, m0_edges, (size_t)te * 4, cudaMemcpyHostToDevice, h->stream));
+      m0_dev = h->d_m0.as<float>();
+    }
+    GX_CUDA_CHECK(h->d_out.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+    out_dev = h->d_out.as<float>();
+    if (feat_mask) { GX_CUDA_CHECK(h->d_feat.reserve((size_t)count * h->m.d * 4)); feat_dev = h->d_feat.as<float>(); }
+  }
+  GxHparamsDev hd;
+  hd.iters = iters; hd.one_minus_b1 = 1.0f - hp->beta1; hd.b2 = hp->beta2; hd.one_minus_b2 = 1.0f - hp->beta2; hd.eps = hp->eps;
+  hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = 0.f;
+  hd.adam_tab = h->d_adam.as<float2>(); hd.init = hp->init; hd.seed = hp->seed;
+  GxExplainLaunch cfg;
+  cfg.order = h->d_order.as<int32_t>(); cfg.ntasks = count; cfg.counter = h->d_counters.as<int32_t>();
+  cfg.smem_bytes = std::max(h->g_max_smem, 1024);
+  cfg.threads = 128;
+  const int per_sm = std::max(1, std::min(16, (227 * 1024) / (cfg.smem_bytes + 1024)));
+  cfg.grid = std::min(count, h->num_sms * per_sm);
+  cfg.idx16 = 1; cfg.gws = nullptr; cfg.gws_stride_words = 0; cfg.dbg = nullptr;
+  cfg.pws_stride_words = ((int64_t)h->g_max_np * 8 + 3) / 4 * 4;
+  GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(cfg.pws_stride_words * cfg.grid, 4) * 4));
+  cfg.pws = h->d_pws.as<float>();
+  GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
+  GX_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->stream));
+  GX_CUDA_CHECK(gx_launch_explain_graphs(cfg, h->gb, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->stream));
+  h->launches += 1;
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
   h->timed = true;
   if (space == GX_HOST) {

@@ -23,6 +23,8 @@ struct GxTask {
   int32_t n1, n2;   // level-order prefix sizes: |dist<=L-2|, |dist<=L-1| for L=3 -> |dist<=1|, |dist<=2|
   int32_t e1;       // directed entries whose source row is < n2 (what the forward ever gathers)
   int32_t status;   // 0 ok; 1 node not inside its own neighbourhood
+  int32_t n_norm;   // the n of the reference's dense tensors (1/n^2 factors, M0 std): n in node mode, max_nodes in graph mode
+  int32_t flags;    // graph mode: bit 0 = some row of the padded graph has no edge (its constant embedding joins the max-pool)
   int32_t cum[GX_MAX_LEVELS + 1];  // cum[t] = #nodes with dist <= t (dist measured from `node`)
   int32_t smem_bytes;              // shared-memory footprint of this task in the explainer kernel
   int64_t node_off;  // into nbrs / lo2gid
@@ -145,6 +147,43 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   return L;
 }
 
+// Shared-memory footprint of one graph-mode task (all `na` rows with at least one edge are computed at every layer).
+struct GxLayoutG {
+  int X, U, Yh1, Yh2, Yh3, q, dZ2, dZ3, a, W1s, W1t, W2s, W2t, W3s, W3t, bs, cst, emb, dE, sF, F, mF, vF, gFp, zs, logit, Wp;
+  int arg, icol, irp, pi, pj, ppij, ppji;
+  int total_words;
+  int dp;
+};
+__host__ __device__ inline GxLayoutG gx_make_layout_graph(int na, int e_d, int np, int d, int hid, int emb, int C, int nwarps) {
+  GxLayoutG L;
+  const int dp = gx_round_up(d, 4);
+  L.dp = dp;
+  int o = 0;
+  auto takef = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
+  auto takei = [&](int elems) { int r = o; o += gx_round_up((elems * 2 + 3) / 4, 4); return r; };
+  L.X = takef(na * dp); L.U = takef(na * dp);
+  L.Yh1 = takef(na * hid); L.Yh2 = takef(na * hid); L.Yh3 = takef(na * emb);
+  L.q = takef(3 * na);
+  L.dZ2 = takef(na * hid); L.dZ3 = takef(na * hid);
+  L.a = takef(e_d);
+  L.W1s = takef(dp * hid); L.W1t = takef(hid * dp); L.W2s = takef(hid * hid); L.W2t = takef(hid * hid);
+  L.W3s = takef(hid * emb); L.W3t = takef(emb * hid);
+  L.bs = takef(2 * hid + emb);
+  L.cst = takef(2 * hid + emb);   // embedding of an edge-less row: relu(normalize(b_l)) / normalize(b_3)
+  L.emb = takef(2 * hid + emb);
+  L.dE = takef(2 * hid + emb);
+  L.sF = takef(dp); L.F = takef(dp); L.mF = takef(dp); L.vF = takef(dp);
+  L.gFp = takef(nwarps * dp);
+  L.zs = takef(nwarps * 128);
+  L.logit = takef(C < 32 ? 32 : C);
+  L.Wp = takef(C * (2 * hid + emb + 1) <= GX_WP_SMEM_MAX ? C * (2 * hid + emb + 1) : 0);
+  L.arg = takef(2 * hid + emb);   // int: arg-max row of every pooled feature (-1: the edge-less constant)
+  L.icol = takei(e_d); L.irp = takei(na + 1);
+  L.pi = takei(np); L.pj = takei(np); L.ppij = takei(np); L.ppji = takei(np);
+  L.total_words = o;
+  return L;
+}
+
 // ---------------------------------------------------------------------------------------------
 #define GX_CUDA_CHECK(expr)                                                          \
   do {                                                                               \
@@ -196,6 +235,17 @@ cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, c
                               const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                               float* out_mask, float* out_feat, cudaStream_t s);
 int gx_explain_max_smem();
+struct GxGraphBatchDev {
+  int32_t num_graphs, max_nodes, d;
+  const int32_t* rowptr;  // [G*max_nodes+1], global edge offsets
+  const int32_t* col;     // node id within the graph
+  const float* feat;      // [G*max_nodes*d]
+  const int32_t* label;   // [G]
+};
+cudaError_t gx_launch_graph_plan(const GxGraphBatchDev& gb, int count, GxPlanArrays plan, cudaStream_t s);
+cudaError_t gx_launch_explain_graphs(const GxExplainLaunch& cfg, const GxGraphBatchDev& gb, const GxModelDev& m,
+                                     const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0, float* out_mask,
+                                     float* out_feat, cudaStream_t s);
 cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
                                   const float* m0, float* out_mask, cudaStream_t s);
 cudaError_t gx_launch_densify(const GxPlanArrays& plan, int count, const int64_t* dense_off,

@@ -184,6 +184,8 @@ khop_count_kernel(GxGraphDev g, const int32_t* __restrict__ nodes, int count, in
       T.n2 = T.cum[row_lvl];
       T.n1 = row_lvl >= 1 ? T.cum[row_lvl - 1] : 0;
       T.smem_bytes = 0;
+      T.n_norm = tail - 1;
+      T.flags = 0;
       T.node_off = T.edge_off = T.pair_off = T.rp_off = 0;
       tasks[t] = T;
     }

@@ -15,6 +15,7 @@ EXPORTS = [
     "gx_default_hparams", "gx_last_error", "gx_version", "gx_create", "gx_destroy", "gx_set_stream",
     "gx_sync", "gx_set_model", "gx_set_graph_csr", "gx_neighborhood_rows", "gx_plan_nodes",
     "gx_plan_fetch", "gx_explain_nodes", "gx_densify", "gx_launch_count", "gx_last_explain_ms",
+    "gx_set_graph_batch_csr", "gx_plan_graphs", "gx_explain_graphs",
 ]
 
 
@@ -64,6 +65,9 @@ def lib():
     L.gx_plan_fetch.argtypes = [vp, i64p, i64p, i32p, i32p, i32p, i32p]
     L.gx_explain_nodes.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, f32p, f32p]
     L.gx_densify.argtypes = [vp, C.c_int, f32p, vp]
+    L.gx_set_graph_batch_csr.argtypes = [vp, C.c_int32, C.c_int32, i32p, i32p, f32p, C.c_int32, i32p]
+    L.gx_plan_graphs.argtypes = [vp, i32p, C.c_int32, i64p, C.POINTER(C.c_int64)]
+    L.gx_explain_graphs.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, f32p, f32p]
     L.gx_launch_count.argtypes = [vp]
     L.gx_launch_count.restype = C.c_int64
     L.gx_last_explain_ms.argtypes = [vp, C.POINTER(C.c_float)]

@@ -150,6 +150,42 @@ class Engine:
         self._plan = Plan(np.asarray(nodes), node_off, edge_off, nbrs, idx_new, srp, scol)
         return self._plan
 
+    # ---------------------------------------------------------------- graph-classification mode
+    def set_graph_batch(self, adj, feat, label):
+        """adj (G,n,n) 0/1 symmetric, feat (G,n,d), label (G,): the padded batch of Explainer(graph_mode=True)."""
+        adj = np.asarray(adj)
+        G, n, _ = adj.shape
+        gi, ri, ci = np.nonzero(adj)
+        if gi.size and not np.all(adj[gi, ri, ci] == 1):
+            raise NotImplementedError("weighted adjacency is not built (reference datasets are 0/1)")
+        rowptr = np.zeros(G * n + 1, dtype=np.int64)
+        np.add.at(rowptr, gi * n + ri + 1, 1)
+        rowptr = np.cumsum(rowptr).astype(np.int32)
+        col = _i32c(ci)
+        feat = _f32c(np.asarray(feat).reshape(G * n, -1))
+        label = _i32c(np.asarray(label).reshape(G))
+        _abi.check(self._lib.gx_set_graph_batch_csr(self._h, G, n, _np_ptr(rowptr), _np_ptr(col), _np_ptr(feat),
+                                                    feat.shape[1], _np_ptr(label)))
+        self.batch_rowptr, self.batch_col, self.batch_G, self.batch_n = rowptr, col, G, n
+
+    def plan_graphs(self, graph_ids):
+        gids = _i32c(graph_ids)
+        edge_off = np.empty(len(gids) + 1, np.int64)
+        te = C.c_int64()
+        _abi.check(self._lib.gx_plan_graphs(self._h, _np_ptr(gids), len(gids), _np_ptr(edge_off), C.byref(te)))
+        return edge_off
+
+    def graph_rows_cols(self, g):
+        """(rows, cols) of graph g's adjacency entries in slot (row-major) order."""
+        n = self.batch_n
+        rp = self.batch_rowptr[g * n: (g + 1) * n + 1]
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+        return rows, self.batch_col[rp[0]:rp[-1]].astype(np.int64)
+
+    def explain_graphs_host(self, hp, m0_edges, edge_mask_out, feat_mask_out=None):
+        _abi.check(self._lib.gx_explain_graphs(self._h, C.byref(hp), _abi.GX_HOST, _np_ptr(m0_edges),
+                                               _np_ptr(edge_mask_out), _np_ptr(feat_mask_out)))
+
     # ---------------------------------------------------------------- hot path
     def make_hparams(self, num_epochs=100, lr=0.1, init=_abi.GX_INIT_M0, seed=0, **over):
         hp = _abi.GxHparams()

@@ -85,8 +85,6 @@ class Explainer:
         self.writer = writer
         self.print_training = print_training
         self._neighborhoods = None
-        if graph_mode:
-            raise NotImplementedError("graph-classification mode (explain_graphs) is the next scope row")
         if getattr(args, "mask_act", "sigmoid") != "sigmoid":
             raise NotImplementedError("mask_act=%r is not built (default: sigmoid)" % args.mask_act)
         if getattr(args, "mask_bias", False):
@@ -101,6 +99,12 @@ class Explainer:
         weights, num_layers = model_weights(model)
         self.engine.set_model(weights, num_layers=num_layers)
         adj_np = np.asarray(adj)
+        if graph_mode:
+            # graph classification: the whole padded batch goes to the device once (explain.py:80-85)
+            if adj_np.ndim != 3:
+                raise ValueError("graph mode expects adj of shape (G,n,n)")
+            self.engine.set_graph_batch(adj_np, np.asarray(feat), np.asarray(label))
+            return
         if adj_np.ndim != 3 or adj_np.shape[0] != 1:
             raise NotImplementedError("node mode expects adj of shape (1,N,N) (single graph)")
         self._rowptr, self._col = _gu.csr_from_dense(adj_np[0])
@@ -179,10 +183,52 @@ class Explainer:
         return fname
 
     # ---------------------------------------------------------------- public API
+    def _explain_graph_batch(self, graph_indices):
+        gids = [int(g) for g in graph_indices]
+        edge_off = self.engine.plan_graphs(gids)
+        hp, init = self._hparams()
+        n = self.engine.batch_n
+        m0 = None
+        rc = [self.engine.graph_rows_cols(g) for g in gids]
+        if init == "torch":
+            m0 = np.empty(int(edge_off[-1]), dtype=np.float32)
+            std = torch.nn.init.calculate_gain("relu") * math.sqrt(2.0 / (n + n))
+            for t, (rows, cols) in enumerate(rc):
+                M = torch.FloatTensor(n, n).normal_(1.0, std).numpy()      # explain.py:645-652, n = padded size
+                m0[edge_off[t]:edge_off[t + 1]] = M[rows, cols]
+        edge_mask = np.empty(int(edge_off[-1]), dtype=np.float32)
+        self.engine.explain_graphs_host(hp, m0, edge_mask)
+        out = []
+        for t, (rows, cols) in enumerate(rc):
+            D = np.zeros((n, n), dtype=np.float64)
+            D[rows, cols] = edge_mask[edge_off[t]:edge_off[t + 1]]
+            out.append(D)
+        return out
+
+    def explain_graphs(self, graph_indices, save=True):
+        """explain.py:356-402 -> list of (n,n) masked adjacencies (one batched launch; the reference's
+        denoise_graph/log_graph drawing is out of scope)."""
+        if not self.graph_mode:
+            raise ValueError("Explainer was not constructed with graph_mode=True")
+        out = self._explain_graph_batch(graph_indices)
+        if save:
+            for m in out:
+                self._save(m, 0)      # the reference overwrites one file: node_idx_0 graph_idx_<self.graph_idx>
+        return out
+
     def explain(self, node_idx, graph_idx=0, graph_mode=False, unconstrained=False, model="exp"):
-        """explain.py:74-221 -> (n,n) float64 masked adjacency of the node's k-hop subgraph."""
-        if graph_mode:
-            raise NotImplementedError("graph-classification mode is the next scope row")
+        """explain.py:74-221 -> (n,n) float64 masked adjacency of the node's k-hop subgraph (node mode)
+        or of the whole padded graph `graph_idx` (graph_mode=True)."""
+        if graph_mode or self.graph_mode:
+            if not self.graph_mode:
+                raise ValueError("Explainer was not constructed with graph_mode=True")
+            if model != "exp" or unconstrained:
+                raise NotImplementedError("only model='exp', unconstrained=False are built")
+            masked_adj = self._explain_graph_batch([graph_idx])[0]
+            fname = self._save(masked_adj, node_idx)
+            if self.print_training:
+                print("Saved adjacency matrix to ", fname)
+            return masked_adj
         plan, edge_mask = self._explain_batch([node_idx], graph_idx, model, unconstrained)
         masked_adj = plan.dense_of(0, edge_mask, dtype=np.float64)
         fname = self._save(masked_adj, node_idx)

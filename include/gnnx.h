@@ -133,6 +133,21 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
 int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
                      float* edge_mask, float* feat_mask);
 
+/* ---- graph-classification mode (Explainer(..., graph_mode=True), explain_graphs: explain.py:80-85,356-363) ----
+ * Batch of padded graphs, replacing Explainer(adj (G,n,n), feat (G,n,d), label (G)): block CSR over
+ * G*max_nodes rows (rowptr[G*max_nodes+1] with global edge offsets, col = node id inside its graph,
+ * ascending per row, symmetric 0/1, no self loops), features (G*max_nodes, d), one label per graph. */
+int gx_set_graph_batch_csr(gx_handle* h, int32_t num_graphs, int32_t max_nodes, const int32_t* rowptr,
+                           const int32_t* col, const float* feat, int32_t feat_dim, const int32_t* label);
+/* Plans the graphs to explain; edge_off[count+1] (may be NULL) receives the packed slot offsets: the slots of
+ * graph t are the entries of its adjacency in row-major order (its slice of the CSR). */
+int gx_plan_graphs(gx_handle* h, const int32_t* graph_ids, int32_t count, int64_t* edge_off, int64_t* total_edges);
+/* Explainer.explain(node_idx=0, graph_idx=g, graph_mode=True) for every planned graph (model =
+ * GcnEncoderGraph: per-layer max-pool readout, models.py:269-316; lap_loss = 0, explain.py:787-788).
+ * m0_edges / edge_mask: [total_edges] in `space`, as for gx_explain_nodes. */
+int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
+                      float* edge_mask, float* feat_mask);
+
 /* Expands packed edge masks to the dense (n_t, n_t) float64 arrays Explainer.explain returns
  * (explain.py:209-221), task after task, into out (sum_t n_t^2 doubles, `space`). */
 int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* out);

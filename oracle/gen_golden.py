@@ -221,11 +221,76 @@ def gen_short_horizon(R, which, epochs):
     print("  %s: %d nodes at %d epochs" % (which, len(gold["nodes"]), epochs))
 
 
+def gen_graph_mode(R, epochs_list=(10, 100)):
+    """Graph-classification mode (explain.py:80-85,356-363; models.py:269-316): synthetic stand-in for
+    Mutagenicity (dataset absent, no network): padded molecule-like graphs, one-hot 14-d node features,
+    GcnEncoderGraph(14,20,20,2,3) with random weights and non-zero biases."""
+    import networkx as nx
+    rng = np.random.default_rng(21)
+    G_n, max_nodes, d, C = 12, 40, 14, 2
+    adj = np.zeros((G_n, max_nodes, max_nodes)); feat = np.zeros((G_n, max_nodes, d)); label = rng.integers(0, C, G_n)
+    num_nodes = []
+    for g in range(G_n):
+        n = int(rng.integers(6, 36))
+        T = nx.random_labeled_tree(n, seed=int(rng.integers(1 << 30))) if hasattr(nx, "random_labeled_tree") else nx.random_tree(n, seed=int(rng.integers(1 << 30)))
+        for _ in range(max(1, n // 6)):
+            u, v = rng.integers(0, n, 2)
+            if u != v:
+                T.add_edge(int(u), int(v))
+        if g == 3:                       # one graph with an isolated real node
+            T.remove_edges_from(list(T.edges(0)))
+        A = nx.to_numpy_array(T, nodelist=range(n))
+        adj[g, :n, :n] = A
+        feat[g, np.arange(n), rng.integers(0, d, n)] = 1.0
+        num_nodes.append(n)
+    torch.manual_seed(3)
+    targs = train_args(input_dim=d)
+    model = R.models.GcnEncoderGraph(d, 20, 20, C, 3, bn=False, args=targs)
+    with torch.no_grad():
+        for name, p_ in model.named_parameters():
+            if name.endswith("bias"):
+                p_.normal_(0.0, 0.3)
+    model.eval()
+    with torch.no_grad():
+        pred = np.stack([model(torch.tensor(feat[g:g + 1], dtype=torch.float), torch.tensor(adj[g:g + 1], dtype=torch.float))[0][0].numpy()
+                         for g in range(G_n)])[None]
+    out = dict(num_graphs=np.int64(G_n), max_nodes=np.int64(max_nodes), adj=adj.astype(np.uint8), feat=feat.astype(np.float32),
+               label=label.astype(np.int64), pred=pred.astype(np.float32), num_nodes=np.asarray(num_nodes, np.int64), **state_to_np(model))
+    for epochs in epochs_list:
+        eargs = ref_harness.explainer_args(dataset="graphs", num_epochs=epochs)
+        with ref_harness.quiet():
+            ex = R.explain.Explainer(model=model, adj=torch.tensor(adj, dtype=torch.float), feat=torch.tensor(feat, dtype=torch.float),
+                                     label=torch.tensor(label), pred=pred, train_idx=list(range(G_n)), args=eargs,
+                                     writer=None, print_training=False, graph_mode=True, graph_idx=0)
+        for g in range(G_n):
+            seed = 7000 + g
+            if epochs == epochs_list[0]:
+                torch.manual_seed(seed)
+                std = torch.nn.init.calculate_gain("relu") * math.sqrt(2.0 / (max_nodes + max_nodes))
+                M0 = torch.FloatTensor(max_nodes, max_nodes).normal_(1.0, std).numpy()
+                ei, ej = np.nonzero(adj[g])
+                out["g%d_m0" % g] = M0[ei, ej].astype(np.float32)
+                out["g%d_seed" % g] = np.int64(seed)
+            torch.manual_seed(seed)
+            with ref_harness.quiet():
+                masked = np.asarray(ex.explain(node_idx=0, graph_idx=g, graph_mode=True))
+            ei, ej = np.nonzero(adj[g])
+            off = masked.copy(); off[ei, ej] = 0
+            assert np.all(off == 0)
+            out["g%d_mask_e%d" % (g, epochs)] = masked[ei, ej].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "graphs_golden.npz"), **out)
+    print("  graph mode: %d graphs, max_nodes %d, epochs %s" % (G_n, max_nodes, list(epochs_list)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--short", type=int, default=0, help="also/only generate the short-horizon golden (epochs)")
     a = ap.parse_args()
+    if a.only == "graph":
+        torch.set_num_threads(8)
+        gen_graph_mode(ref_harness.load())
+        return
     if a.short:
         torch.set_num_threads(8)
         R = ref_harness.load()
