@@ -336,6 +336,97 @@ def main_ours(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] stand-in (dataset absent, no network): 4337 padded molecule-like graphs, graph-level masks
+# ------------------------------------------------------------------------------------------------
+def make_graph_batch(G=4337, max_nodes=100, d=14, C=2, seed=0):
+    rng = np.random.default_rng(seed)
+    adj = np.zeros((G, max_nodes, max_nodes), np.uint8)
+    feat = np.zeros((G, max_nodes, d), np.float32)
+    for g in range(G):
+        n = int(np.clip(rng.normal(30, 20), 4, max_nodes))
+        par = np.array([rng.integers(0, i) for i in range(1, n)])          # random recursive tree
+        u = np.arange(1, n)
+        adj[g, u, par] = 1; adj[g, par, u] = 1
+        k = max(1, n // 6)
+        a, b = rng.integers(0, n, k), rng.integers(0, n, k)
+        ok = a != b
+        adj[g, a[ok], b[ok]] = 1; adj[g, b[ok], a[ok]] = 1
+        feat[g, np.arange(n), rng.integers(0, d, n)] = 1.0
+    label = rng.integers(0, C, G).astype(np.int32)
+    sc = lambda *s_: (rng.normal(size=s_) * 0.4).astype(np.float32)
+    W = dict(W1=sc(d, 20), b1=sc(20), W2=sc(20, 20), b2=sc(20), W3=sc(20, 20), b3=sc(20), Wp=sc(C, 60), bp=sc(C))
+    return adj, feat, label, W
+
+
+def _cpu_graph_one(args):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gnnx_oracle as O
+    torch.set_num_threads(1)
+    A, X, y, W, seed = args
+    M0 = O.draw_m0(A.shape[0], seed=seed)
+    return float(O.explain_dense_torch(A.astype(float), X, int(y), None, 0, W, M0, hp=O.default_hparams(num_epochs=NUM_EPOCHS), graph_mode=True).sum())
+
+
+def main_graphs(a):
+    cores = os.cpu_count() or 1
+    adj, feat, label, W = make_graph_batch()
+    G = adj.shape[0]
+    if a.impl == "reference":
+        import multiprocessing as mp
+        procs = a.cpu_procs or min(cores, 64)
+        sample = [int(x) for x in np.linspace(0, G - 1, max(2 * procs, 16)).round()]
+        jobs = [(adj[g], feat[g], label[g], W, 100 + g) for g in sample]
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_graph_one, jobs[:procs], chunksize=1)
+            t0 = time.perf_counter(); pool.map(_cpu_graph_one, jobs, chunksize=1); dt = time.perf_counter() - t0
+        v = len(sample) / dt
+        print(json.dumps({"impl": "reference", "metric": "explained-graphs/sec (100 mask-opt epochs each)", "value": v, "unit": "graphs/s",
+                          "n_gpus": 1, "steps": 1, "warmup": 0, "ms_per_step": 1000 * dt, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "Mutagenicity stand-in: %d padded graphs (max_nodes 100, d=14), graph-level mask" % G,
+                                     "sample": "%d graphs, %d single-thread worker processes" % (len(sample), procs)},
+                          "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": procs, "kind": "port", "sample": "%d graphs x 100 epochs" % len(sample)},
+                          "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    import gnnx
+    from gnnx import _abi
+    torch.cuda.set_device(0)
+    eng = gnnx.Engine(0)
+    eng.set_model(W)
+    eng.set_graph_batch(adj, feat, label)
+    gids = np.arange(G, dtype=np.int32)
+    edge_off = eng.plan_graphs(gids)
+    te = int(edge_off[-1])
+    out_host = torch.empty(te, dtype=torch.float32).pin_memory()
+    hp = eng.make_hparams(num_epochs=NUM_EPOCHS, init=_abi.GX_INIT_PHILOX, seed=7)
+    import ctypes as C
+    lib = _abi.lib()
+
+    def step():
+        eng.plan_graphs(gids)
+        _abi.check(lib.gx_explain_graphs(eng._h, C.byref(hp), _abi.GX_HOST, None, C.c_void_p(out_host.data_ptr()), None))
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); kms = []
+    for _ in range(a.steps):
+        step(); kms.append(eng.last_explain_ms())
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.steps
+    print(json.dumps({"metric": "explained-graphs/sec (100 mask-opt epochs each)", "value": G / (np.mean(kms) / 1e3), "unit": "graphs/s", "n_gpus": 1,
+                      "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(kms)), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "Mutagenicity stand-in: %d padded graphs (max_nodes 100, d=14), graph-level mask, 100 epochs" % G,
+                                 "sum_E_d": te, "init": "device Philox"},
+                      "e2e": {"value": G / dt, "unit": "graphs/s", "ms_per_step": 1000 * dt, "h2d_bytes_per_step": int(G * 4), "d2h_bytes_per_step": int(te * 4)},
+                      "gpu_launches": 2 * a.steps}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -343,9 +434,12 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="syn1", choices=["syn1", "graphs"], help="syn1 = BASELINE configs[1] (default, the contract line); graphs = configs[3] stand-in")
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU baseline (default min(cores,64))")
     a = ap.parse_args()
-    if a.impl == "reference":
+    if a.workload == "graphs":
+        main_graphs(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_ours(a)
