@@ -276,9 +276,8 @@ int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* co
     return GX_ERR_UNSUPPORTED;
   }
   if (dims->flags & GX_MODEL_BN) { gx_set_error("gx_set_model: --bn (models.py:222-228) is not built"); return GX_ERR_UNSUPPORTED; }
-  if (dims->hidden_dim != 20 || dims->embed_dim != 20) {
-    gx_set_error("gx_set_model: hidden_dim=%d output_dim=%d; this build instantiates the reference default 20/20",
-                 dims->hidden_dim, dims->embed_dim);
+  if (dims->hidden_dim < 1 || dims->embed_dim < 1 || dims->hidden_dim > 32 || dims->embed_dim > 32) {
+    gx_set_error("gx_set_model: hidden_dim=%d output_dim=%d; this build supports widths up to 32", dims->hidden_dim, dims->embed_dim);
     return GX_ERR_UNSUPPORTED;
   }
   if (dims->input_dim < 1 || dims->input_dim > 128) {
@@ -287,24 +286,35 @@ int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* co
   }
   if (dims->num_classes < 1) { gx_set_error("gx_set_model: num_classes < 1"); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
-  const int d = dims->input_dim, hid = dims->hidden_dim, emb = dims->embed_dim, C = dims->num_classes;
+  // The kernels are instantiated for the reference default 20/20 and for 32/32; any other width <= 32 is
+  // zero-padded to 32.  Padding is exact: a padded output column is 0*W + 0 = 0, contributes nothing to the
+  // row norm, stays 0 through normalise/ReLU, and its pred_model column is 0 (forward and backward).
+  const int d = dims->input_dim, hid0 = dims->hidden_dim, emb0 = dims->embed_dim, C = dims->num_classes;
+  const bool native = hid0 == 20 && emb0 == 20;
+  const int hid = native ? 20 : 32, emb = native ? 20 : 32;
+  const int in0[3] = {d, hid0, hid0}, out0[3] = {hid0, hid0, emb0};
   const int in_dim[3] = {d, hid, hid}, out_dim[3] = {hid, hid, emb};
-  const int PD = 2 * hid + emb;
+  const int PD0 = 2 * hid0 + emb0, PD = 2 * hid + emb;
   std::vector<float> host;
   size_t offW[3], offWt[3], offb[3], offWp, offbp;
   auto al4 = [&]() { while (host.size() % 4) host.push_back(0.f); };
   for (int l = 0; l < 3; ++l) {
     if (!conv_w[l]) { gx_set_error("gx_set_model: conv_w[%d] is NULL", l); return GX_ERR_INVALID; }
+    auto Wat = [&](int f, int c) -> float { return (f < in0[l] && c < out0[l]) ? conv_w[l][(size_t)f * out0[l] + c] : 0.f; };
     al4(); offW[l] = host.size();
-    host.insert(host.end(), conv_w[l], conv_w[l] + (size_t)in_dim[l] * out_dim[l]);
+    for (int f = 0; f < in_dim[l]; ++f) for (int c = 0; c < out_dim[l]; ++c) host.push_back(Wat(f, c));
     al4(); offWt[l] = host.size();
-    for (int c = 0; c < out_dim[l]; ++c)
-      for (int f = 0; f < in_dim[l]; ++f) host.push_back(conv_w[l][(size_t)f * out_dim[l] + c]);
+    for (int c = 0; c < out_dim[l]; ++c) for (int f = 0; f < in_dim[l]; ++f) host.push_back(Wat(f, c));
     al4(); offb[l] = host.size();
-    for (int c = 0; c < out_dim[l]; ++c) host.push_back((conv_b && conv_b[l]) ? conv_b[l][c] : 0.f);
+    for (int c = 0; c < out_dim[l]; ++c) host.push_back((conv_b && conv_b[l] && c < out0[l]) ? conv_b[l][c] : 0.f);
   }
   al4(); offWp = host.size();
-  host.insert(host.end(), pred_w, pred_w + (size_t)C * PD);
+  for (int c = 0; c < C; ++c)
+    for (int k = 0; k < PD; ++k) {
+      const int part = k / hid >= 2 ? 2 : k / hid, within = k - part * hid;     // padded column -> (layer, feature)
+      const int w0 = part == 2 ? emb0 : hid0;
+      host.push_back(within < w0 ? pred_w[(size_t)c * PD0 + part * hid0 + within] : 0.f);
+    }
   al4(); offbp = host.size();
   host.insert(host.end(), pred_b, pred_b + C);
   GX_CUDA_CHECK(h->m_buf.reserve(host.size() * 4));

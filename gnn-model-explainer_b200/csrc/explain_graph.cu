@@ -431,13 +431,13 @@ cudaError_t gx_launch_explain_graphs(const GxExplainLaunch& cfg, const GxGraphBa
   args.pws = cfg.pws; args.pws_stride_words = cfg.pws_stride_words;
   args.gb = gb; args.m = m; args.hp = hp; args.plan = plan;
   args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat;
-  if (!(m.hid == 20 && m.emb == 20)) return cudaErrorInvalidValue;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
     return cudaGetLastError();
   };
-  if (cfg.threads <= 128) return launch(explain_graph_kernel<20, 20, 128>);
-  return launch(explain_graph_kernel<20, 20, 256>);
+  if (m.hid == 20 && m.emb == 20) return launch(explain_graph_kernel<20, 20, 128>);
+  if (m.hid == 32 && m.emb == 32) return launch(explain_graph_kernel<32, 32, 128>);   // widths <= 32, zero-padded
+  return cudaErrorInvalidValue;
 }

@@ -623,5 +623,6 @@ cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, c
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
   args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg;
   if (m.hid == 20 && m.emb == 20) return launch_dims<20, 20>(cfg, args, s);
-  return cudaErrorInvalidValue;  // gx_set_model rejects other widths before this point
+  if (m.hid == 32 && m.emb == 32) return launch_dims<32, 32>(cfg, args, s);   // any width <= 32, zero-padded by gx_set_model
+  return cudaErrorInvalidValue;
 }

@@ -104,3 +104,30 @@ def test_explainer_dropin_graph_mode(gg, tmp_path):
     torch.manual_seed(1)
     b = ex.explain_graphs([4, 6])
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_graph_mode_other_widths(gg):
+    rng = np.random.default_rng(77)
+    hid, emb, d, C = 12, 24, 14, 3
+    sc = lambda *s: (rng.normal(size=s) * 0.5).astype(np.float32)
+    W = dict(W1=sc(d, hid), b1=sc(hid), W2=sc(hid, hid), b2=sc(hid), W3=sc(hid, emb), b3=sc(emb), Wp=sc(C, 2 * hid + emb), bp=sc(C))
+    eng = gnnx.Engine(0)
+    eng.set_model(W)
+    label = gg["label"] % C
+    eng.set_graph_batch(gg["adj"], gg["feat"], label)
+    gids = [1, 6, 10]
+    edge_off = eng.plan_graphs(gids)
+    n = int(gg["max_nodes"])
+    m0s, dense = [], []
+    for g in gids:
+        M0 = O.draw_m0(n, seed=40 + g)
+        r, c = eng.graph_rows_cols(g)
+        m0s.append(M0[r, c]); dense.append(M0)
+    out = np.zeros(int(edge_off[-1]), np.float32)
+    eng.explain_graphs_host(eng.make_hparams(num_epochs=20), np.concatenate(m0s).astype(np.float32), out)
+    for t, g in enumerate(gids):
+        ref = O.explain_dense_torch(gg["adj"][g].astype(float), gg["feat"][g], label[g], None, 0, W, dense[t],
+                                    hp=O.default_hparams(num_epochs=20), graph_mode=True)
+        r, c = eng.graph_rows_cols(g)
+        assert util.rel_l2(out[edge_off[t]:edge_off[t + 1]], ref[r, c]) <= 1e-4, g
+    eng.close()

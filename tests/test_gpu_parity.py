@@ -348,3 +348,40 @@ def test_error_behaviour(tmp_path):
     with pytest.raises(_abi.GnnxError):
         eng2.explain_nodes_host(eng2.make_hparams(mask_bias=1), np.zeros(10000, np.float32), np.zeros(10000, np.float32))
     eng.close(); eng2.close()
+
+
+# ------------------------------------------------------------------------------------ other layer widths (--hidden-dim / --output-dim)
+@pytest.mark.parametrize("hid,emb,d,C", [(16, 12, 10, 3), (32, 32, 7, 2), (8, 28, 5, 4)])
+def test_other_widths_match_oracle(hid, emb, d, C):
+    """Widths <= 32 run on the 32/32 instantiation with exactly-zero padding (api.cu gx_set_model)."""
+    import networkx as nx
+    rng = np.random.default_rng(hid * 100 + emb)
+    Gx = nx.barabasi_albert_graph(45, 2, seed=hid)
+    A = nx.to_numpy_array(Gx)
+    N = A.shape[0]
+    rowptr, col = O.csr_from_dense(A)
+    feat = rng.normal(size=(N, d)).astype(np.float32)
+    label = rng.integers(0, C, N)
+    sc = lambda *s: (rng.normal(size=s) * 0.5).astype(np.float32)
+    w = dict(W1=sc(d, hid), b1=sc(hid), W2=sc(hid, hid), b2=sc(hid), W3=sc(hid, emb), b3=sc(emb), Wp=sc(C, 2 * hid + emb), bp=sc(C))
+    Wt = O.weights_to_torch(w, False)
+    with torch.no_grad():
+        pred = O._gcn_forward_torch(torch.tensor(feat[None]), torch.tensor(A[None], dtype=torch.float), Wt, False)[0].numpy()
+    cs = types.SimpleNamespace(N=N, rowptr=rowptr, col=col, feat=feat, label=label, weights=w,
+                               pred_label=np.argmax(pred, 1).astype(np.int32))
+    eng = util.make_engine(cs)
+    nodes = [0, 9, 30, 44]
+    plan = eng.plan_nodes(nodes, 3)
+    m0 = np.empty(plan.total_edges, np.float32); dense = []
+    for t in range(plan.count):
+        M0 = O.draw_m0(plan.n(t), seed=hid + t)
+        r, c = plan.rows_cols_of(t)
+        m0[plan.edge_off[t]:plan.edge_off[t + 1]] = M0[r, c]; dense.append(M0)
+    out = np.zeros(plan.total_edges, np.float32)
+    eng.explain_nodes_host(eng.make_hparams(num_epochs=20), m0, out)
+    for t, node in enumerate(nodes):
+        idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(rowptr, col, feat, label, node, 3)
+        ref = O.explain_dense_torch(O.dense_from_csr(srp, scol), sfeat, slabel[idx], cs.pred_label[nbrs], idx, w, dense[t],
+                                    hp=O.default_hparams(num_epochs=20))
+        assert O.rel_l2(plan.dense_of(t, out), ref) <= 1e-4, (node, O.rel_l2(plan.dense_of(t, out), ref))
+    eng.close()

@@ -118,3 +118,22 @@ def test_gradients_match_autograd():
     ei, ej = np.nonzero(A)
     assert O.rel_l2(st["gM"][ei, ej], mask.grad.numpy()[ei, ej]) < 1e-9
     assert O.rel_l2(st["gF"], fmask.grad.numpy()) < 1e-9
+
+
+def test_graph_mode_oracle_matches_reference():
+    """Graph-classification mode (explain.py:80-85, models.py:269-316): torch port bit-exact, closed form 1e-4
+    against golden masks produced by the unmodified reference (oracle/gen_golden.py --only graph)."""
+    g = np.load(util.GOLDEN + "/graphs_golden.npz")
+    W = {k: g[k] for k in ["W1", "b1", "W2", "b2", "W3", "b3", "Wp", "bp"]}
+    n = int(g["max_nodes"])
+    for gi in (0, 3, 9):
+        A = g["adj"][gi].astype(float)
+        ei, ej = np.nonzero(A)
+        M0 = np.zeros((n, n), np.float32)
+        M0[ei, ej] = g["g%d_m0" % gi]
+        out = O.explain_dense_torch(A, g["feat"][gi], g["label"][gi], None, 0, W, M0, hp=O.default_hparams(num_epochs=10), graph_mode=True)
+        assert O.rel_l2(out[ei, ej], g["g%d_mask_e10" % gi]) <= 1e-6
+        for T in (10, 100):
+            cf = O.explain_closed_form(A, g["feat"][gi], g["label"][gi], None, 0, W, M0, hp=O.default_hparams(num_epochs=T),
+                                       graph_mode=True, dtype=np.float32)
+            assert O.rel_l2(cf[ei, ej], g["g%d_mask_e%d" % (gi, T)]) <= 1e-4
