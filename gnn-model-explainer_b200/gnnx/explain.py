@@ -245,6 +245,48 @@ class Explainer:
                 self._save(out[t], int(node))
         return out
 
+    # ---------------------------------------------------------------- evaluation step right after the masks
+    # planted-motif edges relative to the first motif node, in the sorted local numbering (explain.py:537-577)
+    _MOTIF_EDGES = {
+        "syn1": [(0, 1), (1, 2), (2, 3), (0, 3), (0, 4), (1, 4)],          # house
+        "syn2": [(0, 1), (1, 2), (2, 3), (0, 3), (0, 4), (1, 4)],
+        "syn4": [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (0, 5)],          # 6-cycle
+    }
+
+    def make_pred_real(self, adj, start):
+        """explain.py:535-579: (pred, real) over the upper-triangular positive entries of a masked adjacency;
+        real = 1 on the planted motif's edges (fixed offsets from `start`)."""
+        if self.args.dataset not in self._MOTIF_EDGES:
+            raise NotImplementedError("make_pred_real knows syn1/syn2/syn4 only (like the reference)")
+        adj = np.asarray(adj)
+        upper = np.triu(adj) > 0
+        pred = adj[upper]
+        truth = np.zeros(adj.shape, dtype=bool)
+        for (p_, q_) in self._MOTIF_EDGES[self.args.dataset]:
+            if adj[start + p_][start + q_] > 0:        # IndexError past the subgraph, like the reference
+                truth[start + p_, start + q_] = True
+        real = truth[upper].astype(adj.dtype)
+        return pred, real
+
+    def explain_nodes_gnn_stats(self, node_indices, args=None, graph_idx=0, model="exp"):
+        """explain.py:295-353: explain the nodes (one batched launch), score the edge masks against the planted
+        motifs with ROC-AUC and write log/pr/auc_<dataset>_<model>.txt; returns the masks.  The PR-curve PNG
+        and the tensorboard drawings of the reference are not produced (viz, out of scope)."""
+        from sklearn.metrics import roc_auc_score
+        if model != "exp":
+            raise NotImplementedError("model=%r is not built" % model)
+        plan, edge_mask = self._explain_batch(node_indices, graph_idx)
+        masked_adjs = [plan.dense_of(t, edge_mask, dtype=np.float64) for t in range(plan.count)]
+        pred_all, real_all = [], []
+        for t in range(plan.count):
+            pred, real = self.make_pred_real(masked_adjs[t], int(plan.node_idx_new[t]))
+            pred_all.append(pred); real_all.append(real)
+        self.auc = float(roc_auc_score(np.concatenate(real_all), np.concatenate(pred_all)))
+        os.makedirs(os.path.join("log", "pr"), exist_ok=True)
+        with open(os.path.join("log", "pr", "auc_" + self.args.dataset + "_" + model + ".txt"), "w") as f:
+            f.write("dataset: {}, model: {}, auc: {}\n".format(self.args.dataset, "exp", str(self.auc)))
+        return masked_adjs
+
     def explain_nodes_packed(self, node_indices, graph_idx=0):
         """Same computation, returning (plan, edge_mask) without densifying: edge_mask[edge_off[t]:
         edge_off[t+1]] are the masked_adj entries of node t at plan.csr_of(t) (row-major order)."""

@@ -282,11 +282,43 @@ def gen_graph_mode(R, epochs_list=(10, 100)):
     print("  graph mode: %d graphs, max_nodes %d, epochs %s" % (G_n, max_nodes, list(epochs_list)))
 
 
+def gen_auc(R):
+    """Known-answer check downstream of the masks: Explainer.make_pred_real (explain.py:535-579) + roc_auc_score
+    (explain.py:328) evaluated BY THE REFERENCE on its own golden masks (motif-start nodes only)."""
+    from sklearn.metrics import roc_auc_score
+    import types
+    out = {}
+    for which, nodes in (("syn1", [300, 350, 400, 450, 550, 620]), ("syn4", [511])):
+        gold = np.load(os.path.join(OUT, which + "_golden.npz"))
+        g = np.load(os.path.join(OUT, which + "_graph.npz"))
+        N = int(g["N"])
+        A = np.zeros((N, N)); A[g["edges"][:, 0], g["edges"][:, 1]] = 1; A[g["edges"][:, 1], g["edges"][:, 0]] = 1
+        fake = types.SimpleNamespace(args=types.SimpleNamespace(dataset=which))
+        preds, reals = [], []
+        nodes = [n for n in nodes if ("n%d_mask" % n) in gold]
+        for node in nodes:
+            nbrs = gold["n%d_nbrs" % node]
+            sub = A[nbrs][:, nbrs]
+            ei, ej = np.nonzero(sub)
+            M = np.zeros_like(sub); M[ei, ej] = gold["n%d_mask" % node]
+            pred, real = R.explain.Explainer.make_pred_real(fake, M, int(gold["n%d_idx_new" % node]))
+            out["%s_n%d_real" % (which, node)] = real.astype(np.uint8)
+            out["%s_n%d_pred" % (which, node)] = pred.astype(np.float32)
+            preds.append(pred); reals.append(real)
+        out[which + "_nodes"] = np.asarray(nodes, np.int64)
+        out[which + "_auc"] = np.float64(roc_auc_score(np.concatenate(reals), np.concatenate(preds)))
+        print("  %s: AUC of the reference on %d golden nodes = %.4f" % (which, len(nodes), out[which + "_auc"]))
+    np.savez_compressed(os.path.join(OUT, "auc_golden.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--short", type=int, default=0, help="also/only generate the short-horizon golden (epochs)")
     a = ap.parse_args()
+    if a.only == "auc":
+        gen_auc(ref_harness.load())
+        return
     if a.only == "graph":
         torch.set_num_threads(8)
         gen_graph_mode(ref_harness.load())

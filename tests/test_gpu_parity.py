@@ -385,3 +385,25 @@ def test_other_widths_match_oracle(hid, emb, d, C):
                                     hp=O.default_hparams(num_epochs=20))
         assert O.rel_l2(plan.dense_of(t, out), ref) <= 1e-4, (node, O.rel_l2(plan.dense_of(t, out), ref))
     eng.close()
+
+
+def test_gnn_stats_auc_matches_reference(syn1, tmp_path, monkeypatch):
+    """Known-answer check downstream of the masks: ROC-AUC of the edge masks against the planted
+    house motifs, same nodes and seeds as the reference golden run, within 0.01 of the reference's AUC."""
+    import os
+    au = np.load(os.path.join(util.GOLDEN, "auc_golden.npz"))
+    monkeypatch.chdir(tmp_path)
+    ex, args = _explainer(syn1, tmp_path)
+    nodes = [int(n) for n in au["syn1_nodes"]]
+    # per-node seeds of the golden run: draw M0 node by node exactly as the reference did
+    masks = []
+    for node in nodes:
+        torch.manual_seed(int(syn1.gold["n%d_seed" % node]))
+        masks.append(ex.explain_nodes_gnn_stats([node], args)[0])
+    torch.manual_seed(0)
+    ex.explain_nodes_gnn_stats(nodes, args)
+    assert os.path.exists(os.path.join("log", "pr", "auc_syn1_exp.txt"))
+    from sklearn.metrics import roc_auc_score
+    pr = [ex.make_pred_real(m, int(syn1.gold["n%d_idx_new" % n])) for m, n in zip(masks, nodes)]
+    auc = roc_auc_score(np.concatenate([r for _, r in pr]), np.concatenate([p for p, _ in pr]))
+    assert abs(auc - float(au["syn1_auc"])) < 0.01, (auc, float(au["syn1_auc"]))

@@ -68,3 +68,28 @@ def test_shard_indices_partition():
         assert sorted(seen) == list(range(37))
         loads = [costs[shard_indices(37, world, r, costs)].sum() for r in range(world)]
         assert max(loads) - min(loads) <= costs.max()
+
+
+def test_make_pred_real_matches_reference():
+    """explain.py:535-579 restated table-driven: identical (pred, real) and AUC to what the reference's own
+    make_pred_real produced on its golden masks (oracle/gen_golden.py --only auc)."""
+    import os
+    from sklearn.metrics import roc_auc_score
+    import util
+    au = np.load(os.path.join(util.GOLDEN, "auc_golden.npz"))
+    for which in ("syn1", "syn4"):
+        fx = util.load_fixture(which)
+        A = O.dense_from_csr(fx.rowptr, fx.col)
+        ex = gx_explain.Explainer.__new__(gx_explain.Explainer)
+        ex.args = types.SimpleNamespace(dataset=which)
+        preds, reals = [], []
+        for node in au[which + "_nodes"]:
+            nbrs = fx.gold["n%d_nbrs" % node]
+            sub = A[nbrs][:, nbrs]
+            ei, ej = np.nonzero(sub)
+            M = np.zeros_like(sub); M[ei, ej] = fx.gold["n%d_mask" % node]
+            pred, real = ex.make_pred_real(M, int(fx.gold["n%d_idx_new" % node]))
+            assert np.array_equal(real.astype(np.uint8), au["%s_n%d_real" % (which, node)])
+            assert np.array_equal(pred.astype(np.float32), au["%s_n%d_pred" % (which, node)])
+            preds.append(pred); reals.append(real)
+        assert abs(roc_auc_score(np.concatenate(reals), np.concatenate(preds)) - float(au[which + "_auc"])) < 1e-12
