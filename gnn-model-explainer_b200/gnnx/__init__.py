@@ -5,6 +5,6 @@ C ABI, include/gnnx.h); there is no CPU fallback."""
 from . import _abi  # noqa: F401
 from .engine import Engine, Plan  # noqa: F401
 from .explain import Explainer  # noqa: F401
-from . import graph_utils, models  # noqa: F401
+from . import graph_utils, io_utils, models  # noqa: F401
 
-__all__ = ["Engine", "Plan", "Explainer", "graph_utils", "models"]
+__all__ = ["Engine", "Plan", "Explainer", "graph_utils", "io_utils", "models"]
