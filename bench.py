@@ -427,6 +427,105 @@ def main_graphs(a):
     eng.close()
 
 
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: dense BA graph (N=100k, m=32 => avg degree 64), d=128, 3-hop neighbourhood ~ the whole graph.
+# Every task runs in the streaming kernel (explain_stream.cu); a step explains --c5-nodes nodes (default: one per SM).
+# ------------------------------------------------------------------------------------------------
+def make_ba_csr(N, m, seed=0):
+    """Barabasi-Albert preferential attachment (numpy): node v attaches to m distinct earlier nodes drawn from the endpoint list."""
+    rng = np.random.default_rng(seed)
+    rep = np.empty(2 * m * N, np.int32)
+    L = 0
+    edges = np.empty((m * (N - m), 2), np.int32)
+    k = 0
+    targets = np.arange(m, dtype=np.int32)
+    for v in range(m, N):
+        edges[k:k + m, 0] = v; edges[k:k + m, 1] = targets; k += m
+        rep[L:L + m] = targets; rep[L + m:L + 2 * m] = v; L += 2 * m
+        t = np.unique(rep[rng.integers(0, L, 2 * m)])
+        while len(t) < m:
+            t = np.unique(np.concatenate([t, rep[rng.integers(0, L, m)]]))
+        targets = rng.permutation(t)[:m].astype(np.int32)
+    src = np.concatenate([edges[:, 0], edges[:, 1]]); dst = np.concatenate([edges[:, 1], edges[:, 0]])
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    rowptr = np.zeros(N + 1, np.int64)
+    np.add.at(rowptr, src + 1, 1)
+    return np.cumsum(rowptr).astype(np.int32), dst.astype(np.int32)
+
+
+def main_c5(a):
+    import torch
+    import scipy.sparse as sp
+    import gnnx
+    from gnnx import _abi
+    N, m, d, C = a.c5_n, a.c5_m, 128, 4
+    rng = np.random.default_rng(0)
+    t0 = time.perf_counter()
+    rowptr, col = make_ba_csr(N, m, 0)
+    X = rng.normal(size=(N, d)).astype(np.float32)
+    label = rng.integers(0, C, N).astype(np.int32)
+    sc = lambda *s_: (rng.normal(size=s_) * 0.3).astype(np.float32)
+    W = dict(W1=sc(d, 20), b1=sc(20), W2=sc(20, 20), b2=sc(20), W3=sc(20, 20), b3=sc(20), Wp=sc(C, 60), bp=sc(C))
+    # pred_label = argmax of the model's own forward on the full graph (explainer_main.py feeds cg["pred"])
+    A = sp.csr_matrix((np.ones(len(col), np.float32), col, rowptr), shape=(N, N))
+    nrm = lambda Y: Y / np.maximum(np.linalg.norm(Y, axis=1, keepdims=True), 1e-12)
+    H1 = np.maximum(nrm((A @ X) @ W["W1"] + W["b1"]), 0); H2 = np.maximum(nrm((A @ H1) @ W["W2"] + W["b2"]), 0)
+    H3 = nrm((A @ H2) @ W["W3"] + W["b3"])
+    pred_label = np.argmax(np.concatenate([H1, H2, H3], 1) @ W["Wp"].T + W["bp"], 1).astype(np.int32)
+    gen_s = time.perf_counter() - t0
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    eng = gnnx.Engine(0)
+    eng.set_model(W)
+    eng.set_graph_csr(rowptr, col, X, label, pred_label)
+    K = a.c5_nodes
+    nodes = np.random.default_rng(1).permutation(N)[:K].astype(np.int32)
+    hp = eng.make_hparams(num_epochs=NUM_EPOCHS, init=_abi.GX_INIT_PHILOX, seed=99)
+    tp0 = time.perf_counter()
+    eng.plan_nodes(nodes, 3, fetch=False)
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - tp0
+    _, total_n, total_e = eng._plan_sizes
+    out_dev = torch.empty(total_e, dtype=torch.float32, device=dev)
+    out_host = torch.empty(total_e, dtype=torch.float32).pin_memory()
+    sampler = ClockSampler(0)
+    kms, wall = [], []
+    for i in range(a.warmup + a.steps):
+        if i == a.warmup:
+            sampler.start()
+        tw = time.perf_counter()
+        eng.plan_nodes(nodes, 3, fetch=False)
+        eng.explain_nodes_ptr(hp, _abi.GX_DEVICE, 0, out_dev.data_ptr())
+        out_host.copy_(out_dev, non_blocking=False)      # masks delivered to the host (what explain_nodes returns)
+        torch.cuda.synchronize()
+        if i >= a.warmup:
+            wall.append(time.perf_counter() - tw); kms.append(eng.last_explain_ms())
+    clocks = sampler.stop()
+    kern_s = float(np.mean(kms)) / 1e3
+    algo = float(NUM_EPOCHS * (84.0 * total_e + 8.0 * d * total_n))          # SURVEY 8(d), no spill term
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_hbm = float(json.load(open(pk)).get("hbm_gbs", 6650.0)) if os.path.exists(pk) else 6650.0
+    mask = out_host.numpy()
+    print(json.dumps({
+        "metric": METRIC, "value": K / kern_s, "unit": "nodes/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * kern_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[4]: BA(N=%d, m=%d) d=128 C=4, %d explained nodes per step, 3-hop, 100 epochs, streaming kernel" % (N, m, K),
+                   "sum_n": int(total_n), "sum_E_d": int(total_e), "init": "device Philox N(1,2/n)", "graph_gen_s": gen_s, "first_plan_s": plan_s,
+                   "l2": "working set (%.1f GB of per-task state) exceeds L2" % (total_e * 4 * 3 / 1e9)},
+        "e2e": {"value": K / float(np.mean(wall)), "unit": "nodes/s", "ms_per_step": 1e3 * float(np.mean(wall)),
+                "h2d_bytes_per_step": int(K * 4), "d2h_bytes_per_step": int(total_e * 4)},
+        "gpu_launches": int(4 * a.steps), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": algo / kern_s / 1e9, "peak": peak_hbm, "unit": "GB/s", "frac": algo / kern_s / 1e9 / peak_hbm, "traffic": None,
+                     "kernel": "explain_stream_kernel + outer_pairs_kernel", "algorithmic_bytes_per_step": algo,
+                     "note": "algorithmic bytes = SURVEY 8(d) fused lower bound of the UNPRUNED algorithm (84*E_d + 8*n*d per node-epoch); the kernel "
+                             "prunes to the receptive field and runs outermost pairs as register recurrences, so it can move fewer bytes than that"},
+        "cpu_baseline": None,
+        "mask_checksum": {"mean": float(mask.mean()), "min": float(mask.min()), "max": float(mask.max()), "finite": bool(np.isfinite(mask).all())},
+    }), flush=True)
+    eng.close()
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,11 +533,16 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="syn1", choices=["syn1", "graphs"], help="syn1 = BASELINE configs[1] (default, the contract line); graphs = configs[3] stand-in")
+    ap.add_argument("--workload", default="syn1", choices=["syn1", "graphs", "c5"], help="syn1 = BASELINE configs[1] (default, the contract line); graphs = configs[3] stand-in; c5 = configs[4] (streaming kernel)")
+    ap.add_argument("--c5-n", type=int, default=100000)
+    ap.add_argument("--c5-m", type=int, default=32)
+    ap.add_argument("--c5-nodes", type=int, default=148, help="explained nodes per step of the c5 workload")
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU baseline (default min(cores,64))")
     a = ap.parse_args()
     if a.workload == "graphs":
         main_graphs(a)
+    elif a.workload == "c5":
+        main_c5(a)
     elif a.impl == "reference":
         main_reference(a)
     else:

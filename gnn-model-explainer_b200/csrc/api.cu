@@ -69,6 +69,7 @@ struct gx_handle {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   bool timed = false;
   float* dbg = nullptr;
+  bool force_stream = false;  // test knob (gx_debug_force_stream / GNNX_FORCE_STREAM): every task goes to the streaming class
   cudaEvent_t ev_join[kNumStreams] = {};
   int64_t launches = 0;
 
@@ -139,9 +140,9 @@ int ensure_slot_ws(gx_handle* h) {
   return GX_OK;
 }
 
-int task_smem_class(const GxTask& T, const GxModelDev& m, int* bytes_out, int* idx16_out) {
+int task_smem_class(const GxTask& T, const GxModelDev& m, bool force_stream, int* bytes_out, int* idx16_out) {
   // shared-memory classes always use 16-bit indices: a task with n or e1 >= 65535 cannot fit 227 KB anyway
-  const bool small_idx = T.n < 65535 && T.e1 < 65535;
+  const bool small_idx = !force_stream && T.n < 65535 && T.e1 < 65535;
   for (int c = 0; small_idx && c < kNumClasses - 1; ++c) {
     const int nwarps = kClasses[c].threads / 32;
     const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, m.d, m.hid, m.emb, m.C, nwarps, 2);
@@ -152,9 +153,7 @@ int task_smem_class(const GxTask& T, const GxModelDev& m, int* bytes_out, int* i
       return c;
     }
   }
-  const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, m.d, m.hid, m.emb, m.C,
-                                    kClasses[kNumClasses - 1].threads / 32, 4);
-  *bytes_out = L.total_words;  // words (may exceed int bytes range for huge tasks)
+  *bytes_out = 0;  // streaming class (explain_stream.cu): state in a global slab, sized by gx_make_stream_layout
   *idx16_out = 0;
   return kNumClasses - 1;
 }
@@ -210,6 +209,7 @@ int gx_create(int device, gx_handle** out) {
   gx_handle* h = new gx_handle();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* env = getenv("GNNX_FORCE_STREAM")) h->force_stream = atoi(env) != 0;
   for (int i = 0; i < kNumStreams; ++i) {
     GX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
     GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
@@ -258,6 +258,9 @@ int64_t gx_launch_count(gx_handle* h) { return h ? h->launches : 0; }
 
 /* debug only (not in gnnx.h): device buffer receiving the shared-memory slab of the first task of each class */
 int gx_debug_set_dump(gx_handle* h, float* dev_buf) { if (!h) return GX_ERR_INVALID; h->dbg = dev_buf; return GX_OK; }
+
+/* debug only (not in gnnx.h): plan every task into the streaming class (explain_stream.cu) regardless of its size */
+int gx_debug_force_stream(gx_handle* h, int on) { if (!h) return GX_ERR_INVALID; h->force_stream = on != 0; h->has_plan = false; return GX_OK; }
 
 int gx_last_explain_ms(gx_handle* h, float* ms) {
   if (!h || !ms) { gx_set_error("gx_last_explain_ms: NULL argument"); return GX_ERR_INVALID; }
@@ -437,9 +440,10 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
     tn += T.n; te += T.e_d; tp += T.npairs;
     int bytes = 0, idx16 = 0;
-    const int cls = task_smem_class(T, h->m, &bytes, &idx16);
+    const int cls = task_smem_class(T, h->m, h->force_stream, &bytes, &idx16);
     T.smem_bytes = bytes;
-    if (cls == kNumClasses - 1) gws_words = std::max<int64_t>(gws_words, bytes);
+    if (cls == kNumClasses - 1)
+      gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
     h->class_order[cls].push_back(t);
   }
   h->gws_stride_words = (gws_words + 3) / 4 * 4;
@@ -575,9 +579,19 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
   hd.init = hp->init;
   hd.seed = hp->seed;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
+  int stream_grid = 0;
   if (!h->class_order[kNumClasses - 1].empty()) {
-    const int last_grid = std::min<int>((int)h->class_order[kNumClasses - 1].size(), h->num_sms);
-    GX_CUDA_CHECK(h->d_gws.reserve((size_t)last_grid * h->gws_stride_words * 4));
+    // streaming class: one CTA per SM, fewer when the per-CTA slabs (node/edge state + 32 B per inner pair) would not fit
+    stream_grid = std::min<int>((int)h->class_order[kNumClasses - 1].size(), h->num_sms);
+    int maxnp = 0;
+    for (int32_t t : h->class_order[kNumClasses - 1]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
+    const int64_t per_cta = (h->gws_stride_words + (int64_t)maxnp * 8 + 4) * 4;
+    size_t free_b = 0, total_b = 0;
+    GX_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t budget = (int64_t)(free_b + h->d_gws.cap + h->d_pws.cap) * 8 / 10;
+    if (per_cta > budget) { gx_set_error("gx_explain_nodes: a task needs %lld MB of device workspace, %lld MB are free", (long long)(per_cta >> 20), (long long)(budget >> 20)); return GX_ERR_CUDA; }
+    stream_grid = (int)std::max<int64_t>(1, std::min<int64_t>(stream_grid, budget / per_cta));
+    GX_CUDA_CHECK(h->d_gws.reserve((size_t)stream_grid * h->gws_stride_words * 4));
   }
   // per-CTA pair-state slabs (one region per launch class, 8 floats per inner pair of its largest task)
   int64_t pws_off[kNumClasses + 1], pws_stride[kNumClasses];
@@ -589,7 +603,7 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
       int maxnp = 0;
       for (int32_t t : h->class_order[c]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
       pws_stride[c] = ((int64_t)maxnp * 8 + 3) / 4 * 4;
-      grids[c] = c == kNumClasses - 1 ? std::min<int>(nt, h->num_sms) : std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
+      grids[c] = c == kNumClasses - 1 ? stream_grid : std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
       pws_off[c] = acc_words;
       acc_words += pws_stride[c] * std::max(grids[c], 0);
     }
@@ -626,7 +640,8 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
       cfg.smem_bytes = c == kNumClasses - 2 ? kClasses[c].cap_bytes : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
-    GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    if (c == kNumClasses - 1) GX_CUDA_CHECK(gx_launch_explain_stream(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    else GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
     h->launches += 1;
     GX_CUDA_CHECK(cudaEventRecord(h->ev_join[c], h->side[c]));
     used.push_back(c);

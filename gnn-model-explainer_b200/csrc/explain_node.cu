@@ -600,7 +600,7 @@ cudaError_t launch_dims(const GxExplainLaunch& cfg, const ExplainArgs& args, cud
     if (cfg.threads <= 256) return launch_one<true, uint16_t, HID, EMB, 256>(cfg, args, s);
     return launch_one<true, uint16_t, HID, EMB, 512>(cfg, args, s);
   }
-  return launch_one<false, int32_t, HID, EMB, 512>(cfg, args, s);
+  return cudaErrorInvalidValue;  // tasks that do not fit shared memory belong to explain_stream.cu
 }
 
 }  // namespace

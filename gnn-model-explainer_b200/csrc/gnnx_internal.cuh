@@ -147,6 +147,32 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   return L;
 }
 
+// Global-memory slab of one task in the streaming kernel (explain_stream.cu: tasks whose state does not fit
+// shared memory).  Offsets in 4-byte words; the CSR / pair index arrays are read straight from the plan.
+struct GxStreamLayout {
+  int64_t a, P, Yh1, q1, dY1, Yh2, q2, dZ2, y, cnt1, cnt2, llist, llistB, llistO, gFp;
+  int64_t total_words;
+  int dp;
+};
+__host__ __device__ inline GxStreamLayout gx_make_stream_layout(int n, int n1, int n2, int e_d, int d, int hid, int nwarps) {
+  GxStreamLayout L;
+  const int dp = gx_round_up(d, 4);
+  L.dp = dp;
+  int64_t o = 0;
+  auto take = [&](int64_t words) { int64_t r = o; o += (words + 3) / 4 * 4; return r; };
+  L.a = take(e_d);                     // masked-adjacency value of every internal slot (rows >= n2: only their < n2 prefix is live)
+  L.P = take((int64_t)n * hid);        // (X . sF) W1 of every node
+  L.Yh1 = take((int64_t)n2 * hid); L.q1 = take(n2); L.dY1 = take((int64_t)n2 * hid);
+  L.Yh2 = take((int64_t)n1 * hid); L.q2 = take(n1); L.dZ2 = take((int64_t)n1 * hid);
+  L.y = take(n);
+  L.cnt1 = take(n2);                   // per row < n2: leading columns < n1
+  L.cnt2 = take(n);                    // per row: leading columns < n2
+  L.llist = take(n2); L.llistB = take(n2); L.llistO = take(n);
+  L.gFp = take((int64_t)nwarps * dp);
+  L.total_words = o;
+  return L;
+}
+
 // Shared-memory footprint of one graph-mode task (all `na` rows with at least one edge are computed at every layer).
 struct GxLayoutG {
   int X, U, Yh1, Yh2, Yh3, q, dZ2, dZ3, a, W1s, W1t, W2s, W2t, W3s, W3t, bs, cst, emb, dE, sF, F, mF, vF, gFp, zs, logit, Wp;
@@ -234,6 +260,10 @@ struct GxExplainLaunch {
 cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                               const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                               float* out_mask, float* out_feat, cudaStream_t s);
+cudaError_t gx_launch_explain_stream(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
+                                     const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
+                                     float* out_mask, float* out_feat, cudaStream_t s);
+constexpr int GX_STREAM_THREADS = 1024;
 int gx_explain_max_smem();
 struct GxGraphBatchDev {
   int32_t num_graphs, max_nodes, d;

@@ -212,6 +212,11 @@ class Engine:
         _abi.check(self._lib.gx_densify(self._h, _abi.GX_HOST, _np_ptr(_f32c(edge_mask)), _np_ptr(out)))
         return out
 
+    def debug_force_stream(self, on=True):
+        """Test knob: plan every task into the streaming kernel (explain_stream.cu) regardless of its size."""
+        self._lib.gx_debug_force_stream.argtypes = [C.c_void_p, C.c_int]
+        _abi.check(self._lib.gx_debug_force_stream(self._h, int(bool(on))))
+
     def launch_count(self):
         return int(self._lib.gx_launch_count(self._h))
 
