@@ -443,7 +443,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     const int cls = task_smem_class(T, h->m, h->force_stream, &bytes, &idx16);
     T.smem_bytes = bytes;
     if (cls == kNumClasses - 1)
-      gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
+      gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, T.npairs_in, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
     h->class_order[cls].push_back(t);
   }
   h->gws_stride_words = (gws_words + 3) / 4 * 4;

@@ -3,7 +3,7 @@
 //
 // Same arithmetic contract as explain_node.cu (explainer/explain.py:137-146,665-715,740-808 + autograd + Adam,
 // models.py:58-80,230-267,363-376), different data placement and a different contraction order:
-//   * one persistent CTA (1024 threads) per task, model weights and per-warp scratch in shared memory, every
+//   * one persistent CTA (768 threads) per task, model weights and per-warp scratch in shared memory, every
 //     per-node / per-edge array in a per-CTA global slab (L2 / HBM), the CSR and pair index arrays read in
 //     place from the plan (no per-task copy);
 //   * layer 1 is evaluated as A_m (X' W1) instead of (A_m X') W1: the d-wide feature row of a node is read
@@ -12,6 +12,10 @@
 //     bytes per edge than the U = A_m X order the shared-memory kernel uses for d <= hid;
 //   * dP = A_m^T dY1 needs, for every node j (also the outermost ones), its neighbours inside the layer-1 row
 //     set: the plan's level-partitioned rows give that as a prefix of row j (cnt2).
+//   * sparse aggregations stage the gathered hid-wide rows in shared memory with cp.async (LDGSTS, 16 B per lane,
+//     no registers held by loads in flight): a warp streams its rows as chunks of up to 32 edges, two chunks in
+//     flight across row boundaries, and reduces from shared memory (staged_rows);
+//   * the two dense passes over the d-wide feature rows (F0, B0) keep four rows per warp in flight in registers.
 // Phases per epoch (one __syncthreads each): F0 | F1 | F2 | S | B2 | B1 | B0 | P.
 // Pairs between two outermost nodes are regulariser-only scalar recurrences (outer_pairs_kernel).
 #include "explain_common.cuh"
@@ -19,20 +23,150 @@
 namespace {
 
 struct StreamSmem {
-  int W1s, W1t, W2s, W2t, W3s, bs, sF, F, mF, vF, zs, dE, dZ3, logit, Wp, total;
+  int W1s, W1t, W1m, W2s, W2t, W3s, bs, sF, F, mF, vF, zs, dE, dZ3, logit, Wp, stage, astage, stage_per_warp, total;
 };
+constexpr int kStageBufs = 2;                                                   // chunks in flight per warp
+__host__ __device__ constexpr int stage_chunk(int hid) { return hid <= 20 ? 32 : 16; }  // edges per chunk
+constexpr int kTileRows = 4;                                                    // feature rows per tile of the dense passes
+__host__ __device__ inline int tile_stride(int dp) { return gx_round_up(dp, 32) + 8; }  // bank-conflict-free row stride (floats)
 __host__ __device__ inline StreamSmem stream_smem(int dp, int hid, int emb, int C, int nwarps) {
   StreamSmem S;
   int o = 0;
   auto take = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
-  S.W1s = take(dp * hid); S.W1t = take(hid * dp); S.W2s = take(hid * hid); S.W2t = take(hid * hid);
+  S.W1s = take(dp * hid); S.W1t = take(hid * dp); S.W1m = take(dp * hid); S.W2s = take(hid * hid); S.W2t = take(hid * hid);
   S.W3s = take(hid * emb); S.bs = take(2 * hid + emb);
   S.sF = take(dp); S.F = take(dp); S.mF = take(dp); S.vF = take(dp);
   S.zs = take(nwarps * 128);
   S.dE = take(2 * hid); S.dZ3 = take(hid); S.logit = take(C < 32 ? 32 : C);
   S.Wp = take(C * (2 * hid + emb + 1) <= GX_WP_SMEM_MAX ? C * (2 * hid + emb + 1) : 0);
+  // per warp: the gathered hid-wide rows of the sparse passes, or two 4-row tiles of d-wide feature rows (+ their dP rows)
+  const int sp_rows = kStageBufs * stage_chunk(hid) * hid, sp_tiles = 2 * kTileRows * (tile_stride(dp) + hid);
+  S.stage_per_warp = gx_round_up(sp_rows > sp_tiles ? sp_rows : sp_tiles, 4);
+  S.stage = take(nwarps * S.stage_per_warp);
+  S.astage = take(nwarps * kStageBufs * stage_chunk(hid));        // their edge values
   S.total = o;
   return S;
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Sparse aggregation of the rows i = warp, warp + nwarps, ... < R of one warp:  z_i = sum_{e in [r0_i, r1_i)} a[e] f(src[icol[e]])
+// with hid-wide source rows.  The rows are streamed as chunks of <= CH edges (a chunk never spans two rows, an empty row is
+// one empty chunk).  Issuing side: lane l reads (icol, a) of edge l one chunk ahead into registers; H4 adjacent lanes then
+// copy one source row into the warp's staging buffer with cp.async (one 128-byte line per row and instruction),
+// kStageBufs chunks in flight across row boundaries.  Consuming side: lane = (edge slot, float4 index) reads the staged
+// rows, reduces the edge slots through `red` (128 floats) at the end of a row and calls epi(i, z) with the warp converged;
+// z is valid on lanes < H4 (lane q holds features 4q..4q+3).  bounds(i, r0, r1) returns the edge range of row i.
+// kDot: additionally gout[e] = <src[icol[e]], dotsrc[i]> for every edge e of row i (the edge-gradient dots of the layer,
+// taken while the gathered row is in shared memory anyway).
+template <int HID, bool kRelu, bool kDot, typename Bounds, typename Epi>
+__device__ __forceinline__ void staged_rows(int R, int warp, int nwarps, int lane, const int32_t* __restrict__ icol,
+                                            const float* a, const float* src, float* stage, float* astage, float* red,
+                                            const float* dotsrc, float* gout, Bounds bounds, Epi epi) {
+  constexpr int HS = HID, H4 = HID / 4, EPL = 32 / H4, CH = stage_chunk(HID), NB = kStageBufs;
+  constexpr int NK = (CH + EPL - 1) / EPL;
+  const int es = lane / H4, q = lane - es * H4;
+  const bool cons = es < EPL;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)(es * HS + 4 * q) * 4u;
+  const char* const src_q = reinterpret_cast<const char*>(src) + 16 * q;
+  int i_iss = warp, e_iss = 0, end_iss = 0;
+  if (i_iss < R) bounds(i_iss, e_iss, end_iss);
+  int i_con = i_iss, e_con = e_iss, end_con = end_iss;
+  int nx0 = 0, nx1 = 0;                                   // edge range of the issuing side's NEXT row, loaded one row ahead
+  if (i_iss + nwarps < R) bounds(i_iss + nwarps, nx0, nx1);
+  int c_nx = 0;
+  float a_nx = 0.f;
+  auto prefetch = [&]() {
+    const int e = e_iss + lane;
+    if (i_iss < R && lane < CH && e < end_iss) { c_nx = __ldg(icol + e); a_nx = a[e]; }
+  };
+  auto issue = [&](int buf) {
+    if (i_iss < R) {
+      const int nvalid = min(CH, end_iss - e_iss);
+      if (lane < nvalid) astage[buf * CH + lane] = a_nx;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int slot = k * EPL + es;
+        const int c = __shfl_sync(0xffffffffu, c_nx, slot & 31);
+        if (cons && slot < nvalid) {
+          const uint32_t d = stage_s + (uint32_t)((buf * CH + k * EPL) * HS) * 4u;
+          const char* g = src_q + (size_t)((uint32_t)c * (uint32_t)(HS * 4));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+        }
+      }
+      e_iss += CH;
+      if (e_iss >= end_iss) {
+        i_iss += nwarps;
+        e_iss = nx0; end_iss = nx1;
+        if (i_iss + nwarps < R) bounds(i_iss + nwarps, nx0, nx1);
+      }
+    }
+    cp_async_commit();
+    prefetch();
+  };
+  prefetch();
+#pragma unroll
+  for (int b = 0; b < NB; ++b) issue(b);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kDot && i_con < R && lane < 32 && cons) dv = ld4(dotsrc + i_con * HS + 4 * q);
+  int buf = 0;
+  while (i_con < R) {
+    cp_async_wait<NB - 1>();
+    __syncwarp();
+    const int cnt = min(CH, end_con - e_con);
+    const float* st = stage + buf * CH * HS + 4 * q;
+    const float* as_ = astage + buf * CH;
+    const int nsteps = (cnt + EPL - 1) / EPL;   // warp-uniform (<= 0 for an empty row)
+    for (int k = 0; k < nsteps; ++k) {
+      const int sidx = k * EPL + es;
+      const bool ok = cons && sidx < cnt;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float av = 0.f;
+      if (ok) { v = ld4(st + sidx * HS); av = as_[sidx]; }
+      if (kRelu) v = relu4(v);
+      fma4(acc, av, v);
+      if (kDot) {
+        float pd = fmaf(v.x, dv.x, fmaf(v.y, dv.y, fmaf(v.z, dv.z, v.w * dv.w)));
+        if (H4 == 8) {
+          pd += __shfl_xor_sync(0xffffffffu, pd, 1); pd += __shfl_xor_sync(0xffffffffu, pd, 2); pd += __shfl_xor_sync(0xffffffffu, pd, 4);
+        } else {   // H4 == 5: lanes es*5 .. es*5+4; only the q == 0 lane's sum is used
+          const float t1 = pd + __shfl_down_sync(0xffffffffu, pd, 1);
+          const float t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
+          pd = t2 + __shfl_down_sync(0xffffffffu, pd, 4);
+        }
+        if (ok && q == 0) gout[e_con + sidx] = pd;
+      }
+    }
+    e_con += CH;
+    const bool row_done = e_con >= end_con;
+    __syncwarp();
+    issue(buf);
+    buf = buf + 1 == NB ? 0 : buf + 1;
+    if (row_done) {
+      st4(red + lane * 4, acc);
+      __syncwarp();
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < H4) {
+#pragma unroll
+        for (int s2 = 0; s2 < EPL; ++s2) { const float4 o = ld4(red + (s2 * H4 + lane) * 4); z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w; }
+      }
+      __syncwarp();
+      epi(i_con, z);
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      i_con += nwarps;
+      if (i_con < R) {
+        bounds(i_con, e_con, end_con);
+        if (kDot && cons) dv = ld4(dotsrc + i_con * HS + 4 * q);
+      }
+    }
+  }
+  cp_async_wait<0>();
 }
 
 // this lane's float4 (features 4q..4q+3) of a feature row of the full graph
@@ -47,6 +181,135 @@ __device__ __forceinline__ float4 load_x4(const float* __restrict__ row, int q, 
   return v;
 }
 
+// F0, vector path: P[j] = X[j] (sF (.) W1) for all nodes.  A warp takes tiles of kTileRows feature rows, copied with
+// cp.async into its staging area (two tiles in flight); lane = (row r of the tile, feature slice s = f mod 8) keeps all
+// HID outputs of its row in registers, so one pass over W1m (shared memory) serves the four rows of the tile.
+template <int HID>
+__device__ __forceinline__ void dense_forward_tiles(int n, int d, int dp, int warp, int nwarps, int lane,
+                                                    const float* __restrict__ feat, const int32_t* __restrict__ lo2gid,
+                                                    const float* W1m, float* xb, float* P) {
+  constexpr int HS = HID, H4 = HID / 4, TR = kTileRows;
+  const int D4 = dp / 4, xs = tile_stride(dp);
+  const int ntile = (n + TR - 1) / TR;
+  const int r = lane >> 3, sl = lane & 7;
+  int t_iss = warp;
+  auto gid_of = [&](int t) { const int row = t * TR + lane; return (t < ntile && lane < TR && row < n) ? __ldg(lo2gid + row) : -1; };
+  int g_nx = gid_of(t_iss);
+  auto issue = [&](int buf) {
+    if (t_iss < ntile) {
+#pragma unroll
+      for (int rr = 0; rr < TR; ++rr) {
+        const int gid = __shfl_sync(0xffffffffu, g_nx, rr);
+        if (gid >= 0 && lane < D4) cp_async16(xb + (buf * TR + rr) * xs + 4 * lane, feat + (int64_t)gid * d + 4 * lane);
+      }
+      t_iss += nwarps;
+      g_nx = gid_of(t_iss);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  int buf = 0;
+  for (int t = warp; t < ntile; t += nwarps) {
+    cp_async_wait<1>();
+    __syncwarp();
+    float acc[HID];
+#pragma unroll
+    for (int h = 0; h < HID; ++h) acc[h] = 0.f;
+    const float* xr = xb + (buf * TR + r) * xs;
+    for (int f = sl; f < dp; f += 8) {
+      const float xv = xr[f];
+      const float* w = W1m + f * HS;
+#pragma unroll
+      for (int h4 = 0; h4 < H4; ++h4) {
+        const float4 w4 = ld4(w + 4 * h4);
+        acc[4 * h4] = fmaf(xv, w4.x, acc[4 * h4]); acc[4 * h4 + 1] = fmaf(xv, w4.y, acc[4 * h4 + 1]);
+        acc[4 * h4 + 2] = fmaf(xv, w4.z, acc[4 * h4 + 2]); acc[4 * h4 + 3] = fmaf(xv, w4.w, acc[4 * h4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HID; ++h) {
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 2);
+      acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 4);
+    }
+    const int row = t * TR + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h4 = 0; h4 < H4; ++h4)
+      if (sl == h4) v = make_float4(acc[4 * h4], acc[4 * h4 + 1], acc[4 * h4 + 2], acc[4 * h4 + 3]);
+    if (row < n && sl < H4) st4(P + row * HS + 4 * sl, v);
+    __syncwarp();
+    issue(buf);
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+// B0, vector path: this warp's share of dL/dsF = sum_j X_j (.) (dP_j W1^T).  Same tiling; lane l owns features 4l..4l+3
+// and keeps the four rows' products in registers, so one pass over W1t serves the tile.
+template <int HID>
+__device__ __forceinline__ float4 dense_backward_tiles(int n, int d, int dp, int warp, int nwarps, int lane,
+                                                       const float* __restrict__ feat, const int32_t* __restrict__ lo2gid,
+                                                       const float* W1t, float* xb, const float* dP) {
+  constexpr int HS = HID, H4 = HID / 4, TR = kTileRows;
+  const int D4 = dp / 4, xs = tile_stride(dp);
+  float* const pb = xb + 2 * TR * xs;
+  const int ntile = (n + TR - 1) / TR;
+  int t_iss = warp;
+  auto gid_of = [&](int t) { const int row = t * TR + lane; return (t < ntile && lane < TR && row < n) ? __ldg(lo2gid + row) : -1; };
+  int g_nx = gid_of(t_iss);
+  auto issue = [&](int buf) {
+    if (t_iss < ntile) {
+#pragma unroll
+      for (int rr = 0; rr < TR; ++rr) {
+        const int gid = __shfl_sync(0xffffffffu, g_nx, rr);
+        if (gid >= 0 && lane < D4) cp_async16(xb + (buf * TR + rr) * xs + 4 * lane, feat + (int64_t)gid * d + 4 * lane);
+      }
+      if (lane < TR * H4) {
+        const int rr = lane / H4, c = lane - rr * H4, row = t_iss * TR + rr;
+        if (row < n) cp_async16(pb + (buf * TR + rr) * HS + 4 * c, dP + row * HS + 4 * c);
+      }
+      t_iss += nwarps;
+      g_nx = gid_of(t_iss);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int buf = 0;
+  for (int t = warp; t < ntile; t += nwarps) {
+    cp_async_wait<1>();
+    __syncwarp();
+    if (lane < D4) {
+      float4 tq[TR];
+#pragma unroll
+      for (int rr = 0; rr < TR; ++rr) tq[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* pr = pb + buf * TR * HS;
+#pragma unroll 4
+      for (int h = 0; h < HID; ++h) {
+        const float4 w4 = ld4(W1t + h * dp + 4 * lane);
+#pragma unroll
+        for (int rr = 0; rr < TR; ++rr) fma4(tq[rr], pr[rr * HS + h], w4);
+      }
+#pragma unroll
+      for (int rr = 0; rr < TR; ++rr) {
+        if (t * TR + rr < n) {
+          const float4 x = ld4(xb + (buf * TR + rr) * xs + 4 * lane);
+          gacc.x = fmaf(tq[rr].x, x.x, gacc.x); gacc.y = fmaf(tq[rr].y, x.y, gacc.y);
+          gacc.z = fmaf(tq[rr].z, x.z, gacc.z); gacc.w = fmaf(tq[rr].w, x.w, gacc.w);
+        }
+      }
+    }
+    __syncwarp();
+    issue(buf);
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+  return gacc;
+}
+
 // first slot in [r0,r1) whose column is >= bound (columns are partitioned by level, so the predicate is monotone)
 __device__ __forceinline__ int prefix_below(const int32_t* __restrict__ icol, int r0, int r1, int bound) {
   int lo = r0, hi = r1;
@@ -57,29 +320,12 @@ __device__ __forceinline__ int prefix_below(const int32_t* __restrict__ icol, in
   return lo - r0;
 }
 
-// warp w builds the ascending list of rows i < R with len(i) > kLongRow; returns the count (and, in *below,
-// how many of them are < split)
-template <typename LenF>
-__device__ __forceinline__ int build_long_list(int R, int split, int32_t* list, int lane, LenF len, int* below) {
-  int cnt = 0, cb = 0;
-  for (int b0 = 0; b0 < R; b0 += 32) {
-    const int i = b0 + lane;
-    const bool lg = i < R && len(i) > kLongRow;
-    const uint32_t bal = __ballot_sync(0xffffffffu, lg);
-    if (lg) list[cnt + __popc(bal & ((1u << lane) - 1u))] = i;
-    cnt += __popc(bal);
-    cb += __popc(__ballot_sync(0xffffffffu, lg && i < split));
-  }
-  *below = cb;
-  return cnt;
-}
-
 template <int HID, int EMB, int NT>
 __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_task;
-  __shared__ int s_long[4];  // long rows: among [0,n2), among [0,n1), rows < n2 with a long < n1 prefix, rows < n with a long < n2 prefix
-  static_assert(HID % 4 == 0 && EMB % 4 == 0 && HID <= 32 && EMB <= 32, "hidden widths: multiples of 4, <= 32");
+  __shared__ long long s_ph[9];   // debug: per-phase cycle sums of the CTA's first task + last stamp
+  static_assert((HID == 20 || HID == 32) && EMB % 4 == 0 && EMB <= 32, "hidden width 20 or 32 (others are zero-padded to 32 by gx_set_model)");
   constexpr int HS = HID, H4 = HID / 4, PD = 2 * HID + EMB;
   constexpr int nwarps = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,6 +338,9 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
   float* const W1s = sm + S.W1s; float* const W1t = sm + S.W1t; float* const W2s = sm + S.W2s; float* const W2t = sm + S.W2t;
   float* const W3s = sm + S.W3s; float* const bs = sm + S.bs; float* const sF = sm + S.sF; float* const Fm = sm + S.F;
   float* const mF = sm + S.mF; float* const vF = sm + S.vF; float* const zw = sm + S.zs + warp * 128;
+  float* const stage = sm + S.stage + warp * S.stage_per_warp;
+  float* const W1m = sm + S.W1m;
+  float* const astage = sm + S.astage + warp * (kStageBufs * stage_chunk(HID));
   float* const dE = sm + S.dE; float* const dZ3 = sm + S.dZ3; float* const logit = sm + S.logit;
   const bool wp_smem = C * (PD + 1) <= GX_WP_SMEM_MAX;
   const float* const Wpp = wp_smem ? sm + S.Wp : m.Wp;
@@ -129,7 +378,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
     const int n = Tp->n, n1 = Tp->n1, n2 = Tp->n2, e_d = Tp->e_d, np = Tp->npairs_in;
     const int gt = Tp->gt_label;
     const int64_t node_off = Tp->node_off, rp_off = Tp->rp_off, edge_off = Tp->edge_off, pair_off = Tp->pair_off;
-    const GxStreamLayout L = gx_make_stream_layout(n, n1, n2, e_d, d, HID, nwarps);
+    const GxStreamLayout L = gx_make_stream_layout(n, n1, n2, e_d, np, d, HID, nwarps);
     const int32_t* __restrict__ lo2gid = A.plan.lo2gid + node_off;
     const int32_t* const irp = A.plan.irowptr + rp_off;
     const int32_t* const icol = A.plan.icol + edge_off;
@@ -138,17 +387,15 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
     const int32_t* __restrict__ poij = A.plan.pair_oij + pair_off; const int32_t* __restrict__ poji = A.plan.pair_oji + pair_off;
     float* const a = slab + L.a; float* const P = slab + L.P; float* const Yh1 = slab + L.Yh1; float* const q1 = slab + L.q1;
     float* const dY1 = slab + L.dY1; float* const Yh2 = slab + L.Yh2; float* const q2 = slab + L.q2; float* const dZ2 = slab + L.dZ2;
-    float* const yv = slab + L.y; float* const gFp = slab + L.gFp;
+    float* const lapg = slab + L.lapg; float* const gFp = slab + L.gFp;
     int32_t* const cnt1 = reinterpret_cast<int32_t*>(slab + L.cnt1); int32_t* const cnt2 = reinterpret_cast<int32_t*>(slab + L.cnt2);
-    int32_t* const llist = reinterpret_cast<int32_t*>(slab + L.llist); int32_t* const llistB = reinterpret_cast<int32_t*>(slab + L.llistB);
-    int32_t* const llistO = reinterpret_cast<int32_t*>(slab + L.llistO);
+    float* const dP = slab + L.dP; float* const gE = slab + L.gE;
     float2* const MM = MM0; float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
     const float nn = (float)n * (float)n;
     const float ent_over_nn = hp.c_ent / nn;
     const float lap_over_nn = hp.c_lap / nn;
 
     // ------------------------------------------------------------------ per-task state
-    for (int i = tid; i < n; i += NT) yv[i] = (float)__ldg(A.g.pred_label + lo2gid[i]);
     for (int f = tid; f < dp; f += NT) { sF[f] = 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f; }  // feat_mask = 0 (explain.py:633-643)
     {
       const float m0_std = sqrtf(2.0f / (float)n);  // gain('relu') * sqrt(2/(n+n)) (explain.py:647-651)
@@ -170,46 +417,42 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         const float a0 = 0.5f * (Si + Sj);  // explain.py:665-678
         a[ppij[p]] = a0;
         a[ppji[p]] = a0;
+        {   // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2 (explain.py:780-793): constant over the epochs
+          const float yd = (float)__ldg(A.g.pred_label + lo2gid[pi[p]]) - (float)__ldg(A.g.pred_label + lo2gid[pj[p]]);
+          lapg[p] = lap_over_nn * yd * yd;
+        }
         if (hp.iters == 0) {
           A.out_mask[edge_off + oij] = a0;
           A.out_mask[edge_off + oji] = a0;
         }
       }
     }
+    for (int e = tid; e < e_d; e += NT) gE[e] = 0.f;   // slots outside the < n2 prefixes are never written and must read as 0
     for (int i = tid; i < n; i += NT) {
       const int r0 = irp[i], r1 = irp[i + 1];
       cnt2[i] = prefix_below(icol, r0, r1, n2);
       if (i < n2) cnt1[i] = prefix_below(icol, r0, r1, n1);
     }
     __syncthreads();
-    if (warp == 0) {
-      int below;
-      const int c = build_long_list(n2, n1, llist, lane, [&](int i) { return irp[i + 1] - irp[i]; }, &below);
-      if (lane == 0) { s_long[0] = c; s_long[1] = below; }
-    } else if (warp == 1) {
-      int below;
-      const int c = build_long_list(n2, 0, llistB, lane, [&](int i) { return cnt1[i]; }, &below);
-      if (lane == 0) s_long[2] = c;
-    } else if (warp == 2) {
-      int below;
-      const int c = build_long_list(n, 0, llistO, lane, [&](int i) { return cnt2[i]; }, &below);
-      if (lane == 0) s_long[3] = c;
-    }
-    __syncthreads();
-    const int nlongF1 = s_long[0], nlongF2 = s_long[1], nlongB1 = s_long[2], nlongO = s_long[3];
 
+    const int np1 = prefix_below(pi, 0, np, n1);   // pairs are sorted by i: the first np1 touch rows < n1 (layer-2/3 terms)
     // ------------------------------------------------------------------ epochs
+    const bool timed = A.dbg != nullptr && qi == 0;
+#define GXS_MARK(k) if (timed && warp == 0) { const long long c_ = clock64(); if (lane == 0) { s_ph[k] += c_ - s_ph[8]; s_ph[8] = c_; } __syncwarp(); }
+    if (timed && warp == 0) { const long long c_ = clock64(); if (lane == 0) { for (int k = 0; k < 8; ++k) s_ph[k] = 0; s_ph[8] = c_; } __syncwarp(); }
     for (int it = 1; it <= hp.iters; ++it) {
       // ---- F0: all nodes: P = (X . sigmoid(feat_mask)) W1                         (explain.py:707, models.py:70-71)
-      {
+      if (xvec) {
+        for (int idx = tid; idx < dp * HS; idx += NT) W1m[idx] = W1s[idx] * sF[idx / HS];   // fold the feature mask into W1
+        __syncthreads();
+        dense_forward_tiles<HID>(n, d, dp, warp, nwarps, lane, A.g.feat, lo2gid, W1m, stage, P);
+      } else {
         const float4 s4 = lane < D4 ? ld4(sF + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int chunk = (D4 + epi - 1) / epi;            // the four lane groups split the feature axis
         const int f0 = G.grp * chunk, f1 = min(D4, f0 + chunk);
-        for (int j = warp; j < n; j += nwarps) {
-          if (lane < D4) {
-            const float4 x = load_x4(A.g.feat + (int64_t)lo2gid[j] * d, lane, d, xvec);
-            st4(zw + 4 * lane, make_float4(x.x * s4.x, x.y * s4.y, x.z * s4.z, x.w * s4.w));
-          }
+        for (int j = warp; j < n; j += nwarps) {     // (rare path: d % 4 != 0, scalar feature loads)
+          const float4 x = lane < D4 ? load_x4(A.g.feat + (int64_t)lo2gid[j] * d, lane, d, false) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lane < D4) st4(zw + 4 * lane, make_float4(x.x * s4.x, x.y * s4.y, x.z * s4.z, x.w * s4.w));
           __syncwarp();
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           if (q < H4 && f0 < f1) acc = group_dense(zw + 4 * f0, f1 - f0, W1s + 4 * f0 * HS, HS, q, acc);
@@ -223,41 +466,36 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         }
       }
       __syncthreads();
+      GXS_MARK(0)
       // ---- F1: rows [0,n2): Y1 = A_m P + b1 ; row normalise                                   (models.py:70-78)
-      {
-        const int ntask = nlongF1 + (n2 + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
-          float4 z;
-          const int i = row_task_gather<int32_t, false, true>(t, nlongF1, llist, n2, G, H4, irp, icol, a, P, HS, (const int32_t*)nullptr, zw, z);
-          const bool act = i >= 0;
+      staged_rows<HID, false, false>(n2, warp, nwarps, lane, icol, a, P, stage, astage, zw, nullptr, nullptr,
+        [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
+        [&](int i, float4 z) {
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (act && q < H4) { const float4 b = ld4(bs + 4 * q); y = make_float4(z.x + b.x, z.y + b.y, z.z + b.z, z.w + b.w); }
-          const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
+          if (lane < H4) { const float4 b = ld4(bs + 4 * lane); y = make_float4(z.x + b.x, z.y + b.y, z.z + b.z, z.w + b.w); }
+          const float ss = warp_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w);
           const float qn = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(p=2, dim=2), eps 1e-12
-          if (act && q < H4) st4(Yh1 + i * HS + 4 * q, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
-          if (act && q == 0) q1[i] = qn;
-        }
-      }
+          if (lane < H4) st4(Yh1 + i * HS + 4 * lane, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
+          if (lane == 0) q1[i] = qn;
+        });
       __syncthreads();
+      GXS_MARK(1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
-      {
-        const int ntask = nlongF2 + (n1 + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
-          float4 z;
-          const int i = row_task_gather<int32_t, true, true>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, (const int32_t*)nullptr, zw, z);
-          const bool act = i >= 0;
-          if (act && q < H4) st4(zw + lane * 4, z);
+      staged_rows<HID, true, false>(n1, warp, nwarps, lane, icol, a, Yh1, stage, astage, zw, nullptr, nullptr,
+        [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
+        [&](int i, float4 z) {
+          if (lane < H4) st4(zw + 4 * lane, z);
           __syncwarp();
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (act && q < H4) y = group_dense(zw + G.gbase * 4, H4, W2s, HS, q, ld4(bs + HID + 4 * q));
-          const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
+          if (lane < H4) y = group_dense(zw, H4, W2s, HS, lane, ld4(bs + HID + 4 * lane));
+          const float ss = warp_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w);
           const float qn = fmaxf(sqrtf(ss), 1e-12f);
-          if (act && q < H4) st4(Yh2 + i * HS + 4 * q, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
-          if (act && q == 0) q2[i] = qn;
+          if (lane < H4) st4(Yh2 + i * HS + 4 * lane, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
+          if (lane == 0) q2[i] = qn;
           __syncwarp();
-        }
-      }
+        });
       __syncthreads();
+      GXS_MARK(2)
       // ---- S: row r (= level-order id 0): layer 3, readout, softmax, -log p[gt], layer-3 backward
       if (warp == 0) {
         {
@@ -318,6 +556,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         if (lane < HID) dZ3[lane] = dot_v4(zw, W3s + lane * EMB, EMB / 4);
       }
       __syncthreads();
+      GXS_MARK(3)
       // ---- B2: rows {r} U N(r): dYh2 = dEmb2 (row r) + a[r,j] dZ3 (j in N(r)), relu', normalise', dZ2 = dY2 W2^T
       {
         const int r0 = irp[0];
@@ -357,44 +596,43 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         }
       }
       __syncthreads();
+      GXS_MARK(4)
       // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise' -> dY1
-      {
-        const int ntask = nlongB1 + (n2 + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
-          float4 dh;
-          const int i = row_task_gather<int32_t, false, true>(t, nlongB1, llistB, n2, G, H4, irp, icol, a, dZ2, HS, cnt1, zw, dh);
-          const bool act = i >= 0;
+      staged_rows<HID, false, false>(n2, warp, nwarps, lane, icol, a, dZ2, stage, astage, zw, nullptr, nullptr,
+        [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt1[i]; },
+        [&](int i, float4 dh) {
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
-          if (act && q < H4) {
-            yh = ld4(Yh1 + i * HS + 4 * q);
-            if (i == 0) { const float4 e4 = ld4(dE + 4 * q); dh.x += e4.x; dh.y += e4.y; dh.z += e4.z; dh.w += e4.w; }
+          if (lane < H4) {
+            yh = ld4(Yh1 + i * HS + 4 * lane);
+            if (i == 0) { const float4 e4 = ld4(dE + 4 * lane); dh.x += e4.x; dh.y += e4.y; dh.z += e4.z; dh.w += e4.w; }
             dy.x = yh.x > 0.f ? dh.x : 0.f; dy.y = yh.y > 0.f ? dh.y : 0.f;
             dy.z = yh.z > 0.f ? dh.z : 0.f; dy.w = yh.w > 0.f ? dh.w : 0.f;
           }
-          const float sdot = group_sum(yh.x * dy.x + yh.y * dy.y + yh.z * dy.z + yh.w * dy.w, G);
-          if (act && q < H4) {
+          const float sdot = warp_sum(yh.x * dy.x + yh.y * dy.y + yh.z * dy.z + yh.w * dy.w);
+          if (lane < H4) {
             const float qn = q1[i];
-            st4(dY1 + i * HS + 4 * q, make_float4((dy.x - yh.x * sdot) / qn, (dy.y - yh.y * sdot) / qn,
-                                                  (dy.z - yh.z * sdot) / qn, (dy.w - yh.w * sdot) / qn));
+            st4(dY1 + i * HS + 4 * lane, make_float4((dy.x - yh.x * sdot) / qn, (dy.y - yh.y * sdot) / qn,
+                                                     (dy.z - yh.z * sdot) / qn, (dy.w - yh.w * sdot) / qn));
           }
-        }
-      }
+        });
       __syncthreads();
-      // ---- B0: all nodes: dP = A_m^T dY1 (columns < n2 of row j), dL/dsF += X_j (.) (dP_j W1^T)
+      GXS_MARK(5)
+      // ---- B0: all nodes: dP = A_m^T dY1 (columns < n2 of row j), then dL/dsF += X_j (.) (dP_j W1^T) for the warp's own rows
       {
+        staged_rows<HID, false, true>(n, warp, nwarps, lane, icol, a, dY1, stage, astage, zw, P, gE,
+          [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; },
+          [&](int i, float4 z) { if (lane < H4) st4(dP + i * HS + 4 * lane, z); });
+        __syncthreads();   // the tiles below read dP rows written by other warps
         float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int ntask = nlongO + (n + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
-          float4 z;
-          const int i = row_task_gather<int32_t, false, true>(t, nlongO, llistO, n, G, H4, irp, icol, a, dY1, HS, cnt2, zw, z);
-          for (int g2 = 0; g2 < epi; ++g2) {
-            const int ig = __shfl_sync(0xffffffffu, i, g2 * 8);
-            if (ig < 0) continue;  // warp-uniform
-            if (G.grp == g2 && q < H4) st4(zw + 4 * q, z);
+        if (xvec) {
+          gacc = dense_backward_tiles<HID>(n, d, dp, warp, nwarps, lane, A.g.feat, lo2gid, W1t, stage, dP);
+        } else {
+          for (int j = warp; j < n; j += nwarps) {
+            if (lane < H4) st4(zw + 4 * lane, ld4(dP + j * HS + 4 * lane));
             __syncwarp();
             if (lane < D4) {
               const float4 o = group_dense(zw, H4, W1t, dp, lane, make_float4(0.f, 0.f, 0.f, 0.f));
-              const float4 x = load_x4(A.g.feat + (int64_t)lo2gid[ig] * d, lane, d, xvec);
+              const float4 x = load_x4(A.g.feat + (int64_t)lo2gid[j] * d, lane, d, false);
               gacc.x = fmaf(o.x, x.x, gacc.x); gacc.y = fmaf(o.y, x.y, gacc.y);
               gacc.z = fmaf(o.z, x.z, gacc.z); gacc.w = fmaf(o.w, x.w, gacc.w);
             }
@@ -404,6 +642,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         if (lane < D4) st4(gFp + warp * dp + 4 * lane, gacc);  // per-warp partial, summed in warp order below
       }
       __syncthreads();
+      GXS_MARK(6)
       // ---- P: per undirected edge: dA_ij, dA_ji, symmetrise, regularisers, Adam, next mask value
       {
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
@@ -422,15 +661,17 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
           sF[f] = sigmoid_f(Fv);
         }
+        // The layer-1 dots <dY1[i], P[j]> and <dY1[j], P[i]> were taken in B0 while the gathered rows were staged (gE);
+        // only the few pairs touching rows < n1 (listed first) carry layer-2/3 terms.
         for (int p = tid; p < np; p += NT) {
-          const int i = pi[p], j = pj[p];   // i < j, i < n2
-          const float yd = yv[i] - yv[j];
-          float Gd = lap_over_nn * yd * yd;  // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2 (explain.py:780-793)
-          Gd += dot_v4(dY1 + i * HS, P + j * HS, H4);
-          if (j < n2) Gd += dot_v4(dY1 + j * HS, P + i * HS, H4);
-          if (i < n1) Gd += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
-          if (j < n1) Gd += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
-          if (i == 0) Gd += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
+          const int sij = ppij[p], sji = ppji[p];
+          float Gd = lapg[p] + gE[sji] + gE[sij];
+          if (p < np1) {
+            const int i = pi[p], j = pj[p];   // i < j, i < n1
+            Gd += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
+            if (j < n1) Gd += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
+            if (i == 0) Gd += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
+          }
           Gd *= 0.5f;  // sym_mask = (S + S^T)/2 (explain.py:671)
           float2 Mv = MM[p];
           const float2 Sv = SS[p];
@@ -447,8 +688,8 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
           const float2 Sn = make_float2(sigmoid_fast(Mv.x), sigmoid_fast(Mv.y));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
-          a[ppij[p]] = an;
-          a[ppji[p]] = an;
+          a[sij] = an;
+          a[sji] = an;
           if (last) {
             A.out_mask[edge_off + poij[p]] = an;
             A.out_mask[edge_off + poji[p]] = an;
@@ -456,15 +697,20 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         }
       }
       __syncthreads();
+      GXS_MARK(7)
+    }
+    if (timed && tid == 0) {
+      float* o = A.dbg + (1 << 19);
+      for (int k = 0; k < 8; ++k) o[k] = (float)s_ph[k];
+      o[8] = (float)n; o[9] = (float)n1; o[10] = (float)n2; o[11] = (float)np; o[12] = (float)e_d; o[13] = (float)NT;
     }
     if (A.out_feat != nullptr)
       for (int f = tid; f < d; f += NT) A.out_feat[(int64_t)task_id * d + f] = sF[f];
   }
 }
 
-template <int HID, int EMB>
-cudaError_t launch_stream(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  constexpr int NT = GX_STREAM_THREADS;
+template <int HID, int EMB, int NT>
+cudaError_t launch_stream_nt(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
   auto kern = explain_stream_kernel<HID, EMB, NT>;
   const StreamSmem S = stream_smem(gx_round_up(args.m.d, 4), HID, EMB, args.m.C, NT / 32);
   const int bytes = S.total * 4;
@@ -472,6 +718,10 @@ cudaError_t launch_stream(const GxExplainLaunch& cfg, const ExplainArgs& args, c
   if (e != cudaSuccess) return e;
   kern<<<cfg.grid, NT, bytes, s>>>(args);
   return cudaGetLastError();
+}
+template <int HID, int EMB>
+cudaError_t launch_stream(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
+  return launch_stream_nt<HID, EMB, GX_STREAM_THREADS>(cfg, args, s);
 }
 
 }  // namespace
@@ -484,7 +734,7 @@ cudaError_t gx_launch_explain_stream(const GxExplainLaunch& cfg, const GxGraphDe
   args.gws = cfg.gws; args.gws_stride_words = cfg.gws_stride_words;
   args.pws = cfg.pws; args.pws_stride_words = cfg.pws_stride_words;
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
-  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = nullptr;
+  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg;
   if (m.hid == 20 && m.emb == 20) return launch_stream<20, 20>(cfg, args, s);
   if (m.hid == 32 && m.emb == 32) return launch_stream<32, 32>(cfg, args, s);   // any width <= 32, zero-padded by gx_set_model
   return cudaErrorInvalidValue;

@@ -150,24 +150,25 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
 // Global-memory slab of one task in the streaming kernel (explain_stream.cu: tasks whose state does not fit
 // shared memory).  Offsets in 4-byte words; the CSR / pair index arrays are read straight from the plan.
 struct GxStreamLayout {
-  int64_t a, P, Yh1, q1, dY1, Yh2, q2, dZ2, y, cnt1, cnt2, llist, llistB, llistO, gFp;
+  int64_t a, gE, P, dP, Yh1, q1, dY1, Yh2, q2, dZ2, lapg, cnt1, cnt2, gFp;
   int64_t total_words;
   int dp;
 };
-__host__ __device__ inline GxStreamLayout gx_make_stream_layout(int n, int n1, int n2, int e_d, int d, int hid, int nwarps) {
+__host__ __device__ inline GxStreamLayout gx_make_stream_layout(int n, int n1, int n2, int e_d, int np_in, int d, int hid, int nwarps) {
   GxStreamLayout L;
   const int dp = gx_round_up(d, 4);
   L.dp = dp;
   int64_t o = 0;
   auto take = [&](int64_t words) { int64_t r = o; o += (words + 3) / 4 * 4; return r; };
   L.a = take(e_d);                     // masked-adjacency value of every internal slot (rows >= n2: only their < n2 prefix is live)
+  L.gE = take(e_d);                    // layer-1 edge-gradient dot <dY1[col], P[row]> of every live slot (0 elsewhere)
   L.P = take((int64_t)n * hid);        // (X . sF) W1 of every node
+  L.dP = take((int64_t)n * hid);       // A_m^T dY1 of every node
   L.Yh1 = take((int64_t)n2 * hid); L.q1 = take(n2); L.dY1 = take((int64_t)n2 * hid);
   L.Yh2 = take((int64_t)n1 * hid); L.q2 = take(n1); L.dZ2 = take((int64_t)n1 * hid);
-  L.y = take(n);
+  L.lapg = take(np_in);               // per inner pair: its (epoch-invariant) Laplacian-regulariser gradient
   L.cnt1 = take(n2);                   // per row < n2: leading columns < n1
   L.cnt2 = take(n);                    // per row: leading columns < n2
-  L.llist = take(n2); L.llistB = take(n2); L.llistO = take(n);
   L.gFp = take((int64_t)nwarps * dp);
   L.total_words = o;
   return L;
@@ -263,7 +264,7 @@ cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, c
 cudaError_t gx_launch_explain_stream(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                                      const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                                      float* out_mask, float* out_feat, cudaStream_t s);
-constexpr int GX_STREAM_THREADS = 1024;
+constexpr int GX_STREAM_THREADS = 768;  // 24 warps: 80 registers per thread, 5 KB of cp.async staging per warp
 int gx_explain_max_smem();
 struct GxGraphBatchDev {
   int32_t num_graphs, max_nodes, d;
