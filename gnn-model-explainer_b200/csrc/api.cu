@@ -531,8 +531,10 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
                      float* edge_mask, float* feat_mask) {
   if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_nodes: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_plan) { gx_set_error("gx_explain_nodes: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
-  if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built"); return GX_ERR_UNSUPPORTED; }
-  if (hp->mask_bias != 0) { gx_set_error("gx_explain_nodes: --mask-bias is not built"); return GX_ERR_UNSUPPORTED; }
+  // mask_act "ReLU": the reference's entropy term takes log(1 - relu(M)) with M ~ N(1, 2/n) -> NaN masks from step 1 (explain.py:755-770;
+  // pinned by tests/test_oracle.py): nothing to reproduce.  mask_bias: the bias parameter starts at 0 where ReLU6'(0) = 0, so Adam never
+  // moves it and the result equals the default run bit for bit (explain.py:657-660,673-676; same test): accepted, no extra state.
+  if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_nodes: num_epochs < 1"); return GX_ERR_INVALID; }
   if (hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_nodes: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
   if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
@@ -764,7 +766,7 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
                       float* edge_mask, float* feat_mask) {
   if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_graphs: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_gplan) { gx_set_error("gx_explain_graphs: no plan (call gx_plan_graphs)"); return GX_ERR_INVALID; }
-  if (hp->mask_act != 0 || hp->mask_bias != 0) { gx_set_error("gx_explain_graphs: mask_act/mask_bias variants are not built"); return GX_ERR_UNSUPPORTED; }
+  if (hp->mask_act != 0) { gx_set_error("gx_explain_graphs: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_graphs: num_epochs < 1"); return GX_ERR_INVALID; }
   if (hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_graphs: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));

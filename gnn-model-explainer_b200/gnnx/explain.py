@@ -86,9 +86,10 @@ class Explainer:
         self.print_training = print_training
         self._neighborhoods = None
         if getattr(args, "mask_act", "sigmoid") != "sigmoid":
-            raise NotImplementedError("mask_act=%r is not built (default: sigmoid)" % args.mask_act)
-        if getattr(args, "mask_bias", False):
-            raise NotImplementedError("--mask-bias is not built")
+            raise NotImplementedError("mask_act=%r is not built (default: sigmoid; the reference's ReLU variant returns NaN masks, "
+                                      "tests/test_oracle.py)" % args.mask_act)
+        # args.mask_bias: accepted.  The reference's bias matrix starts at 0 where ReLU6 has zero gradient, Adam never moves it and the
+        # masks equal the default run bit for bit (explain.py:657-660,673-676; pinned by tests/test_oracle.py) -- no extra state needed.
         if getattr(args, "opt", "adam") != "adam" or getattr(args, "opt_scheduler", "none") != "none":
             raise NotImplementedError("only Adam without scheduler (explainer_main.py defaults) is built")
         if getattr(model, "bn", False):

@@ -64,7 +64,7 @@ typedef struct gx_hparams {
   float coef_ent;        /* coeffs["ent"] = 1.0                                           */
   float coef_lap;        /* coeffs["lap"] = 1.0 (forced to 0 in graph mode)               */
   int32_t mask_act;      /* 0 = sigmoid (args.mask_act default); others GX_ERR_UNSUPPORTED */
-  int32_t mask_bias;     /* args.mask_bias; non-zero -> GX_ERR_UNSUPPORTED                */
+  int32_t mask_bias;     /* args.mask_bias: accepted; a no-op exactly as in the reference (bias stays 0: ReLU6'(0)=0) */
   int32_t init;          /* GX_INIT_*                                                     */
   uint64_t seed;         /* GX_INIT_PHILOX: stream seed                                   */
 } gx_hparams;

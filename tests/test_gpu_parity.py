@@ -346,7 +346,14 @@ def test_error_behaviour(tmp_path):
     eng2 = util.make_engine(fx)
     eng2.plan_nodes([0], 3)
     with pytest.raises(_abi.GnnxError):
-        eng2.explain_nodes_host(eng2.make_hparams(mask_bias=1), np.zeros(10000, np.float32), np.zeros(10000, np.float32))
+        eng2.explain_nodes_host(eng2.make_hparams(mask_act=1), np.zeros(10000, np.float32), np.zeros(10000, np.float32))
+    # --mask-bias is accepted and, as in the reference (tests/test_oracle.py), changes nothing
+    pl = eng2.plan_nodes([0, 7], 3)
+    m0 = np.random.default_rng(0).normal(1, 0.3, pl.total_edges).astype(np.float32)
+    o1 = np.zeros(pl.total_edges, np.float32); o2 = np.zeros(pl.total_edges, np.float32)
+    eng2.explain_nodes_host(eng2.make_hparams(num_epochs=10), m0, o1)
+    eng2.explain_nodes_host(eng2.make_hparams(num_epochs=10, mask_bias=1), m0, o2)
+    assert np.array_equal(o1, o2) and o1.max() > 0
     eng.close(); eng2.close()
 
 
