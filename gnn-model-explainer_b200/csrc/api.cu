@@ -527,8 +527,11 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
   return GX_OK;
 }
 
-int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
-                     float* edge_mask, float* feat_mask) {
+}  // extern "C"
+
+// mode 0: Explainer.explain's optimisation loop; mode 1: its model="grad" baseline (one forward/backward, explain.py:125-133,717-738)
+static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_memspace space, const float* m0_edges,
+                              float* edge_mask, float* feat_mask) {
   if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_nodes: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_plan) { gx_set_error("gx_explain_nodes: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
   // mask_act "ReLU": the reference's entropy term takes log(1 - relu(M)) with M ~ N(1, 2/n) -> NaN masks from step 1 (explain.py:755-770;
@@ -536,12 +539,12 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
   // moves it and the result equals the default run bit for bit (explain.py:657-660,673-676; same test): accepted, no extra state.
   if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_nodes: num_epochs < 1"); return GX_ERR_INVALID; }
-  if (hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_nodes: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
+  if (mode == 0 && hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_nodes: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
   if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   const int count = h->count;
   const int64_t te = h->total_e;
-  const int iters = hp->num_epochs - 1;
+  const int iters = mode == 1 ? 1 : hp->num_epochs - 1;
   // Adam bias-correction table in double, exactly as torch's python scalars (torch/optim/adam.py)
   std::vector<float2> tab(std::max(iters, 1));
   for (int t = 1; t <= iters; ++t) {
@@ -558,7 +561,7 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
   if (space == GX_DEVICE) {
     m0_dev = m0_edges; out_dev = edge_mask; feat_dev = feat_mask;
   } else {
-    if (hp->init == GX_INIT_M0) {
+    if (mode == 0 && hp->init == GX_INIT_M0) {
       GX_CUDA_CHECK(h->d_m0.reserve((size_t)std::max<int64_t>(te, 1) * 4));
       GX_CUDA_CHECK(cudaMemcpyAsync(h->d_m0.p, m0_edges, (size_t)te * 4, cudaMemcpyHostToDevice, h->stream));
       m0_dev = h->d_m0.as<float>();
@@ -579,6 +582,7 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
   hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = hp->coef_lap;
   hd.adam_tab = h->d_adam.as<float2>();
   hd.init = hp->init;
+  hd.mode = mode;
   hd.seed = hp->seed;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
   int stream_grid = 0;
@@ -660,6 +664,19 @@ int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, cons
     GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   }
   return GX_OK;
+}
+
+extern "C" {
+
+int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
+                     float* edge_mask, float* feat_mask) {
+  return explain_nodes_impl(h, hp, 0, space, m0_edges, edge_mask, feat_mask);
+}
+
+int gx_grad_nodes(gx_handle* h, gx_memspace space, float* edge_mask) {
+  gx_hparams hp;
+  gx_default_hparams(&hp);
+  return explain_nodes_impl(h, &hp, 1, space, nullptr, edge_mask, nullptr);
 }
 
 int gx_set_graph_batch_csr(gx_handle* h, int32_t G, int32_t max_nodes, const int32_t* rowptr, const int32_t* col,
@@ -795,7 +812,7 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
   GxHparamsDev hd;
   hd.iters = iters; hd.one_minus_b1 = 1.0f - hp->beta1; hd.b2 = hp->beta2; hd.one_minus_b2 = 1.0f - hp->beta2; hd.eps = hp->eps;
   hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = 0.f;
-  hd.adam_tab = h->d_adam.as<float2>(); hd.init = hp->init; hd.seed = hp->seed;
+  hd.adam_tab = h->d_adam.as<float2>(); hd.init = hp->init; hd.mode = 0; hd.seed = hp->seed;
   GxExplainLaunch cfg;
   cfg.order = h->d_order.as<int32_t>(); cfg.ntasks = count; cfg.counter = h->d_counters.as<int32_t>();
   cfg.smem_bytes = std::max(h->g_max_smem, 1024);

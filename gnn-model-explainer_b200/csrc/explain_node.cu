@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     if (A.dbg != nullptr && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
     const GxTask* __restrict__ Tp = A.plan.tasks + task_id;
     const int n = Tp->n, n1 = Tp->n1, n2 = Tp->n2, e1 = Tp->e1, np = Tp->npairs_in;  // inner pairs only
-    const int gt = Tp->gt_label;
+    // gradient baseline: the loss is taken at the node's PREDICTED label (explain.py:130), otherwise at label[node] (explain.py:750-753)
+    const int gt = hp.mode ? __ldg(A.g.pred_label + Tp->node) : Tp->gt_label;
     const int64_t node_off = Tp->node_off, rp_off = Tp->rp_off, edge_off = Tp->edge_off, pair_off = Tp->pair_off;
     if (tid == 0) sL = gx_make_layout(n, n1, n2, e1, np, d, HID, EMB, C, nwarps, (int)sizeof(IdxT));
     __syncthreads();
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     for (int i = tid; i <= n2; i += nthreads) irp[i] = (IdxT)A.plan.irowptr[rp_off + i];
     for (int i = tid; i < n; i += nthreads) yv[i] = (float)__ldg(A.g.pred_label + lo2gid[i]);
     for (int f = tid; f < dp; f += nthreads) {
-      sF[f] = 0.5f;  // sigmoid(0): feat_mask is initialised to 0 (explain.py:633-643)
+      sF[f] = hp.mode ? 1.0f : 0.5f;  // sigmoid(0): feat_mask is initialised to 0 (explain.py:633-643); gradient baseline: unmasked features
       Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f;
     }
     for (int idx = tid; idx < nwarps * dp; idx += nthreads) gFp[idx] = 0.f;
@@ -124,7 +125,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       ppij[p] = i < n2 ? (IdxT)pij : kNone;
       ppji[p] = j < n2 ? (IdxT)pji : kNone;
       float Mi, Mj;
-      if (hp.init == GX_INIT_M0) {
+      if (hp.mode) {
+        Mi = Mj = 0.f;
+      } else if (hp.init == GX_INIT_M0) {
         Mi = __ldg(A.m0 + edge_off + oij);
         Mj = __ldg(A.m0 + edge_off + oji);
       } else {
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       vv[p] = make_float2(0.f, 0.f);
       const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
       SS[p] = make_float2(Si, Sj);
-      const float a0 = 0.5f * (Si + Sj);  // explain.py:665-678
+      const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
       if (i < n2) a[pij] = a0;
       if (j < n2) a[pji] = a0;
       if (hp.iters == 0) {
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
         const bool last = (it == hp.iters);
         // feature mask: dL/dF = sF(1-sF) (sum_i dZ1[i] U[i] + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
-        for (int f = tid; f < d; f += nthreads) {
+        for (int f = tid; f < d && !hp.mode; f += nthreads) {
           float gsum = 0.f;
           for (int w = 0; w < nwarps; ++w) gsum += gFp[w * dp + f];
           const float s = sF[f];
@@ -475,6 +478,21 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
           sF[f] = sigmoid_f(Fv);
         }
+        if (hp.mode) {
+          // gradient baseline (explain.py:125-133): mask_ij = sigmoid(|dL/dA_ij| + |dL/dA_ji|) on the edges, no regulariser, no update
+          for (int p = tid; p < np; p += nthreads) {
+            const int i = pi[p], j = pj[p];
+            float gij = 0.f, gji = 0.f;
+            if (i < n2) gij += dot_v4(dZ1s + i * dp, X + j * dp, D4);
+            if (j < n2) gji += dot_v4(dZ1s + j * dp, X + i * dp, D4);
+            if (i < n1) gij += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
+            if (j < n1) gji += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
+            if (i == 0) gij += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
+            const float an = sigmoid_f(fabsf(gij) + fabsf(gji));
+            A.out_mask[edge_off + A.plan.pair_oij[pair_off + p]] = an;
+            A.out_mask[edge_off + A.plan.pair_oji[pair_off + p]] = an;
+          }
+        } else
         for (int p = tid; p < np; p += nthreads) {
           const int i = pi[p], j = pj[p];
           const float yd = yv[i] - yv[j];
@@ -550,6 +568,11 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
     for (int p = np_in + threadIdx.x; p < np; p += blockDim.x) {
       const int i = plan.pair_i[pair_off + p], j = plan.pair_j[pair_off + p];
       const int oij = plan.pair_oij[pair_off + p], oji = plan.pair_oji[pair_off + p];
+      if (hp.mode) {   // gradient baseline: no gradient reaches an edge outside the receptive field -> sigmoid(0)
+        out_mask[edge_off + oij] = 0.5f;
+        out_mask[edge_off + oji] = 0.5f;
+        continue;
+      }
       float Mi, Mj;
       if (hp.init == GX_INIT_M0) {
         Mi = __ldg(m0 + edge_off + oij);

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
     const int task_id = A.order[qi];
     const GxTask* __restrict__ Tp = A.plan.tasks + task_id;
     const int n = Tp->n, n1 = Tp->n1, n2 = Tp->n2, e_d = Tp->e_d, np = Tp->npairs_in;
-    const int gt = Tp->gt_label;
+    const int gt = hp.mode ? __ldg(A.g.pred_label + Tp->node) : Tp->gt_label;   // gradient baseline: predicted label (explain.py:130)
     const int64_t node_off = Tp->node_off, rp_off = Tp->rp_off, edge_off = Tp->edge_off, pair_off = Tp->pair_off;
     const GxStreamLayout L = gx_make_stream_layout(n, n1, n2, e_d, np, d, HID, nwarps);
     const int32_t* __restrict__ lo2gid = A.plan.lo2gid + node_off;
@@ -396,13 +396,15 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
     const float lap_over_nn = hp.c_lap / nn;
 
     // ------------------------------------------------------------------ per-task state
-    for (int f = tid; f < dp; f += NT) { sF[f] = 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f; }  // feat_mask = 0 (explain.py:633-643)
+    for (int f = tid; f < dp; f += NT) { sF[f] = hp.mode ? 1.0f : 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f; }  // feat_mask = 0 (explain.py:633-643)
     {
       const float m0_std = sqrtf(2.0f / (float)n);  // gain('relu') * sqrt(2/(n+n)) (explain.py:647-651)
       for (int p = tid; p < np; p += NT) {
         const int oij = poij[p], oji = poji[p];
         float Mi, Mj;
-        if (hp.init == GX_INIT_M0) {
+        if (hp.mode) {
+          Mi = Mj = 0.f;
+        } else if (hp.init == GX_INIT_M0) {
           Mi = __ldg(A.m0 + edge_off + oij);
           Mj = __ldg(A.m0 + edge_off + oji);
         } else {
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         vv[p] = make_float2(0.f, 0.f);
         const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
         SS[p] = make_float2(Si, Sj);
-        const float a0 = 0.5f * (Si + Sj);  // explain.py:665-678
+        const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
         a[ppij[p]] = a0;
         a[ppji[p]] = a0;
         {   // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2 (explain.py:780-793): constant over the epochs
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
         const bool last = (it == hp.iters);
         // feature mask: dL/dF = sF(1-sF) (sum_j X_j (.) dX'_j + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
-        for (int f = tid; f < d; f += NT) {
+        for (int f = tid; f < d && !hp.mode; f += NT) {
           float gsum = 0.f;
           for (int w = 0; w < nwarps; ++w) gsum += gFp[w * dp + f];
           const float s = sF[f];
@@ -663,6 +665,21 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         }
         // The layer-1 dots <dY1[i], P[j]> and <dY1[j], P[i]> were taken in B0 while the gathered rows were staged (gE);
         // only the few pairs touching rows < n1 (listed first) carry layer-2/3 terms.
+        if (hp.mode) {
+          // gradient baseline (explain.py:125-133): mask_ij = sigmoid(|dL/dA_ij| + |dL/dA_ji|) on the edges
+          for (int p = tid; p < np; p += NT) {
+            float gij = gE[ppji[p]], gji = gE[ppij[p]];
+            if (p < np1) {
+              const int i = pi[p], j = pj[p];
+              gij += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
+              if (j < n1) gji += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
+              if (i == 0) gij += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
+            }
+            const float an = sigmoid_f(fabsf(gij) + fabsf(gji));
+            A.out_mask[edge_off + poij[p]] = an;
+            A.out_mask[edge_off + poji[p]] = an;
+          }
+        } else
         for (int p = tid; p < np; p += NT) {
           const int sij = ppij[p], sji = ppji[p];
           float Gd = lapg[p] + gE[sji] + gE[sij];

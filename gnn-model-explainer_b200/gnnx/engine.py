@@ -203,6 +203,11 @@ class Engine:
         _abi.check(self._lib.gx_explain_nodes(self._h, C.byref(hp), _abi.GX_HOST, _np_ptr(m0_edges),
                                               _np_ptr(edge_mask_out), _np_ptr(feat_mask_out)))
 
+    def grad_nodes_host(self, edge_mask_out):
+        """Gradient baseline (explain(model="grad")) of every planned node into a host buffer."""
+        self._lib.gx_grad_nodes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _abi.check(self._lib.gx_grad_nodes(self._h, _abi.GX_HOST, _np_ptr(edge_mask_out)))
+
     def explain_nodes_ptr(self, hp, space, m0_ptr, out_ptr, feat_ptr=0):
         _abi.check(self._lib.gx_explain_nodes(self._h, C.byref(hp), int(space), C.c_void_p(int(m0_ptr) or None),
                                               C.c_void_p(int(out_ptr)), C.c_void_p(int(feat_ptr) or None)))

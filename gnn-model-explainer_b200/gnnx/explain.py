@@ -161,17 +161,22 @@ class Explainer:
         return m0
 
     def _explain_batch(self, node_indices, graph_idx=0, model="exp", unconstrained=False):
-        if model != "exp":
-            raise NotImplementedError("model=%r ('grad' baseline / att) is not built" % model)
+        if model not in ("exp", "grad"):
+            raise NotImplementedError("model=%r (att) is not built" % model)
         if unconstrained:
             raise NotImplementedError("unconstrained=True is not built")
         if graph_idx not in (0, -1):
             raise NotImplementedError("multi-graph node tasks (graph_idx != 0) are not built")
         nodes = [int(i) for i in node_indices]
         plan = self.engine.plan_nodes(nodes, self.n_hops)
+        edge_mask = np.empty(plan.total_edges, dtype=np.float32)
+        if model == "grad":        # explain.py:125-133: one backward to the adjacency, no mask parameters (the reference still
+            if self._hparams()[1] == "torch":      # constructs an ExplainModule per node, i.e. consumes n^2 normals: keep the RNG in step)
+                self._draw_m0(plan)
+            self.engine.grad_nodes_host(edge_mask)
+            return plan, edge_mask
         hp, init = self._hparams()
         m0 = self._draw_m0(plan) if init == "torch" else None
-        edge_mask = np.empty(plan.total_edges, dtype=np.float32)
         self.engine.explain_nodes_host(hp, m0, edge_mask)
         return plan, edge_mask
 
@@ -274,9 +279,7 @@ class Explainer:
         motifs with ROC-AUC and write log/pr/auc_<dataset>_<model>.txt; returns the masks.  The PR-curve PNG
         and the tensorboard drawings of the reference are not produced (viz, out of scope)."""
         from sklearn.metrics import roc_auc_score
-        if model != "exp":
-            raise NotImplementedError("model=%r is not built" % model)
-        plan, edge_mask = self._explain_batch(node_indices, graph_idx)
+        plan, edge_mask = self._explain_batch(node_indices, graph_idx, model)
         masked_adjs = [plan.dense_of(t, edge_mask, dtype=np.float64) for t in range(plan.count)]
         pred_all, real_all = [], []
         for t in range(plan.count):

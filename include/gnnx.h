@@ -133,6 +133,12 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
 int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
                      float* edge_mask, float* feat_mask);
 
+/* The gradient baseline, Explainer.explain(..., model="grad") (explain.py:125-133) with ExplainModule.adj_feat_grad
+ * (explain.py:717-738), for every planned node: one forward of the frozen model on the unmasked sub-adjacency and
+ * features, loss = -log softmax(logits[node])[predicted label of the node], one backward to the adjacency;
+ *   edge_mask [total_edges] float32 in `space`: sigmoid(|dL/dA_ij| + |dL/dA_ji|) at the sub_col slots. */
+int gx_grad_nodes(gx_handle* h, gx_memspace space, float* edge_mask);
+
 /* ---- graph-classification mode (Explainer(..., graph_mode=True), explain_graphs: explain.py:80-85,356-363) ----
  * Batch of padded graphs, replacing Explainer(adj (G,n,n), feat (G,n,d), label (G)): block CSR over
  * G*max_nodes rows (rowptr[G*max_nodes+1] with global edge offsets, col = node id inside its graph,

@@ -311,6 +311,45 @@ def gen_auc(R):
     np.savez_compressed(os.path.join(OUT, "auc_golden.npz"), **out)
 
 
+def gen_grad(R):
+    """Gradient baseline (explain(model="grad"), explain.py:125-133,717-738) of the unmodified reference on the syn1
+    and rand fixtures' graphs/weights -> tests/golden/grad_golden.npz (per node: mask entries at the nonzeros of sub_adj)."""
+    import gnnx_oracle as O
+    out = {}
+    for which, nodes in (("syn1", [300, 450, 683, 13, 0, 699]), ("rand", [0, 7, 33, 100, 149])):
+        g = np.load(os.path.join(OUT, which + "_graph.npz"))
+        N = int(g["N"]); d = g["feat"].shape[1]; C = g["Wp"].shape[0]
+        adj = np.zeros((1, N, N)); e = g["edges"]; adj[0, e[:, 0], e[:, 1]] = 1; adj[0, e[:, 1], e[:, 0]] = 1
+        model = R.models.GcnEncoderNode(d, 20, 20, C, 3, bn=False, args=train_args(input_dim=d))
+        sd = {"conv_first.weight": g["W1"], "conv_first.bias": g["b1"], "conv_block.0.weight": g["W2"], "conv_block.0.bias": g["b2"],
+              "conv_last.weight": g["W3"], "conv_last.bias": g["b3"], "pred_model.weight": g["Wp"], "pred_model.bias": g["bp"]}
+        model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+        model.eval()
+        cg = dict(adj=adj, feat=g["feat"][None].astype(np.float64), label=g["label"][None], pred=g["pred"][None], train_idx=list(range(N)))
+        args = ref_harness.explainer_args(dataset=which)
+        with ref_harness.quiet():
+            ex = R.explain.Explainer(model=model, adj=cg["adj"], feat=cg["feat"], label=cg["label"], pred=cg["pred"],
+                                     train_idx=cg["train_idx"], args=args, writer=None, print_training=False, graph_idx=-1)
+        W = {k: g[k] for k in ["W1", "b1", "W2", "b2", "W3", "b3", "Wp", "bp"]}
+        for node in nodes:
+            with ref_harness.quiet():
+                torch.manual_seed(1)
+                masked = np.asarray(ex.explain(node, graph_idx=0, model="grad"))
+                idx_new, sub_adj, sub_feat, sub_label, nbrs = ex.extract_neighborhood(node, 0)
+            ei, ej = np.nonzero(sub_adj)
+            off = masked.copy(); off[ei, ej] = 0
+            assert np.all(off == 0)
+            out["%s_n%d_mask" % (which, node)] = masked[ei, ej].astype(np.float32)
+            # the oracle restatement must agree with the reference
+            pl = int(np.argmax(g["pred"][nbrs], 1)[idx_new])
+            mine = O.grad_baseline_dense_torch(sub_adj, sub_feat, pl, idx_new, W)
+            err = O.rel_l2(mine[ei, ej], masked[ei, ej])
+            assert err < 1e-6, (which, node, err)
+        out[which + "_nodes"] = np.asarray(nodes, np.int64)
+    np.savez_compressed(os.path.join(OUT, "grad_golden.npz"), **out)
+    print("  grad baseline golden written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -318,6 +357,9 @@ def main():
     a = ap.parse_args()
     if a.only == "auc":
         gen_auc(ref_harness.load())
+        return
+    if a.only == "grad":
+        gen_grad(ref_harness.load())
         return
     if a.only == "graph":
         torch.set_num_threads(8)

@@ -252,6 +252,24 @@ def explain_dense_torch(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
 # ----------------------------------------------------------------------------------------------
 
 
+def grad_baseline_dense_torch(sub_adj, sub_feat, pred_label_node, node_idx_new, weights):
+    """The reference's gradient baseline, Explainer.explain(model="grad") (explain.py:125-133) with
+    ExplainModule.adj_feat_grad (explain.py:717-738), restated: one forward of the frozen model on the UNMASKED
+    sub-adjacency and features, loss = -log softmax(logits[node])[predicted label of the node], one backward w.r.t.
+    the dense adjacency; result sigmoid(|dA| + |dA|^T) * A."""
+    import torch
+    A = torch.tensor(np.asarray(sub_adj, np.float32)[None], dtype=torch.float, requires_grad=True)
+    x = torch.tensor(np.asarray(sub_feat, np.float32)[None], dtype=torch.float, requires_grad=True)
+    W = weights_to_torch(weights)
+    ypred = _gcn_forward_torch(x, A, W, False)
+    logit = torch.softmax(ypred[0, node_idx_new, :], dim=0)[int(pred_label_node)]
+    loss = -torch.log(logit)
+    loss.backward()
+    g = torch.abs(A.grad)[0]
+    m = torch.sigmoid(g + g.t())
+    return m.detach().numpy() * np.asarray(sub_adj, np.float32)
+
+
 def _sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 

@@ -414,3 +414,32 @@ def test_gnn_stats_auc_matches_reference(syn1, tmp_path, monkeypatch):
     pr = [ex.make_pred_real(m, int(syn1.gold["n%d_idx_new" % n])) for m, n in zip(masks, nodes)]
     auc = roc_auc_score(np.concatenate([r for _, r in pr]), np.concatenate([p for p, _ in pr]))
     assert abs(auc - float(au["syn1_auc"])) < 0.01, (auc, float(au["syn1_auc"]))
+
+
+@pytest.mark.parametrize("which", ["syn1", "rand"])
+def test_grad_baseline_matches_reference(which, tmp_path):
+    """Explainer.explain(model="grad") (explain.py:125-133,717-738): gx_grad_nodes against masks produced by the unmodified
+    reference (tests/golden/grad_golden.npz, oracle/gen_golden.py --only grad), shared-memory and streaming kernels."""
+    fx = util.load_fixture(which)
+    g = np.load(util.GOLDEN + "/grad_golden.npz")
+    nodes = [int(x) for x in g[which + "_nodes"]]
+    for stream in (False, True):
+        eng = util.make_engine(fx)
+        if stream:
+            eng.debug_force_stream(True)
+        plan = eng.plan_nodes(nodes, 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        eng.grad_nodes_host(out)
+        eng.close()
+        for t, node in enumerate(nodes):
+            ref = g["%s_n%d_mask" % (which, node)]
+            got = out[plan.edge_off[t]:plan.edge_off[t + 1]]
+            assert len(ref) == len(got)
+            assert util.rel_l2(got, ref) <= 1e-5, (which, node, stream, util.rel_l2(got, ref))
+            assert np.abs(got - ref).max() <= 1e-5
+    if which == "syn1":
+        ex, args = _explainer(fx, tmp_path, num_epochs=10)
+        masked = ex.explain(300, graph_idx=0, model="grad")
+        idx_new, sub_adj, _, _, _ = ex.extract_neighborhood(300)
+        ei, ej = np.nonzero(sub_adj)
+        assert util.rel_l2(masked[ei, ej], g["syn1_n300_mask"]) <= 1e-5

@@ -181,3 +181,16 @@ def test_reference_option_variants_mask_bias_noop_and_relu_nan():
     relu = run(mask_act="ReLU")
     ei, ej = np.nonzero(base)
     assert np.isnan(relu[ei, ej]).all()
+
+
+def test_grad_baseline_oracle_matches_reference_golden():
+    """oracle.grad_baseline_dense_torch against the masks the unmodified reference produced for model="grad"."""
+    g = np.load(util.GOLDEN + "/grad_golden.npz")
+    for which in ("syn1", "rand"):
+        fx = util.load_fixture(which)
+        for node in [int(x) for x in g[which + "_nodes"]][:3]:
+            idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(fx.rowptr, fx.col, fx.feat, fx.label, node, 3)
+            A = O.dense_from_csr(srp, scol)
+            m = O.grad_baseline_dense_torch(A, sfeat, int(fx.pred_label[nbrs][idx]), idx, fx.weights)
+            ei, ej = np.nonzero(A)
+            assert O.rel_l2(m[ei, ej], g["%s_n%d_mask" % (which, node)]) < 1e-6
