@@ -521,7 +521,8 @@ def main_c5(a):
                      "kernel": "explain_stream_kernel + outer_pairs_kernel", "algorithmic_bytes_per_step": algo,
                      "note": "algorithmic bytes = SURVEY 8(d) fused lower bound of the UNPRUNED algorithm (84*E_d + 8*n*d per node-epoch); the kernel "
                              "prunes to the receptive field and runs outermost pairs as register recurrences, so it can move fewer bytes than that"},
-        "cpu_baseline": None,
+        "cpu_baseline": {"value": None, "unit": "nodes/s", "cores": 0, "kind": "reference",
+                         "sample": "not runnable: the reference needs dense n x n float tensors (40 GB per temporary at n = 100 000, 120 GB of mask + Adam state per node)"},
         "mask_checksum": {"mean": float(mask.mean()), "min": float(mask.min()), "max": float(mask.max()), "finite": bool(np.isfinite(mask).all())},
     }), flush=True)
     eng.close()
