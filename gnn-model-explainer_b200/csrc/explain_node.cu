@@ -1,10 +1,10 @@
-// explain_node.cu -- K2: the persistent per-node mask-optimisation kernel (node mode), v2.
+// explain_node.cu -- K2: the persistent per-node mask-optimisation kernel (node mode), shared-memory resident.
 //
 // One CTA owns one explained node for ALL epochs: mask build A (.) sym(sigmoid(M)), the reference's
 // 3-layer GCN forward ((A_m H) W + b -> row L2-normalise -> ReLU), softmax / -log p[gt], the
 // size / entropy / Laplacian / feature-size regularisers, the hand-derived backward to dL/dM and
-// dL/dF, and the Adam step, with every array resident in shared memory (or, for tasks that do not
-// fit 227 KB, in a per-CTA global-memory slab that stays in L2).  Replaces, for the default
+// dL/dF, and the Adam step, with every array resident in shared memory (tasks that do not fit 227 KB run in
+// explain_stream.cu).  Replaces, for the default
 // hyper-parameters, explainer/explain.py:137-146 (epoch loop) + :665-715 (ExplainModule.forward)
 // + :740-808 (loss) + autograd + torch.optim.Adam, and models.py:58-80,230-267,363-376.
 //
@@ -34,7 +34,7 @@
 
 namespace {
 
-template <bool kShared, typename IdxT, int HID, int EMB, int NT>
+template <typename IdxT, int HID, int EMB, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ int s_task;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
   constexpr int PD = 2 * HID + EMB;  // pred_model input width (concat of the three layers)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  float* const base = kShared ? smem_dyn : (A.gws + (int64_t)blockIdx.x * A.gws_stride_words);
+  float* const base = smem_dyn;
   const GxModelDev& m = A.m;
   const GxHparamsDev& hp = A.hp;
   const int d = m.d, C = m.C;
@@ -606,24 +606,20 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
   }
 }
 
-template <bool kShared, typename IdxT, int HID, int EMB, int NT>
+template <typename IdxT, int HID, int EMB, int NT>
 cudaError_t launch_one(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  auto kern = explain_node_kernel<kShared, IdxT, HID, EMB, NT>;
-  if (kShared) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
-    if (e != cudaSuccess) return e;
-  }
-  kern<<<cfg.grid, cfg.threads, kShared ? cfg.smem_bytes : 0, s>>>(args);
+  auto kern = explain_node_kernel<IdxT, HID, EMB, NT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
   return cudaGetLastError();
 }
 
 template <int HID, int EMB>
 cudaError_t launch_dims(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  if (cfg.smem_bytes > 0) {
-    if (cfg.threads <= 256) return launch_one<true, uint16_t, HID, EMB, 256>(cfg, args, s);
-    return launch_one<true, uint16_t, HID, EMB, 512>(cfg, args, s);
-  }
-  return cudaErrorInvalidValue;  // tasks that do not fit shared memory belong to explain_stream.cu
+  if (cfg.smem_bytes <= 0) return cudaErrorInvalidValue;  // tasks that do not fit shared memory belong to explain_stream.cu
+  if (cfg.threads <= 256) return launch_one<uint16_t, HID, EMB, 256>(cfg, args, s);
+  return launch_one<uint16_t, HID, EMB, 512>(cfg, args, s);
 }
 
 }  // namespace
