@@ -42,8 +42,8 @@ NUM_EPOCHS = 100
 D_FEAT = 10
 
 
-def load_syn1():
-    g = np.load(os.path.join(ROOT, "tests", "golden", "syn1_graph.npz"))
+def load_syn1(name="syn1"):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + "_graph.npz"))
     N = int(g["N"])
     e = g["edges"].astype(np.int64)
     src = np.concatenate([e[:, 0], e[:, 1]]); dst = np.concatenate([e[:, 1], e[:, 0]])
@@ -204,7 +204,8 @@ def main_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    g = load_syn1()
+    g = load_syn1("syn4" if a.workload == "syn4" else "syn1")   # syn4 = BASELINE configs[2] (Tree-Cycle, 871 nodes, tiny subgraphs)
+    workload = WORKLOAD if a.workload != "syn4" else "syn4 Tree-Cycle, explain all %d nodes batched, 100 epochs, 3-hop subgraphs" % g["N"]
     eng = gnnx.Engine(local_rank)
     eng.set_model(g["weights"])
     eng.set_graph_csr(g["rowptr"], g["col"], g["feat"], g["label"], g["pred_label"])
@@ -297,7 +298,7 @@ def main_ours(a):
         achieved = algo_bytes_step / (kern_ms / 1e3) / 1e9
         traffic = None
         tj = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram__bytes_read+write of the explainer kernels of one step (ncu)
-        if os.path.exists(tj):
+        if os.path.exists(tj) and a.workload == "syn1":
             traffic = float(json.load(open(tj))["traffic_bytes_per_step"])
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak_hbm, "unit": "GB/s", "frac": achieved / peak_hbm,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "explain_node_kernel (one launch per size class, concurrent streams) + outer_pairs_kernel",
@@ -306,7 +307,7 @@ def main_ours(a):
                         "summed over the 700 nodes) are served from SMEM; measured DRAM traffic (ncu) is the compulsory one-time read of "
                         "the subgraphs; the kernel is latency bound (DESIGN.md 6)"}
         cpu = None
-        if world == 1 and not a.no_cpu:
+        if world == 1 and not a.no_cpu and a.workload == "syn1":
             # separate process: the CPU pool must fork before torch/CUDA exist in the parent
             import subprocess
             try:
@@ -321,7 +322,7 @@ def main_ours(a):
             "metric": METRIC, "value": value, "unit": "nodes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "nodes_per_gpu": count, "epochs": NUM_EPOCHS, "sum_E_d": int(sizes.sum()),
+            "config": {"workload": workload, "nodes_per_gpu": count, "epochs": NUM_EPOCHS, "sum_E_d": int(sizes.sum()),
                        "sum_n": int(n_t.sum()), "init": "device Philox N(1,2/n)", "l2": "flushed between steps (256 MiB write)",
                        "parallelism": "dp%d (node list replicated per rank, one all-gather of masks)" % world},
             "e2e": {"value": e2e_v, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -534,7 +535,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="syn1", choices=["syn1", "graphs", "c5"], help="syn1 = BASELINE configs[1] (default, the contract line); graphs = configs[3] stand-in; c5 = configs[4] (streaming kernel)")
+    ap.add_argument("--workload", default="syn1", choices=["syn1", "syn4", "graphs", "c5"], help="syn1 = BASELINE configs[1] (default, the contract line); syn4 = configs[2]; graphs = configs[3] stand-in; c5 = configs[4] (streaming kernel)")
     ap.add_argument("--c5-n", type=int, default=100000)
     ap.add_argument("--c5-m", type=int, default=32)
     ap.add_argument("--c5-nodes", type=int, default=148, help="explained nodes per step of the c5 workload")
