@@ -297,14 +297,24 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float yh3 = lane < EMB ? y3 / q3 : 0.f;
         const float e1v = lane < HID ? fmaxf(Yh1[lane], 0.f) : 0.f;  // row 0 of H1
         const float e2v = lane < HID ? fmaxf(Yh2[lane], 0.f) : 0.f;  // row 0 of H2
-        // logits = pred_model(concat) (models.py:260,375), softmax over classes (explain.py:714)
-        for (int c = 0; c < C; ++c) {
-          const float* wp = Wpp + c * PD;
+        // logits = pred_model(concat) (models.py:260,375), softmax over classes (explain.py:714): the concatenated embedding of the
+        // node goes through the scratch row, then four classes at a time, eight lanes per class (one dependent reduction per four
+        // classes instead of one per class)
+        __syncwarp();
+        if (lane < HID) { zs[lane] = e1v; zs[HID + lane] = e2v; }
+        if (lane < EMB) zs[2 * HID + lane] = yh3;
+        __syncwarp();
+        for (int cb = 0; cb < C; cb += 4) {
+          const int c = cb + (lane >> 3);
           float t = 0.f;
-          if (lane < HID) t = fmaf(e1v, wp[lane], fmaf(e2v, wp[HID + lane], t));
-          if (lane < EMB) t = fmaf(yh3, wp[2 * HID + lane], t);
-          t = warp_sum(t);
-          if (lane == 0) logit[c] = t + bpp[c];
+          if (c < C) {
+            const float* wp = Wpp + c * PD;
+            for (int k = lane & 7; k < PD; k += 8) t = fmaf(zs[k], wp[k], t);
+          }
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 4);
+          if (c < C && (lane & 7) == 0) logit[c] = t + bpp[c];
         }
         __syncwarp();
         float mx = -INFINITY;
@@ -466,7 +476,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
         const bool last = (it == hp.iters);
         // feature mask: dL/dF = sF(1-sF) (sum_i dZ1[i] U[i] + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
-        for (int f = tid; f < d && !hp.mode; f += nthreads) {
+        // (done by the LAST warps of the CTA: the first ones carry the most pair work below, and a warp whose first lanes run this
+        //  serial update would hold back its 32 pairs)
+        const int fthreads = min(nthreads, gx_round_up(d, 32));
+        for (int f = tid - (nthreads - fthreads); f >= 0 && f < d && !hp.mode; f += fthreads) {
           float gsum = 0.f;
           for (int w = 0; w < nwarps; ++w) gsum += gFp[w * dp + f];
           const float s = sF[f];
@@ -494,6 +507,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           }
         } else
         for (int p = tid; p < np; p += nthreads) {
+          // optimiser state of the pair (L2-resident slab): issued first so that the L2 round trip overlaps the dots below
+          float2 Mv = MM[p];
+          const float2 Sv = SS[p];
+          float2 m2 = mm[p], v2 = vv[p];
           const int i = pi[p], j = pj[p];
           const float yd = yv[i] - yv[j];
           float Gd = lap_over_nn * yd * yd;  // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2 (explain.py:780-793)
@@ -503,12 +520,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           if (j < n1) Gd += dot_relu_v4(dZ2 + j * HS, Yh1 + i * HS, H4);
           if (i == 0) Gd += dot_relu_v4(dZ3, Yh2 + j * HS, H4);
           Gd *= 0.5f;  // sym_mask = (S + S^T)/2 (explain.py:671)
-          float2 Mv = MM[p];
-          const float2 Sv = SS[p];
           // size: coeff*sum(S) ; entropy: mean over n^2 of H(S), dH/dM = -M S(1-S) (explain.py:755-770)
           const float gi = Sv.x * (1.f - Sv.x) * (Gd + hp.c_size - ent_over_nn * Mv.x);
           const float gj = Sv.y * (1.f - Sv.y) * (Gd + hp.c_size - ent_over_nn * Mv.y);
-          float2 m2 = mm[p], v2 = vv[p];
           m2.x = m2.x + (gi - m2.x) * hp.one_minus_b1;
           m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
           v2.x = v2.x * hp.b2 + hp.one_minus_b2 * gi * gi;
