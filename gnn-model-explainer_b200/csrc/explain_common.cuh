@@ -5,6 +5,9 @@
 
 namespace {
 
+#ifndef GX_SHORT_DEPTH
+#define GX_SHORT_DEPTH 1   // edges in flight per lane group on short rows in the small launch classes (2 measured slower: 3.93 -> 4.33 ms, more registers/instructions)
+#endif
 constexpr int kLongRow = 32;  // rows with more edges than this are aggregated by a whole warp
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -127,12 +130,12 @@ __device__ __forceinline__ float4 group_dense(const float* zrow, int F4, const f
 // this lane's float4 slice of  sum_{e = r0, r0+estep, .. < r1} a[e] * f(src[col[e]]).  Four edges are kept in
 // flight: the loop is a chain of two dependent shared-memory loads per edge, so without this a lane
 // group waits ~2 LDS latencies per edge (hub rows: thousands of cycles).
-template <typename IdxT, bool kRelu, bool kUnroll>
+template <typename IdxT, bool kRelu, int kDepth>
 __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const IdxT* icol, const float* a,
                                              const float* src, int src_stride, int q) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int e = r0;
-  if (kUnroll)
+  if (kDepth >= 4)
   for (; e + 3 * estep < r1; e += 4 * estep) {
     const int c0 = icol[e], c1 = icol[e + estep], c2 = icol[e + 2 * estep], c3 = icol[e + 3 * estep];
     const float a0 = a[e], a1 = a[e + estep], a2 = a[e + 2 * estep], a3 = a[e + 3 * estep];
@@ -140,6 +143,14 @@ __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const Id
     float4 v2 = ld4(src + c2 * src_stride + 4 * q), v3 = ld4(src + c3 * src_stride + 4 * q);
     if (kRelu) { v0 = relu4(v0); v1 = relu4(v1); v2 = relu4(v2); v3 = relu4(v3); }
     fma4(acc, a0, v0); fma4(acc, a1, v1); fma4(acc, a2, v2); fma4(acc, a3, v3);
+  }
+  if (kDepth >= 2)
+  for (; e + estep < r1; e += 2 * estep) {
+    const int c0 = icol[e], c1 = icol[e + estep];
+    const float a0 = a[e], a1 = a[e + estep];
+    float4 v0 = ld4(src + c0 * src_stride + 4 * q), v1 = ld4(src + c1 * src_stride + 4 * q);
+    if (kRelu) { v0 = relu4(v0); v1 = relu4(v1); }
+    fma4(acc, a0, v0); fma4(acc, a1, v1);
   }
   for (; e < r1; e += estep) {
     float4 v = ld4(src + (int)icol[e] * src_stride + 4 * q);
@@ -152,7 +163,7 @@ __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const Id
 // A "row task" of a phase: either one long row taken by the whole warp (edges split across the groups,
 // partial sums reduced into group 0 through the scratch) or a chunk of epi short rows, one per group.
 // Returns the row id (or -1) and this lane's float4 of the aggregate; W4 = source width in float4.
-template <typename IdxT, bool kRelu, bool kUnrollShort>
+template <typename IdxT, bool kRelu, int kShortDepth>
 __device__ __forceinline__ int row_task_gather(int t, int nlong, const IdxT* llist, int R, const Grp& G, int W4,
                                                const IdxT* irp, const IdxT* icol, const float* a,
                                                const float* src, int src_stride, const IdxT* cnt, float* zs,
@@ -163,7 +174,7 @@ __device__ __forceinline__ int row_task_gather(int t, int nlong, const IdxT* lli
     const int r0 = irp[i], r1 = cnt != nullptr ? r0 + (int)cnt[i] : (int)irp[i + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (G.grp < G.epi && G.q < W4)
-      acc = gather_row<IdxT, kRelu, true>(r0 + G.grp, r1, G.epi, icol, a, src, src_stride, G.q);
+      acc = gather_row<IdxT, kRelu, 4>(r0 + G.grp, r1, G.epi, icol, a, src, src_stride, G.q);
     st4(zs + G.lane * 4, acc);
     __syncwarp();
     if (G.grp == 0 && G.q < W4) {
@@ -180,7 +191,7 @@ __device__ __forceinline__ int row_task_gather(int t, int nlong, const IdxT* lli
   if (G.grp >= G.epi || i >= R) return -1;
   const int r0 = irp[i], r1 = cnt != nullptr ? r0 + (int)cnt[i] : (int)irp[i + 1];
   if (nlong > 0 && r1 - r0 > kLongRow) return -1;  // taken by a whole warp above
-  if (G.q < W4) z = gather_row<IdxT, kRelu, kUnrollShort>(r0, r1, 1, icol, a, src, src_stride, G.q);
+  if (G.q < W4) z = gather_row<IdxT, kRelu, kShortDepth>(r0, r1, 1, icol, a, src, src_stride, G.q);
   return i;
 }
 

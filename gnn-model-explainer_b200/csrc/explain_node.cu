@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const int ntask = nlongF1 + (n2 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
           float4 z;
-          const int i = row_task_gather<IdxT, false, (NT >= 512)>(t, nlongF1, llist, n2, G, D4, irp, icol, a, X, dp, (const IdxT*)nullptr, zs, z);
+          const int i = row_task_gather<IdxT, false, (NT >= 512 ? 4 : GX_SHORT_DEPTH)>(t, nlongF1, llist, n2, G, D4, irp, icol, a, X, dp, (const IdxT*)nullptr, zs, z);
           const bool act = i >= 0;
           if (act && q < D4) {
             st4(U + i * dp + 4 * q, z);
@@ -233,8 +233,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           if (act && q < H4) y = group_dense(zs + G.gbase * 4, D4, W1s, HS, q, ld4(bs + 4 * q));
           const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
           const float qn = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(p=2, dim=2), eps 1e-12
-          if (act && q < H4) st4(Yh1 + i * HS + 4 * q, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
-          if (act && q == 0) q1[i] = qn;
+          const float rq = 1.0f / qn;   // one division per row; the row is scaled by (and the backward reuses) the reciprocal
+          if (act && q < H4) st4(Yh1 + i * HS + 4 * q, make_float4(y.x * rq, y.y * rq, y.z * rq, y.w * rq));
+          if (act && q == 0) q1[i] = rq;
           __syncwarp();
         }
       }
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const int ntask = nlongF2 + (n1 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
           float4 z;
-          const int i = row_task_gather<IdxT, true, (NT >= 512)>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, (const IdxT*)nullptr, zs, z);
+          const int i = row_task_gather<IdxT, true, (NT >= 512 ? 4 : GX_SHORT_DEPTH)>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, (const IdxT*)nullptr, zs, z);
           const bool act = i >= 0;
           if (act && q < H4) st4(zs + lane * 4, z);
           __syncwarp();
@@ -259,8 +260,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           if (act && q < H4) y = group_dense(zs + G.gbase * 4, H4, W2s, HS, q, ld4(bs + HID + 4 * q));
           const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
           const float qn = fmaxf(sqrtf(ss), 1e-12f);
-          if (act && q < H4) st4(Yh2 + i * HS + 4 * q, make_float4(y.x / qn, y.y / qn, y.z / qn, y.w / qn));
-          if (act && q == 0) q2[i] = qn;
+          const float rq = 1.0f / qn;
+          if (act && q < H4) st4(Yh2 + i * HS + 4 * q, make_float4(y.x * rq, y.y * rq, y.z * rq, y.w * rq));
+          if (act && q == 0) q2[i] = rq;
           __syncwarp();
         }
       }
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         {  // aggregate of row 0 with its edges split across the lane groups
           const int r0 = irp[0], r1 = irp[1];
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (G.grp < epi && q < H4) acc = gather_row<IdxT, true, true>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q);
+          if (G.grp < epi && q < H4) acc = gather_row<IdxT, true, 4>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q);
           st4(zs + lane * 4, acc);
         }
         __syncwarp();
@@ -294,7 +296,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           for (int f = 0; f < HID; ++f) y3 = fmaf(zs[f], W3s[f * EMB + lane], y3);
         const float ss = warp_sum(lane < EMB ? y3 * y3 : 0.f);
         const float q3 = fmaxf(sqrtf(ss), 1e-12f);
-        const float yh3 = lane < EMB ? y3 / q3 : 0.f;
+        const float rq3 = 1.0f / q3;
+        const float yh3 = lane < EMB ? y3 * rq3 : 0.f;
         const float e1v = lane < HID ? fmaxf(Yh1[lane], 0.f) : 0.f;  // row 0 of H1
         const float e2v = lane < HID ? fmaxf(Yh2[lane], 0.f) : 0.f;  // row 0 of H2
         // logits = pred_model(concat) (models.py:260,375), softmax over classes (explain.py:714): the concatenated embedding of the
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         if (lane < HID) { dE[lane] = d1; dE[HS + lane] = d2; }
         // backward of y/max(|y|,eps): dY = (dYh - Yh <Yh,dYh>)/q ; dZ3 = dY3 W3^T
         const float s3 = warp_sum(yh3 * d3);
-        const float dy3 = lane < EMB ? (d3 - yh3 * s3) / q3 : 0.f;
+        const float dy3 = lane < EMB ? (d3 - yh3 * s3) * rq3 : 0.f;
         __syncwarp();
         if (lane < EMB) zs[lane] = dy3;
         __syncwarp();
@@ -378,9 +381,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           }
           const float sdot = group_sum(yh.x * dy.x + yh.y * dy.y + yh.z * dy.z + yh.w * dy.w, G);
           if (act && q < H4) {
-            const float qn = q2[j];
-            st4(zs + lane * 4, make_float4((dy.x - yh.x * sdot) / qn, (dy.y - yh.y * sdot) / qn,
-                                           (dy.z - yh.z * sdot) / qn, (dy.w - yh.w * sdot) / qn));
+            const float rq = q2[j];   // 1 / max(|Y2[j]|, eps)
+            st4(zs + lane * 4, make_float4((dy.x - yh.x * sdot) * rq, (dy.y - yh.y * sdot) * rq,
+                                           (dy.z - yh.z * sdot) * rq, (dy.w - yh.w * sdot) * rq));
           }
           __syncwarp();
           if (act && q < H4)
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const int ntask = nlongB1 + (n2 + epi - 1) / epi;
         for (int t = warp; t < ntask; t += nwarps) {
           float4 dh;
-          const int i = row_task_gather<IdxT, false, false>(t, nlongB1, llistB, n2, G, H4, irp, icol, a, dZ2, HS, cnt1, zs, dh);
+          const int i = row_task_gather<IdxT, false, (NT >= 512 ? 1 : GX_SHORT_DEPTH)>(t, nlongB1, llistB, n2, G, H4, irp, icol, a, dZ2, HS, cnt1, zs, dh);
           const bool act = i >= 0;
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
           if (act && q < H4) {
@@ -417,9 +420,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           }
           const float sdot = group_sum(yh.x * dy.x + yh.y * dy.y + yh.z * dy.z + yh.w * dy.w, G);
           if (act && q < H4) {
-            const float qn = q1[i];
-            st4(zs + lane * 4, make_float4((dy.x - yh.x * sdot) / qn, (dy.y - yh.y * sdot) / qn,
-                                           (dy.z - yh.z * sdot) / qn, (dy.w - yh.w * sdot) / qn));
+            const float rq = q1[i];   // 1 / max(|Y1[i]|, eps)
+            st4(zs + lane * 4, make_float4((dy.x - yh.x * sdot) * rq, (dy.y - yh.y * sdot) * rq,
+                                           (dy.z - yh.z * sdot) * rq, (dy.w - yh.w * sdot) * rq));
           }
           __syncwarp();
           if (act && q < D4) {

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         {
           const int r0 = irp[0], r1 = irp[1];
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < H4) acc = gather_row<int32_t, true, true>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q);
+          if (q < H4) acc = gather_row<int32_t, true, 4>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q);
           st4(zw + lane * 4, acc);
         }
         __syncwarp();
