@@ -136,6 +136,7 @@ __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const Id
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int e = r0;
   if (kDepth >= 4)
+#pragma unroll 1
   for (; e + 3 * estep < r1; e += 4 * estep) {
     const int c0 = icol[e], c1 = icol[e + estep], c2 = icol[e + 2 * estep], c3 = icol[e + 3 * estep];
     const float a0 = a[e], a1 = a[e + estep], a2 = a[e + 2 * estep], a3 = a[e + 3 * estep];
@@ -145,6 +146,7 @@ __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const Id
     fma4(acc, a0, v0); fma4(acc, a1, v1); fma4(acc, a2, v2); fma4(acc, a3, v3);
   }
   if (kDepth >= 2)
+#pragma unroll 1
   for (; e + estep < r1; e += 2 * estep) {
     const int c0 = icol[e], c1 = icol[e + estep];
     const float a0 = a[e], a1 = a[e + estep];
@@ -152,6 +154,7 @@ __device__ __forceinline__ float4 gather_row(int r0, int r1, int estep, const Id
     if (kRelu) { v0 = relu4(v0); v1 = relu4(v1); }
     fma4(acc, a0, v0); fma4(acc, a1, v1);
   }
+#pragma unroll 1
   for (; e < r1; e += estep) {
     float4 v = ld4(src + (int)icol[e] * src_stride + 4 * q);
     if (kRelu) v = relu4(v);

@@ -34,6 +34,104 @@
 
 namespace {
 
+// Phase S: everything that concerns only the explained node's own row (level-order id 0): layer 3, the concat readout,
+// softmax / -log p[gt] and the layer-3 backward (models.py:256-260,375; explain.py:714,750-753).  One warp, ~1/3 of a tiny
+// task's epoch (profiles/r01f): written for a SHORT serial chain -- compile-time trip counts, clamped lane indices instead
+// of divergent `if (lane < ..)` blocks, one exp per class, the four 8-lane groups of the warp reduced with shuffles.
+// kWpShared only separates the two instantiations so that the pred_model pointer keeps its address space (LDS vs LDG).
+template <typename IdxT, int HID, int EMB, bool kWpShared>
+__device__ __forceinline__ void readout_phase(int lane, int C, int gt, const IdxT* irp, const IdxT* icol, const float* a,
+                                              const float* Yh1, const float* Yh2, float* zs, const float* bs, const float* W3s,
+                                              const float* Wpp, const float* bpp, float* logit, float* dE, float* dZ3) {
+  constexpr int HS = HID, H4 = HID / 4, PD = 2 * HID + EMB;
+  const int g = lane >> 3, q8 = lane & 7;
+  // layer-3 aggregate of row 0: the four 8-lane groups walk its edges four apart, then sum across the groups
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int r0 = irp[0], r1 = irp[1];
+    if (q8 < H4) acc = gather_row<IdxT, true, 4>(r0 + g, r1, 4, icol, a, Yh2, HS, q8);
+  }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane < H4) st4(zs + 4 * lane, acc);
+  __syncwarp();
+  // Y3 = Z3 W3 + b3 (lane = output feature), row normalise
+  const int le = lane < EMB ? lane : EMB - 1;
+  const int lh = lane < HID ? lane : HID - 1;
+  float y3 = bs[2 * HID + le];
+#pragma unroll
+  for (int f4 = 0; f4 < H4; ++f4) {
+    const float4 z4 = ld4(zs + 4 * f4);
+    const float* w = W3s + (4 * f4) * EMB + le;
+    y3 = fmaf(z4.x, w[0], y3); y3 = fmaf(z4.y, w[EMB], y3); y3 = fmaf(z4.z, w[2 * EMB], y3); y3 = fmaf(z4.w, w[3 * EMB], y3);
+  }
+  if (lane >= EMB) y3 = 0.f;
+  const float ss = warp_sum(y3 * y3);
+  const float rq3 = 1.0f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(p=2, dim=2), eps 1e-12
+  const float yh3 = y3 * rq3;
+  const float e1v = fmaxf(Yh1[lh], 0.f);  // row 0 of H1
+  const float e2v = fmaxf(Yh2[lh], 0.f);  // row 0 of H2
+  __syncwarp();
+  if (lane < HID) { zs[lane] = e1v; zs[HID + lane] = e2v; }
+  if (lane < EMB) zs[2 * HID + lane] = yh3;
+  __syncwarp();
+  // logits = pred_model(concat): four classes at a time, eight lanes per class
+  for (int cb = 0; cb < C; cb += 4) {
+    const int c = cb + g;
+    const float* wp = Wpp + (c < C ? c : C - 1) * PD;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < (PD + 7) / 8; ++k) {
+      const int kk = q8 + 8 * k;
+      if (kk < PD) t = fmaf(zs[kk], wp[kk], t);
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    if (c < C && q8 == 0) logit[c] = t + bpp[c];
+  }
+  __syncwarp();
+  // softmax over the classes, dL/dlogits = p - onehot(gt) (explain.py:750-753)
+  if (C <= 32) {
+    const float v = lane < C ? logit[lane] : -INFINITY;
+    const float mx = warp_max(v);
+    const float ex = lane < C ? expf(v - mx) : 0.f;
+    const float se = warp_sum(ex);
+    if (lane < C) logit[lane] = ex / se - (lane == gt ? 1.f : 0.f);
+  } else {
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, logit[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+#pragma unroll 1
+    for (int c = lane; c < C; c += 32) se += expf(logit[c] - mx);
+    se = warp_sum(se);
+    __syncwarp();
+#pragma unroll 1
+    for (int c = lane; c < C; c += 32) logit[c] = expf(logit[c] - mx) / se - (c == gt ? 1.f : 0.f);
+  }
+  __syncwarp();
+  // dEmb = Wp^T g ; backward of y/max(|y|,eps): dY = (dYh - Yh <Yh,dYh>)/q ; dZ3 = dY3 W3^T
+  float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float gc = logit[c];
+    const float* wp = Wpp + c * PD;
+    d1 = fmaf(gc, wp[lh], d1); d2 = fmaf(gc, wp[HID + lh], d2); d3 = fmaf(gc, wp[2 * HID + le], d3);
+  }
+  if (lane < HID) { dE[lane] = d1; dE[HS + lane] = d2; }
+  if (lane >= EMB) d3 = 0.f;
+  const float s3 = warp_sum(yh3 * d3);
+  const float dy3 = (d3 - yh3 * s3) * rq3;
+  __syncwarp();
+  if (lane < EMB) zs[lane] = dy3;
+  __syncwarp();
+  if (lane < HID) dZ3[lane] = dot_v4(zs, W3s + lane * EMB, EMB / 4);
+}
+
 template <typename IdxT, int HID, int EMB, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float smem_dyn[];
@@ -275,76 +373,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const a = base + sL.a; const float* const Yh1 = base + sL.Yh1; const float* const Yh2 = base + sL.Yh2;
         float* const zs = base + sL.zs; const float* const bs = base + sL.bs; const float* const W3s = base + sL.W3s;
         float* const logit = base + sL.logit; float* const dE = base + sL.dE; float* const dZ3 = base + sL.dZ3;
-        const bool wp_smem = C * (PD + 1) <= GX_WP_SMEM_MAX;
-        const float* const Wpp = wp_smem ? base + sL.Wp : m.Wp;        // pred_model.weight (C, 2h+e)
-        const float* const bpp = wp_smem ? base + sL.Wp + C * PD : m.bp;  // pred_model.bias
-        {  // aggregate of row 0 with its edges split across the lane groups
-          const int r0 = irp[0], r1 = irp[1];
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (G.grp < epi && q < H4) acc = gather_row<IdxT, true, 4>(r0 + G.grp, r1, epi, icol, a, Yh2, HS, q);
-          st4(zs + lane * 4, acc);
-        }
-        __syncwarp();
-        float z = 0.f;
-        if (lane < HID)
-          for (int g2 = 0; g2 < epi; ++g2) z += zs[(g2 * G.GW + (lane >> 2)) * 4 + (lane & 3)];
-        __syncwarp();
-        if (lane < HID) zs[lane] = z;
-        __syncwarp();
-        float y3 = lane < EMB ? bs[2 * HID + lane] : 0.f;
-        if (lane < EMB)
-          for (int f = 0; f < HID; ++f) y3 = fmaf(zs[f], W3s[f * EMB + lane], y3);
-        const float ss = warp_sum(lane < EMB ? y3 * y3 : 0.f);
-        const float q3 = fmaxf(sqrtf(ss), 1e-12f);
-        const float rq3 = 1.0f / q3;
-        const float yh3 = lane < EMB ? y3 * rq3 : 0.f;
-        const float e1v = lane < HID ? fmaxf(Yh1[lane], 0.f) : 0.f;  // row 0 of H1
-        const float e2v = lane < HID ? fmaxf(Yh2[lane], 0.f) : 0.f;  // row 0 of H2
-        // logits = pred_model(concat) (models.py:260,375), softmax over classes (explain.py:714): the concatenated embedding of the
-        // node goes through the scratch row, then four classes at a time, eight lanes per class (one dependent reduction per four
-        // classes instead of one per class)
-        __syncwarp();
-        if (lane < HID) { zs[lane] = e1v; zs[HID + lane] = e2v; }
-        if (lane < EMB) zs[2 * HID + lane] = yh3;
-        __syncwarp();
-        for (int cb = 0; cb < C; cb += 4) {
-          const int c = cb + (lane >> 3);
-          float t = 0.f;
-          if (c < C) {
-            const float* wp = Wpp + c * PD;
-            for (int k = lane & 7; k < PD; k += 8) t = fmaf(zs[k], wp[k], t);
-          }
-          t += __shfl_xor_sync(0xffffffffu, t, 1);
-          t += __shfl_xor_sync(0xffffffffu, t, 2);
-          t += __shfl_xor_sync(0xffffffffu, t, 4);
-          if (c < C && (lane & 7) == 0) logit[c] = t + bpp[c];
-        }
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, logit[c]);
-        mx = warp_max(mx);
-        float se = 0.f;
-        for (int c = lane; c < C; c += 32) se += expf(logit[c] - mx);
-        se = warp_sum(se);
-        __syncwarp();
-        for (int c = lane; c < C; c += 32)
-          logit[c] = expf(logit[c] - mx) / se - (c == gt ? 1.f : 0.f);  // dL/dlogits = p - onehot(gt) (explain.py:750-753)
-        __syncwarp();
-        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
-        for (int c = 0; c < C; ++c) {
-          const float gc = logit[c];
-          const float* wp = Wpp + c * PD;
-          if (lane < HID) { d1 = fmaf(gc, wp[lane], d1); d2 = fmaf(gc, wp[HID + lane], d2); }
-          if (lane < EMB) d3 = fmaf(gc, wp[2 * HID + lane], d3);
-        }
-        if (lane < HID) { dE[lane] = d1; dE[HS + lane] = d2; }
-        // backward of y/max(|y|,eps): dY = (dYh - Yh <Yh,dYh>)/q ; dZ3 = dY3 W3^T
-        const float s3 = warp_sum(yh3 * d3);
-        const float dy3 = lane < EMB ? (d3 - yh3 * s3) * rq3 : 0.f;
-        __syncwarp();
-        if (lane < EMB) zs[lane] = dy3;
-        __syncwarp();
-        if (lane < HID) dZ3[lane] = dot_v4(zs, W3s + lane * EMB, EMB / 4);
+        if (C * (PD + 1) <= GX_WP_SMEM_MAX)   // pred_model.weight (C, 2h+e) + bias staged in shared memory
+          readout_phase<IdxT, HID, EMB, true>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, base + sL.Wp, base + sL.Wp + C * PD, logit, dE, dZ3);
+        else
+          readout_phase<IdxT, HID, EMB, false>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, m.Wp, m.bp, logit, dE, dZ3);
       }
       __syncthreads();
       GX_MARK(tS)
