@@ -47,7 +47,7 @@ struct DevBuf {
 };
 
 struct LaunchClass {
-  int cap_bytes;  // dynamic shared memory per CTA (0: global-memory slab variant)
+  int cap_bytes;  // dynamic shared memory per CTA (0: the streaming class, explain_stream.cu)
   int threads;
   int ctas_per_sm;
 };
@@ -87,7 +87,6 @@ struct gx_handle {
   int64_t total_n = 0, total_e = 0;
   std::vector<GxTask> tasks;
   std::vector<int32_t> class_order[kNumClasses];
-  std::vector<int> class_idx16;
   int64_t gws_stride_words = 0;
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
@@ -140,7 +139,7 @@ int ensure_slot_ws(gx_handle* h) {
   return GX_OK;
 }
 
-int task_smem_class(const GxTask& T, const GxModelDev& m, bool force_stream, int* bytes_out, int* idx16_out) {
+int task_smem_class(const GxTask& T, const GxModelDev& m, bool force_stream, int* bytes_out) {
   // shared-memory classes always use 16-bit indices: a task with n or e1 >= 65535 cannot fit 227 KB anyway
   const bool small_idx = !force_stream && T.n < 65535 && T.e1 < 65535;
   for (int c = 0; small_idx && c < kNumClasses - 1; ++c) {
@@ -149,12 +148,10 @@ int task_smem_class(const GxTask& T, const GxModelDev& m, bool force_stream, int
     const int64_t bytes = (int64_t)L.total_words * 4;
     if (bytes <= kClasses[c].cap_bytes) {
       *bytes_out = (int)bytes;
-      *idx16_out = 1;
       return c;
     }
   }
   *bytes_out = 0;  // streaming class (explain_stream.cu): state in a global slab, sized by gx_make_stream_layout
-  *idx16_out = 0;
   return kNumClasses - 1;
 }
 
@@ -427,8 +424,6 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   // host: offsets, launch classes, work order
   int64_t tn = 0, te = 0, tp = 0;
   for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
-  h->class_idx16.assign(kNumClasses, 1);
-  h->class_idx16[kNumClasses - 1] = 0;
   int64_t gws_words = 0;
   for (int t = 0; t < count; ++t) {
     GxTask& T = h->tasks[t];
@@ -439,8 +434,8 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     if (T.e_d % 2 != 0) { gx_set_error("gx_plan_nodes: induced sub-adjacency of node %d is not symmetric", T.node); return GX_ERR_INVALID; }
     T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
     tn += T.n; te += T.e_d; tp += T.npairs;
-    int bytes = 0, idx16 = 0;
-    const int cls = task_smem_class(T, h->m, h->force_stream, &bytes, &idx16);
+    int bytes = 0;
+    const int cls = task_smem_class(T, h->m, h->force_stream, &bytes);
     T.smem_bytes = bytes;
     if (cls == kNumClasses - 1)
       gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, T.npairs_in, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
@@ -632,7 +627,6 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     cfg.counter = h->d_counters.as<int32_t>() + c;
     cfg.smem_bytes = kClasses[c].cap_bytes;
     cfg.threads = kClasses[c].threads;
-    cfg.idx16 = h->class_idx16[c];
     cfg.gws = h->d_gws.as<float>();
     cfg.gws_stride_words = h->gws_stride_words;
     cfg.dbg = h->dbg;
@@ -819,7 +813,7 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
   cfg.threads = 128;
   const int per_sm = std::max(1, std::min(16, (227 * 1024) / (cfg.smem_bytes + 1024)));
   cfg.grid = std::min(count, h->num_sms * per_sm);
-  cfg.idx16 = 1; cfg.gws = nullptr; cfg.gws_stride_words = 0; cfg.dbg = nullptr;
+  cfg.gws = nullptr; cfg.gws_stride_words = 0; cfg.dbg = nullptr;
   cfg.pws_stride_words = ((int64_t)h->g_max_np * 8 + 3) / 4 * 4;
   GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(cfg.pws_stride_words * cfg.grid, 4) * 4));
   cfg.pws = h->d_pws.as<float>();

@@ -249,11 +249,10 @@ struct GxExplainLaunch {
   const int32_t* order;  // [ntasks] task ids of this launch class, most expensive first
   int32_t ntasks;
   int32_t* counter;      // device work-queue counter (zeroed)
-  int32_t smem_bytes;    // dynamic shared memory per CTA (0 => global-memory resident variant)
+  int32_t smem_bytes;    // dynamic shared memory per CTA (shared-memory classes)
   int32_t threads;
   int32_t grid;
-  int32_t idx16;         // 1: 16-bit indices
-  float* gws;            // global workspace for the non-resident variant
+  float* gws;            // per-CTA global slab of the streaming class
   int64_t gws_stride_words;
   float* pws;            // per-CTA pair-state slab: 8 floats per inner pair (M,m,v,S of both directions)
   int64_t pws_stride_words;
