@@ -146,3 +146,21 @@ def test_tu_reader_matches_reference(tmp_path):
         assert np.array_equal(A, out["adj"][g]) and int(Gx.graph["label"]) == int(out["label"][g])
         for i, u in enumerate(Gx.nodes()):
             assert np.array_equal(np.asarray(Gx.nodes[u]["label"], dtype=np.float32), out["feat"][g, i])
+
+
+def test_bench_ba_generator_is_a_simple_symmetric_graph():
+    """bench.py --workload c5 builds its Barabasi-Albert graph with a numpy generator: the CSR must be what
+    gx_set_graph_csr accepts (symmetric, sorted rows, no self loops, no duplicates) with the BA degree structure."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(util.GOLDEN), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    N, m = 3000, 8
+    rowptr, col = bench.make_ba_csr(N, m, 0)
+    assert rowptr[0] == 0 and rowptr[-1] == len(col) == 2 * m * (N - m)
+    deg = np.diff(rowptr)
+    assert deg[m:].min() >= m and deg.max() > 10 * m                      # late nodes keep their m links, early nodes are hubs
+    rows = np.repeat(np.arange(N), deg)
+    assert not np.any(rows == col)                                         # no self loops
+    key = rows.astype(np.int64) * N + col
+    assert np.all(np.diff(key) > 0)                                        # rows sorted, no duplicate edges
+    assert np.array_equal(np.sort(key), np.sort(col.astype(np.int64) * N + rows))   # symmetric
