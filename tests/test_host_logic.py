@@ -152,7 +152,7 @@ def test_bench_ba_generator_is_a_simple_symmetric_graph():
     """bench.py --workload c5 builds its Barabasi-Albert graph with a numpy generator: the CSR must be what
     gx_set_graph_csr accepts (symmetric, sorted rows, no self loops, no duplicates) with the BA degree structure."""
     import importlib.util, os
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(util.GOLDEN), "..", "bench.py"))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "bench.py"))
     bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
     N, m = 3000, 8
     rowptr, col = bench.make_ba_csr(N, m, 0)
