@@ -350,6 +350,48 @@ def gen_grad(R):
     print("  grad baseline golden written")
 
 
+def gen_variants(R, epochs=30):
+    """Model variants the kernels do not build yet (--bn, num_gc_layers != 3), pinned for the oracle now:
+    the unmodified reference on the rand graph with random weights, 2 / 4 layers and 3 layers + --bn ->
+    tests/golden/variants_golden.npz (weights, per node M0 at the edges and the returned mask at the edges)."""
+    import networkx as nx
+    rng = np.random.default_rng(21)
+    G = nx.barabasi_albert_graph(60, 2, seed=4)
+    N, d, C = G.number_of_nodes(), 12, 3
+    adj = nx.to_numpy_array(G)[None]
+    feat = rng.normal(size=(1, N, d))
+    label = rng.integers(0, C, size=(1, N))
+    out = dict(N=np.int64(N), edges=edges_of(adj[0]), feat=feat[0].astype(np.float32), label=label[0].astype(np.int64), num_epochs=np.int64(epochs))
+    for tag, L, bn in (("L2", 2, False), ("L4", 4, False), ("bn", 3, True)):
+        torch.manual_seed(100 + L + int(bn))
+        targs = train_args(input_dim=d, num_gc_layers=L, bn=bn)
+        model = R.models.GcnEncoderNode(d, 20, 20, C, L, bn=bn, args=targs)
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if name.endswith("bias"):
+                    p.normal_(0.0, 0.3)
+        model.eval()
+        with torch.no_grad():
+            pred, _ = model(torch.tensor(feat, dtype=torch.float), torch.tensor(adj, dtype=torch.float))
+        cg = dict(adj=adj, feat=feat, label=label, pred=pred.numpy(), train_idx=list(range(N)))
+        eargs = ref_harness.explainer_args(dataset="var" + tag, num_gc_layers=L, bn=bn, num_epochs=epochs)
+        nodes = [0, 5, 17, 40]
+        gold = explain_nodes_ref(R, model, cg, eargs, nodes, seed_base=7000 + 10 * L)
+        sd = model.state_dict()
+        keys = ["conv_first"] + ["conv_block.%d" % i for i in range(L - 2)] + ["conv_last"]
+        for l, k in enumerate(keys, 1):
+            out["%s_W%d" % (tag, l)] = sd[k + ".weight"].numpy().astype(np.float32)
+            out["%s_b%d" % (tag, l)] = sd[k + ".bias"].numpy().astype(np.float32)
+        out[tag + "_Wp"] = sd["pred_model.weight"].numpy().astype(np.float32)
+        out[tag + "_bp"] = sd["pred_model.bias"].numpy().astype(np.float32)
+        out[tag + "_pred"] = cg["pred"][0].astype(np.float32)
+        out[tag + "_nodes"] = np.asarray(nodes, np.int64)
+        for k, v in gold.items():
+            out[tag + "_" + k] = v
+    np.savez_compressed(os.path.join(OUT, "variants_golden.npz"), **out)
+    print("  variants golden written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -360,6 +402,10 @@ def main():
         return
     if a.only == "grad":
         gen_grad(ref_harness.load())
+        return
+    if a.only == "variants":
+        torch.set_num_threads(8)
+        gen_variants(ref_harness.load())
         return
     if a.only == "graph":
         torch.set_num_threads(8)

@@ -143,9 +143,12 @@ def draw_m0(n, seed=None):
 # ----------------------------------------------------------------------------------------------
 
 
-def _gcn_forward_torch(x, adj, W, graph_mode):
+def _gcn_forward_torch(x, adj, W, graph_mode, bn=False):
     """models.py:58-80 (GraphConv.forward), :230-267 (gcn_forward), :363-376 (node readout),
-    :269-316 (graph readout).  x (1,n,d), adj (1,n,n)."""
+    :269-316 (graph readout).  x (1,n,d), adj (1,n,n).  Any number of layers (len(W["conv_w"]) =
+    args.num_gc_layers).  bn=True: models.py:222-228,242-243,252-253 -- a FRESH BatchNorm1d(n) in train mode
+    after the ReLU of every layer but the last, i.e. each node's row is standardised over its features
+    (biased variance, eps 1e-5, no affine)."""
     import torch
     import torch.nn.functional as F
     outs = []
@@ -159,6 +162,8 @@ def _gcn_forward_torch(x, adj, W, graph_mode):
         y = F.normalize(y, p=2, dim=2)                 # models.py:78
         if l < L - 1:
             y = torch.relu(y)                          # models.py:241,251 (not on the last layer)
+            if bn:
+                y = F.batch_norm(y, None, None, None, None, True, 0.1, 1e-5)   # BatchNorm1d(n)(x) on (1,n,h): channels = nodes
         outs.append(y)
         h = y
     if graph_mode:
@@ -186,7 +191,7 @@ def weights_to_torch(weights, requires_grad=True):
 
 
 def explain_dense_torch(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, weights, M0,
-                        hp=None, graph_mode=False, trace=None):
+                        hp=None, graph_mode=False, trace=None, bn=False):
     """Port of Explainer.explain's optimisation (explain.py:97-146,209-211) with
     ExplainModule.{_masked_adj,forward,loss,mask_density} (explain.py:665-808) inlined.
 
@@ -219,7 +224,7 @@ def explain_dense_torch(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
             x.grad = None
         masked_adj = masked_adj_fn()                                            # explain.py:694
         xm = x * torch.sigmoid(feat_mask)                                       # explain.py:695-707
-        ypred = _gcn_forward_torch(xm, masked_adj, W, graph_mode)               # explain.py:709
+        ypred = _gcn_forward_torch(xm, masked_adj, W, graph_mode, bn)           # explain.py:709
         if graph_mode:
             res = torch.softmax(ypred[0], dim=0)                                # explain.py:711
         else:
@@ -275,8 +280,9 @@ def _sigmoid(x):
 
 
 def explain_closed_form(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, weights, M0,
-                        hp=None, graph_mode=False, dtype=np.float64, return_state=False):
-    """Hand-derived forward/backward.  Dense numpy arrays are used for
+                        hp=None, graph_mode=False, dtype=np.float64, return_state=False, bn=False):
+    """Hand-derived forward/backward, any number of layers; bn=True adds the per-node
+    standardisation of models.py:222-228 after every hidden layer's ReLU (forward and its backward).  Dense numpy arrays are used for
     brevity, but only the edge entries of M carry information: off-edge entries never influence
     the returned array.  Derivation notes next to each line cite what autograd differentiates."""
     hp = hp or default_hparams()
@@ -316,12 +322,22 @@ def explain_closed_form(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
         sF = _sigmoid(F)
         H = [X * sF]
         Yh, q = [], []
+        bn_state = []
         for l in range(L):
             Y = (a @ H[-1]) @ Ws[l] + bs[l]                                         # models.py:70-76
             ql = np.maximum(np.sqrt((Y * Y).sum(1, keepdims=True)), f(1e-12))       # F.normalize eps
             Yl = Y / ql
             Yh.append(Yl); q.append(ql)
-            H.append(np.maximum(Yl, 0) if l < L - 1 else Yl)
+            if l < L - 1:
+                Hl = np.maximum(Yl, 0)
+                if bn:                                                                 # BatchNorm1d(n), train mode, no affine
+                    mu = Hl.mean(1, keepdims=True)
+                    istd = 1 / np.sqrt(((Hl - mu) ** 2).mean(1, keepdims=True) + f(1e-5))
+                    Hl = (Hl - mu) * istd
+                    bn_state.append((Hl, istd))
+                H.append(Hl)
+            else:
+                H.append(Yl)
         dE = [np.zeros((n, dims[l]), f) for l in range(L)]
         if graph_mode:
             pooled = [H[l + 1].max(0) for l in range(L)]
@@ -344,6 +360,9 @@ def explain_closed_form(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
         for l in range(L - 1, -1, -1):
             dYh = dE[l] + dH
             if l < L - 1:
+                if bn:                                                                 # backward of the row standardisation
+                    Hb, istd = bn_state[l]
+                    dYh = (dYh - dYh.mean(1, keepdims=True) - Hb * (dYh * Hb).mean(1, keepdims=True)) * istd
                 dYh = dYh * (Yh[l] > 0)
             dY = (dYh - Yh[l] * (Yh[l] * dYh).sum(1, keepdims=True)) / q[l]          # backward of x/max(|x|,eps)
             dZ = dY @ Ws[l].T

@@ -194,3 +194,29 @@ def test_grad_baseline_oracle_matches_reference_golden():
             m = O.grad_baseline_dense_torch(A, sfeat, int(fx.pred_label[nbrs][idx]), idx, fx.weights)
             ei, ej = np.nonzero(A)
             assert O.rel_l2(m[ei, ej], g["%s_n%d_mask" % (which, node)]) < 1e-6
+
+
+@pytest.mark.parametrize("tag,L,bn", [("L2", 2, False), ("L4", 4, False), ("bn", 3, True)])
+def test_oracle_model_variants_match_reference(tag, L, bn):
+    """SURVEY 8(f3) variants the kernels do not build yet, pinned for the oracle (round-2 groundwork): the unmodified
+    reference with num_gc_layers = 2 / 4 and with --bn (tests/golden/variants_golden.npz, oracle/gen_golden.py --only
+    variants).  The torch port must be bit-exact, the closed form (the kernel specification) within fp32 round-off."""
+    g = np.load(util.GOLDEN + "/variants_golden.npz")
+    N = int(g["N"]); epochs = int(g["num_epochs"])
+    rowptr, col = O.csr_from_edges(N, g["edges"])
+    w = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_W") or k.startswith(tag + "_b")}
+    assert len([k for k in w if k.startswith("W") and k != "Wp"]) == L
+    pred_label = np.argmax(g[tag + "_pred"], 1)
+    for node in [int(x) for x in g[tag + "_nodes"]]:
+        idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(rowptr, col, g["feat"], g["label"], node, L)
+        assert np.array_equal(nbrs, g["%s_n%d_nbrs" % (tag, node)]) and idx == int(g["%s_n%d_idx_new" % (tag, node)])
+        A = O.dense_from_csr(srp, scol)
+        ei, ej = np.nonzero(A)
+        M0 = np.ones_like(A, dtype=np.float32); M0[ei, ej] = g["%s_n%d_m0" % (tag, node)]
+        ref = g["%s_n%d_mask" % (tag, node)]
+        hp = O.default_hparams(num_epochs=epochs)
+        # off-edge entries of M0 never reach the result, so any filler works for the dense port's edge entries
+        port = O.explain_dense_torch(A, sfeat, slabel[idx], pred_label[nbrs], idx, w, M0, hp=hp, bn=bn)
+        assert O.rel_l2(port[ei, ej], ref) < 1e-6, (tag, node, O.rel_l2(port[ei, ej], ref))
+        cf = O.explain_closed_form(A, sfeat, slabel[idx], pred_label[nbrs], idx, w, M0, hp=hp, bn=bn)
+        assert O.rel_l2(cf[ei, ej], ref) < 2e-5, (tag, node, O.rel_l2(cf[ei, ej], ref))
