@@ -295,3 +295,16 @@ class Explainer:
         """Same computation, returning (plan, edge_mask) without densifying: edge_mask[edge_off[t]:
         edge_off[t+1]] are the masked_adj entries of node t at plan.csr_of(t) (row-major order)."""
         return self._explain_batch(node_indices, graph_idx)
+
+    def iter_explain_nodes_packed(self, node_indices, chunk_size, graph_idx=0, model="exp"):
+        """Large graphs (BASELINE configs[4]: a k-hop neighbourhood is most of a 10^5-node graph, ~0.4 GB of plan and optimiser
+        state per explained node): explain the list `chunk_size` nodes at a time and yield (nodes_of_chunk, plan, edge_mask)
+        per chunk, so that neither the device workspace nor the host ever holds more than one chunk (one CTA per SM => 148 is a
+        natural chunk on a B200).  The dense (n,n) arrays of explain_nodes would need 80 GB per node there."""
+        nodes = [int(i) for i in node_indices]
+        if chunk_size < 1:
+            raise ValueError("chunk_size must be >= 1")
+        for s0 in range(0, len(nodes), int(chunk_size)):
+            part = nodes[s0:s0 + int(chunk_size)]
+            plan, edge_mask = self._explain_batch(part, graph_idx, model)
+            yield part, plan, edge_mask

@@ -164,3 +164,16 @@ def test_bench_ba_generator_is_a_simple_symmetric_graph():
     key = rows.astype(np.int64) * N + col
     assert np.all(np.diff(key) > 0)                                        # rows sorted, no duplicate edges
     assert np.array_equal(np.sort(key), np.sort(col.astype(np.int64) * N + rows))   # symmetric
+
+
+def test_iter_explain_nodes_packed_chunks_without_gpu():
+    """Chunked driver for large graphs: pure host logic over _explain_batch (stubbed here, no GPU)."""
+    from gnnx.explain import Explainer
+    ex = Explainer.__new__(Explainer)
+    calls = []
+    ex._explain_batch = lambda nodes, graph_idx=0, model="exp", unconstrained=False: (calls.append(list(nodes)) or ("plan%d" % len(calls), np.zeros(len(nodes))))
+    out = list(ex.iter_explain_nodes_packed(range(10), 4))
+    assert [c[0] for c in out] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]] and calls == [c[0] for c in out]
+    assert [len(c[2]) for c in out] == [4, 4, 2]
+    with pytest.raises(ValueError):
+        list(ex.iter_explain_nodes_packed([1, 2], 0))
