@@ -220,3 +220,33 @@ def test_oracle_model_variants_match_reference(tag, L, bn):
         assert O.rel_l2(port[ei, ej], ref) < 1e-6, (tag, node, O.rel_l2(port[ei, ej], ref))
         cf = O.explain_closed_form(A, sfeat, slabel[idx], pred_label[nbrs], idx, w, M0, hp=hp, bn=bn)
         assert O.rel_l2(cf[ei, ej], ref) < 2e-5, (tag, node, O.rel_l2(cf[ei, ej], ref))
+
+
+@pytest.mark.parametrize("L,bn", [(2, False), (3, False), (4, False), (3, True), (2, True), (4, True)])
+def test_pruned_edge_list_spec_is_exact_for_every_variant(L, bn):
+    """oracle/kernel_spec.py (parameters on the edges, every layer only on its receptive-field rows, inner/outer pair
+    split -- the form the CUDA kernels compute) against the dense unpruned closed form, fp64: the restructuring is exact
+    for any number of layers and with --bn, not only for the 3-layer no-bn model the round-1 kernels build."""
+    import networkx as nx
+    import kernel_spec as KS
+    rng = np.random.default_rng(10 * L + int(bn))
+    G = nx.barabasi_albert_graph(70, 2, seed=L)
+    N, d, C = 70, 9, 4
+    rowptr, col = O.csr_from_edges(N, np.array(G.edges(), dtype=np.int64))
+    feat = rng.normal(size=(N, d)); label = rng.integers(0, C, N); pred_label = rng.integers(0, C, N)
+    sc = lambda *s: rng.normal(size=s) * 0.5
+    w = {}
+    dims = [d] + [20] * L
+    for l in range(1, L + 1):
+        w["W%d" % l] = sc(dims[l - 1], dims[l]); w["b%d" % l] = sc(dims[l])
+    w["Wp"] = sc(C, 20 * L); w["bp"] = sc(C)
+    for node in (3, 41):
+        idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(rowptr, col, feat, label, node, L)
+        n = len(nbrs)
+        A = O.dense_from_csr(srp, scol)
+        M0 = O.draw_m0(n, seed=5 + node).astype(np.float64)
+        ei, ej = np.nonzero(A)
+        ref = O.explain_closed_form(A, sfeat, slabel[idx], pred_label[nbrs], idx, w, M0, hp=O.default_hparams(num_epochs=20), bn=bn)
+        got, st = KS.explain_pruned_edges(srp, scol, sfeat, slabel[idx], pred_label[nbrs], idx, w, M0[ei, ej], num_epochs=20, bn=bn)
+        assert O.rel_l2(got, ref[ei, ej]) < 1e-10, (L, bn, node, O.rel_l2(got, ref[ei, ej]))
+        assert st["rows_per_layer"][-1] == 1 and st["rows_per_layer"][0] <= n and st["inner_slots"] <= st["E"]
