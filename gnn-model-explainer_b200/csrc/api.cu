@@ -69,6 +69,7 @@ struct gx_handle {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   bool timed = false;
   float* dbg = nullptr;
+  bool ieee_edge = false;     // test knob (gx_debug_ieee_edge / GNNX_IEEE_EDGE): IEEE arithmetic in the edge phase
   bool force_stream = false;  // test knob (gx_debug_force_stream / GNNX_FORCE_STREAM): every task goes to the streaming class
   cudaEvent_t ev_join[kNumStreams] = {};
   int64_t launches = 0;
@@ -207,6 +208,7 @@ int gx_create(int device, gx_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* env = getenv("GNNX_FORCE_STREAM")) h->force_stream = atoi(env) != 0;
+  if (const char* env = getenv("GNNX_IEEE_EDGE")) h->ieee_edge = atoi(env) != 0;
   for (int i = 0; i < kNumStreams; ++i) {
     GX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
     GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
@@ -255,6 +257,9 @@ int64_t gx_launch_count(gx_handle* h) { return h ? h->launches : 0; }
 
 /* debug only (not in gnnx.h): device buffer receiving the shared-memory slab of the first task of each class */
 int gx_debug_set_dump(gx_handle* h, float* dev_buf) { if (!h) return GX_ERR_INVALID; h->dbg = dev_buf; return GX_OK; }
+
+/* debug only: IEEE exp/div/sqrt in the edge phase instead of the hardware approximations (parity measurements) */
+int gx_debug_ieee_edge(gx_handle* h, int on) { if (!h) return GX_ERR_INVALID; h->ieee_edge = on != 0; return GX_OK; }
 
 /* debug only (not in gnnx.h): plan every task into the streaming class (explain_stream.cu) regardless of its size */
 int gx_debug_force_stream(gx_handle* h, int on) { if (!h) return GX_ERR_INVALID; h->force_stream = on != 0; h->has_plan = false; return GX_OK; }
@@ -577,6 +582,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = hp->coef_lap;
   hd.adam_tab = h->d_adam.as<float2>();
   hd.init = hp->init;
+  hd.flags = h->ieee_edge ? GX_HP_IEEE_EDGE : 0;
   hd.mode = mode;
   hd.seed = hp->seed;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
@@ -806,7 +812,7 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
   GxHparamsDev hd;
   hd.iters = iters; hd.one_minus_b1 = 1.0f - hp->beta1; hd.b2 = hp->beta2; hd.one_minus_b2 = 1.0f - hp->beta2; hd.eps = hp->eps;
   hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = 0.f;
-  hd.adam_tab = h->d_adam.as<float2>(); hd.init = hp->init; hd.mode = 0; hd.seed = hp->seed;
+  hd.adam_tab = h->d_adam.as<float2>(); hd.init = hp->init; hd.flags = h->ieee_edge ? GX_HP_IEEE_EDGE : 0; hd.mode = 0; hd.seed = hp->seed;
   GxExplainLaunch cfg;
   cfg.order = h->d_order.as<int32_t>(); cfg.ntasks = count; cfg.counter = h->d_counters.as<int32_t>();
   cfg.smem_bytes = std::max(h->g_max_smem, 1024);

@@ -25,9 +25,13 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 // hardware approximations (ex2/rcp/rsqrt, <= 2 ulp): the phase is instruction-issue bound and IEEE
 // division/sqrt sequences were a third of its instructions.  The row-normalised forward/backward keeps
 // IEEE arithmetic.  Effect on parity: none measurable (tests/test_gpu_parity.py thresholds unchanged).
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float adam_delta_fast(float m, float v, float step, float bc2s_inv, float eps) {
-  return step * __fdividef(m, fmaf(__fsqrt_rn(v), bc2s_inv, eps));
+// `ieee` (GxHparamsDev::flags & GX_HP_IEEE_EDGE, test knob gx_debug_ieee_edge) selects the IEEE sequences instead, so the parity
+// tests can measure what the approximations move (tools/parity_report.py; profiles/r02_parity_report.md).
+__device__ __forceinline__ float sigmoid_fast(float x, bool ieee) {
+  return ieee ? 1.0f / (1.0f + expf(-x)) : __fdividef(1.0f, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float adam_delta_fast(float m, float v, float step, float bc2s, float bc2s_inv, float eps, bool ieee) {
+  return ieee ? step * (m / (sqrtf(v) / bc2s + eps)) : step * __fdividef(m, fmaf(__fsqrt_rn(v), bc2s_inv, eps));
 }
 
 // Philox4x32-10 (Salmon et al. 2011), used only for GX_INIT_PHILOX.

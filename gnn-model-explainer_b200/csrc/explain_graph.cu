@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
   const GxModelDev& m = A.m;
   const GxHparamsDev& hp = A.hp;
   const int d = m.d, C = m.C;
+  const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
 
   for (;;) {
     if (tid == 0) s_task = atomicAdd(A.counter, 1);
@@ -393,9 +394,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
           m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
           v2.x = v2.x * hp.b2 + hp.one_minus_b2 * gi * gi;
           v2.y = v2.y * hp.b2 + hp.one_minus_b2 * gj * gj;
-          Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s_inv, hp.eps);
-          Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s_inv, hp.eps);
-          const float2 Sn = make_float2(sigmoid_fast(Mv.x), sigmoid_fast(Mv.y));
+          Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s, bc2s_inv, hp.eps, ieee);
+          Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s, bc2s_inv, hp.eps, ieee);
+          const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
           a[ppij[p]] = an; a[ppji[p]] = an;

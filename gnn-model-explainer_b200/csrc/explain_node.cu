@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
   const GxModelDev& m = A.m;
   const GxHparamsDev& hp = A.hp;
   const int d = m.d, C = m.C;
+  const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
 
   for (;;) {
     if (tid == 0) s_task = atomicAdd(A.counter, 1);
@@ -562,9 +563,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
           v2.x = v2.x * hp.b2 + hp.one_minus_b2 * gi * gi;
           v2.y = v2.y * hp.b2 + hp.one_minus_b2 * gj * gj;
-          Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s_inv, hp.eps);
-          Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s_inv, hp.eps);
-          const float2 Sn = make_float2(sigmoid_fast(Mv.x), sigmoid_fast(Mv.y));
+          Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s, bc2s_inv, hp.eps, ieee);
+          Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s, bc2s_inv, hp.eps, ieee);
+          const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
           const IdxT pa = ppij[p], pb = ppji[p];
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
 __global__ void __launch_bounds__(256)
 outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays plan, int count,
                    const float* __restrict__ m0, float* __restrict__ out_mask) {
+  const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
     const GxTask* __restrict__ Tp = plan.tasks + t;
     const int np = Tp->npairs, np_in = Tp->npairs_in, n = Tp->n;
@@ -643,10 +645,10 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
         vi = vi * hp.b2 + hp.one_minus_b2 * gi * gi;
         vj = vj * hp.b2 + hp.one_minus_b2 * gj * gj;
         const float bc2s_inv = 1.0f / tab.y;
-        Mi = Mi - adam_delta_fast(mi, vi, tab.x, bc2s_inv, hp.eps);
-        Mj = Mj - adam_delta_fast(mj, vj, tab.x, bc2s_inv, hp.eps);
-        Si = sigmoid_fast(Mi);
-        Sj = sigmoid_fast(Mj);
+        Mi = Mi - adam_delta_fast(mi, vi, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
+        Mj = Mj - adam_delta_fast(mj, vj, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
+        Si = sigmoid_fast(Mi, ieee);
+        Sj = sigmoid_fast(Mj, ieee);
       }
       const float an = 0.5f * (Si + Sj);
       out_mask[edge_off + oij] = an;

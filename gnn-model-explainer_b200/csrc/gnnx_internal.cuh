@@ -78,9 +78,12 @@ struct GxHparamsDev {
   float c_size, c_feat_size, c_ent, c_lap;
   const float2* adam_tab;  // [iters] (step_size_t = lr/(1-b1^t), sqrt(1-b2^t)), computed in double on the host
   int32_t init;
+  int32_t flags;  // GX_HP_* bits
   int32_t mode;   // 0: mask optimisation; 1: gradient baseline (explain(model="grad")): one forward/backward on the unmasked subgraph
   uint64_t seed;
 };
+
+#define GX_HP_IEEE_EDGE 1  // edge phase with IEEE exp/div/sqrt instead of the hardware approximations (test knob)
 
 // ---------------------------------------------------------------------------------------------
 // Shared-memory layout of one task in the explainer kernel.  Computed identically on host

@@ -222,6 +222,11 @@ class Engine:
         self._lib.gx_debug_force_stream.argtypes = [C.c_void_p, C.c_int]
         _abi.check(self._lib.gx_debug_force_stream(self._h, int(bool(on))))
 
+    def debug_ieee_edge(self, on=True):
+        """Test knob: IEEE exp/div/sqrt in the edge phase instead of the hardware approximations."""
+        self._lib.gx_debug_ieee_edge.argtypes = [C.c_void_p, C.c_int]
+        _abi.check(self._lib.gx_debug_ieee_edge(self._h, int(bool(on))))
+
     def launch_count(self):
         return int(self._lib.gx_launch_count(self._h))
 

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Small invocation of every kernel for compute-sanitizer (racecheck / memcheck / synccheck are ~100x slower than a plain run):
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+k-hop extraction + shared-memory kernel on a mix of task sizes (syn1: hub node 0 and tiny tasks), the streaming kernel (forced),
+the gradient baseline, graph mode, densify, neighbourhood rows.  A few epochs each."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("gnn-model-explainer_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import util  # noqa: E402
+import gnnx  # noqa: E402
+from gnnx import _abi  # noqa: E402
+
+EPOCHS = int(os.environ.get("SAN_EPOCHS", "4"))
+
+
+def main():
+    which = sys.argv[1:] or ["node", "stream", "graph", "misc"]
+    fx = util.load_fixture("syn1")
+    if "node" in which:
+        eng = util.make_engine(fx)
+        nodes = [0, 3, 300, 301, 683, 699, 13, 550]
+        plan = eng.plan_nodes(nodes, 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS), util.golden_m0(fx, plan), out)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS, init=_abi.GX_INIT_PHILOX, seed=3), None, out)
+        eng.grad_nodes_host(out)
+        print("node ok", float(out.sum()))
+        eng.close()
+    if "stream" in which:
+        fr = util.load_fixture("rand")
+        eng = util.make_engine(fr)
+        eng.debug_force_stream(True)
+        plan = eng.plan_nodes(fr.nodes[:4], 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS), util.golden_m0(fr, plan), out)
+        eng.grad_nodes_host(out)
+        print("stream ok", float(out.sum()))
+        eng.close()
+    if "graph" in which:
+        g = np.load(util.GOLDEN + "/graphs_golden.npz")
+        eng = gnnx.Engine(0)
+        eng.set_model({k: g[k] for k in util.WKEYS})
+        eng.set_graph_batch(g["adj"], g["feat"], g["label"])
+        gids = [0, 3, 5, 11]
+        eoff = eng.plan_graphs(gids)
+        m0 = np.concatenate([g["g%d_m0" % i] for i in gids]).astype(np.float32)
+        out = np.zeros(int(eoff[-1]), np.float32)
+        eng.explain_graphs_host(eng.make_hparams(num_epochs=EPOCHS), m0, out)
+        print("graph ok", float(out.sum()))
+        eng.close()
+    if "misc" in which:
+        eng = util.make_engine(fx)
+        rows = eng.neighborhood_rows(np.arange(0, 700, 50), 3)
+        plan = eng.plan_nodes([300, 5], 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=2), util.golden_m0(fx, plan), out)
+        dense = eng.densify_host(out, int(sum(plan.n(t) ** 2 for t in range(plan.count))))
+        print("misc ok", int(rows.sum()), float(dense.sum()))
+        eng.close()
+
+
+if __name__ == "__main__":
+    main()
