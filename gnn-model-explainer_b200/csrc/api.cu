@@ -91,6 +91,9 @@ struct gx_handle {
   int64_t gws_stride_words = 0;
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
+  DevBuf d_trace, d_trpred, d_trouter, d_min, d_vin, d_fsin, d_Mout, d_mout, d_vout, d_fsout, d_m0dense, d_offedge;   // gx_explain_io staging (GX_HOST)
+  int32_t label_min = 0, label_max = 0, pred_min = 0, pred_max = 0;   // ranges of the uploaded labels (checked against num_classes at plan time)
+  bool has_label = false;
   GxPlanArrays plan{};
   // graph-classification mode
   bool has_batch = false, has_gplan = false;
@@ -178,6 +181,8 @@ void gx_default_hparams(gx_hparams* hp) {
   hp->mask_bias = 0;
   hp->init = GX_INIT_M0;
   hp->seed = 0;
+  hp->start_step = 0;
+  hp->reserved = 0;
 }
 
 int gx_create(int device, gx_handle** out) {
@@ -227,7 +232,8 @@ int gx_destroy(gx_handle* h) {
   DevBuf* bufs[] = {&h->g_rowptr, &h->g_col, &h->g_feat, &h->g_label, &h->g_pred, &h->m_buf, &h->d_nodes,
                     &h->d_tasks, &h->d_nbrs, &h->d_lo2gid, &h->d_srp, &h->d_scol, &h->d_irp, &h->d_icol,
                     &h->d_pairs, &h->d_order, &h->d_counters, &h->gb_rowptr, &h->gb_col, &h->gb_feat, &h->gb_label, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
-                    &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf};
+                    &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf, &h->d_trace, &h->d_trpred, &h->d_trouter, &h->d_min, &h->d_vin,
+                    &h->d_fsin, &h->d_Mout, &h->d_mout, &h->d_vout, &h->d_fsout, &h->d_m0dense, &h->d_offedge};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < kNumStreams; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -357,6 +363,13 @@ int gx_set_graph_csr(gx_handle* h, int64_t N, const int32_t* rowptr, const int32
         return GX_ERR_UNSUPPORTED;
       }
     }
+  h->has_label = label != nullptr;
+  h->label_min = h->label_max = label ? label[0] : 0;
+  h->pred_min = h->pred_max = pred_label[0];
+  for (int64_t i = 0; i < N; ++i) {
+    if (label) { h->label_min = std::min(h->label_min, label[i]); h->label_max = std::max(h->label_max, label[i]); }
+    h->pred_min = std::min(h->pred_min, pred_label[i]); h->pred_max = std::max(h->pred_max, pred_label[i]);
+  }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   GX_CUDA_CHECK(h->g_rowptr.reserve((size_t)(N + 1) * 4));
   GX_CUDA_CHECK(h->g_col.reserve((size_t)std::max<int64_t>(nnz, 1) * 4));
@@ -412,6 +425,9 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   if (count <= 0) { gx_set_error("gx_plan_nodes: count <= 0"); return GX_ERR_INVALID; }
   for (int t = 0; t < count; ++t)
     if (nodes[t] < 0 || nodes[t] >= h->g.N) { gx_set_error("gx_plan_nodes: node %d out of range [0,%lld)", nodes[t], (long long)h->g.N); return GX_ERR_INVALID; }
+  // the reference indexes pred[gt_label] / a float pred_label vector (explain.py:750-753,789): a label outside [0,C) is an IndexError there
+  if (h->has_label && (h->label_min < 0 || h->label_max >= h->m.C)) { gx_set_error("gx_plan_nodes: label values span [%d,%d], model has %d classes", h->label_min, h->label_max, h->m.C); return GX_ERR_INVALID; }
+  if (h->pred_min < 0 || h->pred_max >= h->m.C) { gx_set_error("gx_plan_nodes: pred_label values span [%d,%d], model has %d classes", h->pred_min, h->pred_max, h->m.C); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   h->has_plan = false;
   h->has_gplan = false;
@@ -529,62 +545,153 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
 
 }  // extern "C"
 
+namespace {
+
+// Device views of a gx_explain_io: identity for GX_DEVICE, staged through handle-owned buffers for GX_HOST.
+struct IoDev {
+  const float* m0 = nullptr;
+  float* out = nullptr;
+  float* feat = nullptr;
+  GxExtra x{};
+};
+
+cudaError_t stage_in(gx_handle* h, DevBuf& b, const float* host, size_t n, const float** dev) {
+  *dev = nullptr;
+  if (!host || n == 0) return cudaSuccess;
+  cudaError_t e = b.reserve(n * 4);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(b.p, host, n * 4, cudaMemcpyHostToDevice, h->stream);
+  *dev = b.as<float>();
+  return e;
+}
+cudaError_t stage_out(DevBuf& b, float* host, size_t n, float** dev) {
+  *dev = nullptr;
+  if (!host) return cudaSuccess;
+  cudaError_t e = b.reserve(std::max<size_t>(n, 1) * 4);
+  *dev = b.as<float>();
+  return e;
+}
+
+// Validates the optional buffers, stages them (GX_HOST) and fills the kernels' GxExtra.  epochs = num_epochs of the call.
+int io_prepare(gx_handle* h, const char* who, const gx_hparams* hp, int mode, gx_memspace space, const gx_explain_io* io, int count,
+               int64_t te, int d, int C, IoDev* D) {
+  if (!io || !io->edge_mask) { gx_set_error("%s: io->edge_mask is NULL", who); return GX_ERR_INVALID; }
+  const bool state = mode == 0 && hp->init == GX_INIT_STATE;
+  if (mode == 0 && hp->init != GX_INIT_PHILOX && !io->m0_edges) { gx_set_error("%s: init %d needs m0_edges", who, hp->init); return GX_ERR_INVALID; }
+  if (state && (!io->adam_m_in || !io->adam_v_in)) { gx_set_error("%s: GX_INIT_STATE needs adam_m_in and adam_v_in", who); return GX_ERR_INVALID; }
+  if (state && hp->start_step < 0) { gx_set_error("%s: start_step < 0", who); return GX_ERR_INVALID; }
+  if (!state && hp->start_step != 0) { gx_set_error("%s: start_step != 0 without GX_INIT_STATE", who); return GX_ERR_INVALID; }
+  if (io->trace_pred && !io->trace) { gx_set_error("%s: trace_pred needs trace", who); return GX_ERR_INVALID; }
+  if (io->trace && mode != 0) { gx_set_error("%s: no trace for the gradient baseline", who); return GX_ERR_INVALID; }
+  if (io->trace && hp->num_epochs > 1536) { gx_set_error("%s: a trace supports at most 1536 epochs per call", who); return GX_ERR_UNSUPPORTED; }
+  const size_t ne = (size_t)std::max<int64_t>(te, 1), nf = (size_t)count * d, nfs = (size_t)count * 3 * d;
+  const size_t ntr = (size_t)count * hp->num_epochs * GX_TRACE_COLS, ntp = (size_t)count * hp->num_epochs * C;
+  GxExtra& x = D->x;
+  x.epochs = hp->num_epochs;
+  if (space == GX_DEVICE) {
+    D->m0 = io->m0_edges; D->out = io->edge_mask; D->feat = io->feat_mask;
+    x.trace = io->trace; x.trace_pred = io->trace_pred;
+    x.adam_m_in = io->adam_m_in; x.adam_v_in = io->adam_v_in; x.feat_state_in = io->feat_state_in;
+    x.mask_param_out = io->mask_param_out; x.adam_m_out = io->adam_m_out; x.adam_v_out = io->adam_v_out; x.feat_state_out = io->feat_state_out;
+  } else {
+    const bool need_m0 = mode == 0 && hp->init != GX_INIT_PHILOX;
+    GX_CUDA_CHECK(stage_in(h, h->d_m0, need_m0 ? io->m0_edges : nullptr, (size_t)te, &D->m0));
+    GX_CUDA_CHECK(stage_out(h->d_out, io->edge_mask, ne, &D->out));
+    GX_CUDA_CHECK(stage_out(h->d_feat, io->feat_mask, nf, &D->feat));
+    GX_CUDA_CHECK(stage_out(h->d_trace, io->trace, ntr, &x.trace));
+    GX_CUDA_CHECK(stage_out(h->d_trpred, io->trace_pred, ntp, &x.trace_pred));
+    GX_CUDA_CHECK(stage_in(h, h->d_min, state ? io->adam_m_in : nullptr, (size_t)te, &x.adam_m_in));
+    GX_CUDA_CHECK(stage_in(h, h->d_vin, state ? io->adam_v_in : nullptr, (size_t)te, &x.adam_v_in));
+    GX_CUDA_CHECK(stage_in(h, h->d_fsin, state ? io->feat_state_in : nullptr, nfs, &x.feat_state_in));
+    GX_CUDA_CHECK(stage_out(h->d_Mout, io->mask_param_out, ne, &x.mask_param_out));
+    GX_CUDA_CHECK(stage_out(h->d_mout, io->adam_m_out, ne, &x.adam_m_out));
+    GX_CUDA_CHECK(stage_out(h->d_vout, io->adam_v_out, ne, &x.adam_v_out));
+    GX_CUDA_CHECK(stage_out(h->d_fsout, io->feat_state_out, nfs, &x.feat_state_out));
+  }
+  if (!state) { x.adam_m_in = nullptr; x.adam_v_in = nullptr; x.feat_state_in = nullptr; }
+  if (x.trace) {
+    GX_CUDA_CHECK(h->d_trouter.reserve((size_t)count * hp->num_epochs * 4 * sizeof(double)));
+    GX_CUDA_CHECK(cudaMemsetAsync(h->d_trouter.p, 0, (size_t)count * hp->num_epochs * 4 * sizeof(double), h->stream));
+    x.tr_outer = h->d_trouter.as<double>();
+  }
+  return GX_OK;
+}
+
+// copies the staged outputs back (GX_HOST) and synchronises
+int io_finish(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io, int count, int64_t te, int d, int C, const IoDev& D) {
+  if (space != GX_HOST) return GX_OK;
+  auto back = [&](float* host, const float* dev, size_t n) -> cudaError_t {
+    if (!host || !dev || n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(host, dev, n * 4, cudaMemcpyDeviceToHost, h->stream);
+  };
+  GX_CUDA_CHECK(back(io->edge_mask, D.out, (size_t)te));
+  GX_CUDA_CHECK(back(io->feat_mask, D.feat, (size_t)count * d));
+  GX_CUDA_CHECK(back(io->trace, D.x.trace, (size_t)count * hp->num_epochs * GX_TRACE_COLS));
+  GX_CUDA_CHECK(back(io->trace_pred, D.x.trace_pred, (size_t)count * hp->num_epochs * C));
+  GX_CUDA_CHECK(back(io->mask_param_out, D.x.mask_param_out, (size_t)te));
+  GX_CUDA_CHECK(back(io->adam_m_out, D.x.adam_m_out, (size_t)te));
+  GX_CUDA_CHECK(back(io->adam_v_out, D.x.adam_v_out, (size_t)te));
+  GX_CUDA_CHECK(back(io->feat_state_out, D.x.feat_state_out, (size_t)count * 3 * d));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return GX_OK;
+}
+
+// Adam bias-correction table in double, exactly as torch's python scalars (torch/optim/adam.py), for steps start+1 .. start+iters
+int upload_adam_table(gx_handle* h, const gx_hparams* hp, int iters, int start) {
+  std::vector<float2> tab(std::max(iters, 1));
+  for (int k = 1; k <= iters; ++k) {
+    const double t = (double)(start + k);
+    const double bc1 = 1.0 - std::pow((double)hp->beta1, t);
+    const double bc2 = 1.0 - std::pow((double)hp->beta2, t);
+    tab[k - 1].x = (float)((double)hp->lr / bc1);
+    tab[k - 1].y = (float)std::sqrt(bc2);
+  }
+  GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
+  // pageable source: the copy is staged before the call returns, the vector may go out of scope
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_adam.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  return GX_OK;
+}
+
+void fill_hparams(const gx_handle* h, const gx_hparams* hp, int mode, bool trace, GxHparamsDev* hd) {
+  hd->out_iter = mode == 1 ? 1 : hp->num_epochs - 1;
+  hd->iters = (trace && mode == 0) ? hp->num_epochs : hd->out_iter;   // a trace also needs the last epoch's loss and the density after its step
+  hd->one_minus_b1 = 1.0f - hp->beta1;
+  hd->b2 = hp->beta2;
+  hd->one_minus_b2 = 1.0f - hp->beta2;
+  hd->eps = hp->eps;
+  hd->c_size = hp->coef_size; hd->c_feat_size = hp->coef_feat_size; hd->c_ent = hp->coef_ent; hd->c_lap = hp->coef_lap;
+  hd->adam_tab = h->d_adam.as<float2>();
+  hd->init = hp->init;
+  hd->flags = h->ieee_edge ? GX_HP_IEEE_EDGE : 0;
+  hd->mode = mode;
+  hd->seed = hp->seed;
+}
+
+}  // namespace
+
 // mode 0: Explainer.explain's optimisation loop; mode 1: its model="grad" baseline (one forward/backward, explain.py:125-133,717-738)
-static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_memspace space, const float* m0_edges,
-                              float* edge_mask, float* feat_mask) {
-  if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_nodes: NULL argument"); return GX_ERR_INVALID; }
+static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_memspace space, const gx_explain_io* io) {
+  if (!h || !hp) { gx_set_error("gx_explain_nodes: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_plan) { gx_set_error("gx_explain_nodes: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
   // mask_act "ReLU": the reference's entropy term takes log(1 - relu(M)) with M ~ N(1, 2/n) -> NaN masks from step 1 (explain.py:755-770;
   // pinned by tests/test_oracle.py): nothing to reproduce.  mask_bias: the bias parameter starts at 0 where ReLU6'(0) = 0, so Adam never
   // moves it and the result equals the default run bit for bit (explain.py:657-660,673-676; same test): accepted, no extra state.
   if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_nodes: num_epochs < 1"); return GX_ERR_INVALID; }
-  if (mode == 0 && hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_nodes: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
-  if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
+  if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX && hp->init != GX_INIT_STATE) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   const int count = h->count;
   const int64_t te = h->total_e;
-  const int iters = mode == 1 ? 1 : hp->num_epochs - 1;
-  // Adam bias-correction table in double, exactly as torch's python scalars (torch/optim/adam.py)
-  std::vector<float2> tab(std::max(iters, 1));
-  for (int t = 1; t <= iters; ++t) {
-    const double bc1 = 1.0 - std::pow((double)hp->beta1, (double)t);
-    const double bc2 = 1.0 - std::pow((double)hp->beta2, (double)t);
-    tab[t - 1].x = (float)((double)hp->lr / bc1);
-    tab[t - 1].y = (float)std::sqrt(bc2);
-  }
-  GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
-  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_adam.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  const float* m0_dev = nullptr;
-  float* out_dev = nullptr;
-  float* feat_dev = nullptr;
-  if (space == GX_DEVICE) {
-    m0_dev = m0_edges; out_dev = edge_mask; feat_dev = feat_mask;
-  } else {
-    if (mode == 0 && hp->init == GX_INIT_M0) {
-      GX_CUDA_CHECK(h->d_m0.reserve((size_t)std::max<int64_t>(te, 1) * 4));
-      GX_CUDA_CHECK(cudaMemcpyAsync(h->d_m0.p, m0_edges, (size_t)te * 4, cudaMemcpyHostToDevice, h->stream));
-      m0_dev = h->d_m0.as<float>();
-    }
-    GX_CUDA_CHECK(h->d_out.reserve((size_t)std::max<int64_t>(te, 1) * 4));
-    out_dev = h->d_out.as<float>();
-    if (feat_mask) {
-      GX_CUDA_CHECK(h->d_feat.reserve((size_t)count * h->m.d * 4));
-      feat_dev = h->d_feat.as<float>();
-    }
-  }
+  IoDev D;
+  int rc = io_prepare(h, "gx_explain_nodes", hp, mode, space, io, count, te, h->m.d, h->m.C, &D);
+  if (rc != GX_OK) return rc;
   GxHparamsDev hd;
-  hd.iters = iters;
-  hd.one_minus_b1 = 1.0f - hp->beta1;
-  hd.b2 = hp->beta2;
-  hd.one_minus_b2 = 1.0f - hp->beta2;
-  hd.eps = hp->eps;
-  hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = hp->coef_lap;
-  hd.adam_tab = h->d_adam.as<float2>();
-  hd.init = hp->init;
-  hd.flags = h->ieee_edge ? GX_HP_IEEE_EDGE : 0;
-  hd.mode = mode;
-  hd.seed = hp->seed;
+  fill_hparams(h, hp, mode, D.x.trace != nullptr, &hd);
+  rc = upload_adam_table(h, hp, hd.iters, mode == 0 ? hp->start_step : 0);
+  if (rc != GX_OK) return rc;
+  const float* m0_dev = D.m0;
+  float* out_dev = D.out;
+  float* feat_dev = D.feat;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
   int stream_grid = 0;
   if (!h->class_order[kNumClasses - 1].empty()) {
@@ -636,6 +743,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     cfg.gws = h->d_gws.as<float>();
     cfg.gws_stride_words = h->gws_stride_words;
     cfg.dbg = h->dbg;
+    cfg.x = D.x;
     cfg.pws = h->d_pws.as<float>() + pws_off[c];
     cfg.pws_stride_words = pws_stride[c];
     cfg.grid = grids[c];
@@ -653,30 +761,73 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     used.push_back(c);
   }
   // pairs between two outermost nodes: independent scalar recurrences, whole batch in one launch
-  GX_CUDA_CHECK(gx_launch_outer_pairs(hd, h->g, h->plan, count, m0_dev, out_dev, h->stream));
+  GX_CUDA_CHECK(gx_launch_outer_pairs(hd, h->g, h->plan, count, m0_dev, out_dev, D.x, h->stream));
   h->launches += 1;
   for (int c : used) GX_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_join[c], 0));
+  if (D.x.trace) {
+    GX_CUDA_CHECK(gx_launch_trace_finalize(hd, h->plan, count, D.x, h->stream));
+    h->launches += 1;
+  }
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
   h->timed = true;
-  if (space == GX_HOST) {
-    GX_CUDA_CHECK(cudaMemcpyAsync(edge_mask, out_dev, (size_t)te * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (feat_mask) GX_CUDA_CHECK(cudaMemcpyAsync(feat_mask, feat_dev, (size_t)count * h->m.d * 4, cudaMemcpyDeviceToHost, h->stream));
-    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  }
-  return GX_OK;
+  return io_finish(h, hp, space, io, count, te, h->m.d, h->m.C, D);
 }
 
 extern "C" {
 
 int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
                      float* edge_mask, float* feat_mask) {
-  return explain_nodes_impl(h, hp, 0, space, m0_edges, edge_mask, feat_mask);
+  gx_explain_io io;
+  memset(&io, 0, sizeof(io));
+  io.m0_edges = m0_edges; io.edge_mask = edge_mask; io.feat_mask = feat_mask;
+  return explain_nodes_impl(h, hp, 0, space, &io);
+}
+
+int gx_explain_nodes_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io) {
+  return explain_nodes_impl(h, hp, 0, space, io);
 }
 
 int gx_grad_nodes(gx_handle* h, gx_memspace space, float* edge_mask) {
   gx_hparams hp;
   gx_default_hparams(&hp);
-  return explain_nodes_impl(h, &hp, 1, space, nullptr, edge_mask, nullptr);
+  gx_explain_io io;
+  memset(&io, 0, sizeof(io));
+  io.edge_mask = edge_mask;
+  return explain_nodes_impl(h, &hp, 1, space, &io);
+}
+
+int gx_offedge_regularisers(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_dense, double* out) {
+  if (!h || !hp || !m0_dense || !out) { gx_set_error("gx_offedge_regularisers: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_plan) { gx_set_error("gx_offedge_regularisers: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
+  if (hp->num_epochs < 1 || hp->num_epochs > 3072) { gx_set_error("gx_offedge_regularisers: num_epochs outside [1,3072]"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int count = h->count, E = hp->num_epochs;
+  std::vector<int64_t> doff(count + 1);
+  int64_t acc = 0;
+  for (int t = 0; t < count; ++t) { doff[t] = acc; acc += (int64_t)h->tasks[t].n * h->tasks[t].n; }
+  doff[count] = acc;
+  GX_CUDA_CHECK(h->d_dense_off.reserve((size_t)(count + 1) * 8));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_dense_off.p, doff.data(), (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  GxHparamsDev hd;
+  fill_hparams(h, hp, 0, false, &hd);
+  int rc = upload_adam_table(h, hp, E, 0);
+  if (rc != GX_OK) return rc;
+  const float* m0d = m0_dense;
+  double* od = out;
+  const size_t nout = (size_t)count * E * 2;
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(h->d_m0dense.reserve((size_t)std::max<int64_t>(acc, 1) * 4));
+    GX_CUDA_CHECK(cudaMemcpyAsync(h->d_m0dense.p, m0_dense, (size_t)acc * 4, cudaMemcpyHostToDevice, h->stream));
+    GX_CUDA_CHECK(h->d_offedge.reserve(nout * 8));
+    m0d = h->d_m0dense.as<float>();
+    od = h->d_offedge.as<double>();
+  }
+  GX_CUDA_CHECK(cudaMemsetAsync(od, 0, nout * 8, h->stream));
+  GX_CUDA_CHECK(gx_launch_offedge(hd, h->plan, count, E, h->d_dense_off.as<int64_t>(), m0d, od, h->stream));
+  h->launches += 1;
+  if (space == GX_HOST) GX_CUDA_CHECK(cudaMemcpyAsync(out, od, nout * 8, cudaMemcpyDeviceToHost, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));   // doff (host vector) was copied asynchronously
+  return GX_OK;
 }
 
 int gx_set_graph_batch_csr(gx_handle* h, int32_t G, int32_t max_nodes, const int32_t* rowptr, const int32_t* col,
@@ -779,40 +930,24 @@ int gx_plan_graphs(gx_handle* h, const int32_t* graph_ids, int32_t count, int64_
   return GX_OK;
 }
 
-int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
-                      float* edge_mask, float* feat_mask) {
-  if (!h || !hp || !edge_mask) { gx_set_error("gx_explain_graphs: NULL argument"); return GX_ERR_INVALID; }
+static int explain_graphs_impl(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io) {
+  if (!h || !hp) { gx_set_error("gx_explain_graphs: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_gplan) { gx_set_error("gx_explain_graphs: no plan (call gx_plan_graphs)"); return GX_ERR_INVALID; }
   if (hp->mask_act != 0) { gx_set_error("gx_explain_graphs: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_graphs: num_epochs < 1"); return GX_ERR_INVALID; }
-  if (hp->init == GX_INIT_M0 && !m0_edges) { gx_set_error("gx_explain_graphs: GX_INIT_M0 needs m0_edges"); return GX_ERR_INVALID; }
+  if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX && hp->init != GX_INIT_STATE) { gx_set_error("gx_explain_graphs: unknown init %d", hp->init); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   const int count = h->g_count;
   const int64_t te = h->g_total_e;
-  const int iters = hp->num_epochs - 1;
-  std::vector<float2> tab(std::max(iters, 1));
-  for (int t = 1; t <= iters; ++t) {
-    tab[t - 1].x = (float)((double)hp->lr / (1.0 - std::pow((double)hp->beta1, (double)t)));
-    tab[t - 1].y = (float)std::sqrt(1.0 - std::pow((double)hp->beta2, (double)t));
-  }
-  GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
-  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_adam.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-  const float* m0_dev = nullptr; float* out_dev = nullptr; float* feat_dev = nullptr;
-  if (space == GX_DEVICE) { m0_dev = m0_edges; out_dev = edge_mask; feat_dev = feat_mask; }
-  else {
-    if (hp->init == GX_INIT_M0) {
-      GX_CUDA_CHECK(h->d_m0.reserve((size_t)std::max<int64_t>(te, 1) * 4));
-      GX_CUDA_CHECK(cudaMemcpyAsync(h->d_m0.p, m0_edges, (size_t)te * 4, cudaMemcpyHostToDevice, h->stream));
-      m0_dev = h->d_m0.as<float>();
-    }
-    GX_CUDA_CHECK(h->d_out.reserve((size_t)std::max<int64_t>(te, 1) * 4));
-    out_dev = h->d_out.as<float>();
-    if (feat_mask) { GX_CUDA_CHECK(h->d_feat.reserve((size_t)count * h->m.d * 4)); feat_dev = h->d_feat.as<float>(); }
-  }
+  IoDev D;
+  int rc = io_prepare(h, "gx_explain_graphs", hp, 0, space, io, count, te, h->m.d, h->m.C, &D);
+  if (rc != GX_OK) return rc;
+  D.x.tr_outer = nullptr;   // graph mode has no outer pairs
   GxHparamsDev hd;
-  hd.iters = iters; hd.one_minus_b1 = 1.0f - hp->beta1; hd.b2 = hp->beta2; hd.one_minus_b2 = 1.0f - hp->beta2; hd.eps = hp->eps;
-  hd.c_size = hp->coef_size; hd.c_feat_size = hp->coef_feat_size; hd.c_ent = hp->coef_ent; hd.c_lap = 0.f;
-  hd.adam_tab = h->d_adam.as<float2>(); hd.init = hp->init; hd.flags = h->ieee_edge ? GX_HP_IEEE_EDGE : 0; hd.mode = 0; hd.seed = hp->seed;
+  fill_hparams(h, hp, 0, D.x.trace != nullptr, &hd);
+  hd.c_lap = 0.f;           // lap_loss = 0 in graph mode (explain.py:787-788)
+  rc = upload_adam_table(h, hp, hd.iters, hp->start_step);
+  if (rc != GX_OK) return rc;
   GxExplainLaunch cfg;
   cfg.order = h->d_order.as<int32_t>(); cfg.ntasks = count; cfg.counter = h->d_counters.as<int32_t>();
   cfg.smem_bytes = std::max(h->g_max_smem, 1024);
@@ -820,21 +955,33 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
   const int per_sm = std::max(1, std::min(16, (227 * 1024) / (cfg.smem_bytes + 1024)));
   cfg.grid = std::min(count, h->num_sms * per_sm);
   cfg.gws = nullptr; cfg.gws_stride_words = 0; cfg.dbg = nullptr;
+  cfg.x = D.x;
   cfg.pws_stride_words = ((int64_t)h->g_max_np * 8 + 3) / 4 * 4;
   GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(cfg.pws_stride_words * cfg.grid, 4) * 4));
   cfg.pws = h->d_pws.as<float>();
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->stream));
-  GX_CUDA_CHECK(gx_launch_explain_graphs(cfg, h->gb, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->stream));
+  GX_CUDA_CHECK(gx_launch_explain_graphs(cfg, h->gb, h->m, hd, h->plan, D.m0, D.out, D.feat, h->stream));
   h->launches += 1;
+  if (D.x.trace) {
+    GX_CUDA_CHECK(gx_launch_trace_finalize(hd, h->plan, count, D.x, h->stream));
+    h->launches += 1;
+  }
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
   h->timed = true;
-  if (space == GX_HOST) {
-    GX_CUDA_CHECK(cudaMemcpyAsync(edge_mask, out_dev, (size_t)te * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (feat_mask) GX_CUDA_CHECK(cudaMemcpyAsync(feat_mask, feat_dev, (size_t)count * h->m.d * 4, cudaMemcpyDeviceToHost, h->stream));
-    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  }
-  return GX_OK;
+  return io_finish(h, hp, space, io, count, te, h->m.d, h->m.C, D);
+}
+
+int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
+                      float* edge_mask, float* feat_mask) {
+  gx_explain_io io;
+  memset(&io, 0, sizeof(io));
+  io.m0_edges = m0_edges; io.edge_mask = edge_mask; io.feat_mask = feat_mask;
+  return explain_graphs_impl(h, hp, space, &io);
+}
+
+int gx_explain_graphs_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io) {
+  return explain_graphs_impl(h, hp, space, io);
 }
 
 int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* out) {

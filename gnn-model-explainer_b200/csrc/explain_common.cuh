@@ -102,7 +102,11 @@ struct ExplainArgs {
   float* out_mask;
   float* out_feat;
   float* dbg;  // optional debug dump of the shared-memory arrays of task 0 after the backward of epoch 1
+  GxExtra x;   // optional trace / optimiser-state buffers (gx_explain_io)
 };
+
+// entropy of a Bernoulli(s) in nats, as the reference writes it (explain.py:769): no guard at s -> 0/1, like torch
+__device__ __forceinline__ float bern_entropy(float s) { return -s * logf(s) - (1.0f - s) * logf(1.0f - s); }
 
 // ---------------------------------------------------------------------------------------------
 // Lane-group primitives.  A warp = epi groups of GW lanes; lane = grp*GW + q.

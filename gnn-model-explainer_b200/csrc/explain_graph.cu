@@ -102,12 +102,14 @@ struct GraphArgs {
   const float* m0;
   float* out_mask;
   float* out_feat;
+  GxExtra x;
 };
 
-template <int HID, int EMB, int NT>
+template <int HID, int EMB, int NT, bool kTrace>
 __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const GraphArgs A) {
   extern __shared__ __align__(16) float base[];
   __shared__ int s_task;
+  __shared__ float s_tr[kTrace ? (NT / 32) * 4 + 4 : 1];   // trace: per-warp partial sums of the edge phase + (pred loss, p[gt], feat-size term)
   __shared__ GxLayoutG sL;
   typedef uint16_t IdxT;
   constexpr IdxT kNone = 0xFFFFu;
@@ -173,7 +175,22 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
     }
     for (int e = tid; e < e_d; e += nthreads) icol[e] = (IdxT)A.plan.icol[edge_off + e];
     for (int i = tid; i <= na; i += nthreads) irp[i] = (IdxT)A.plan.irowptr[rp_off + i];
-    for (int f = tid; f < dp; f += nthreads) { sF[f] = 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f; }
+    const bool resume = hp.init == GX_INIT_STATE;   // optimiser state supplied by the caller (gx_explain_io)
+    for (int f = tid; f < dp; f += nthreads) {
+      sF[f] = 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f;
+      if (resume && A.x.feat_state_in != nullptr && f < d) {
+        const float* fs = A.x.feat_state_in + (int64_t)task_id * 3 * d;
+        Fm[f] = fs[f]; mF[f] = fs[d + f]; vF[f] = fs[2 * d + f];
+        sF[f] = sigmoid_f(fs[f]);
+      }
+      if (hp.out_iter == 0 && f < d) {
+        if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sF[f];
+        if (A.x.feat_state_out != nullptr) {
+          float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
+          fo[f] = Fm[f]; fo[d + f] = mF[f]; fo[2 * d + f] = vF[f];
+        }
+      }
+    }
     const float m0_std = sqrtf(2.0f / (float)Tp->n_norm);
     for (int p = tid; p < np; p += nthreads) {
       const int i = A.plan.pair_i[pair_off + p], j = A.plan.pair_j[pair_off + p];
@@ -181,17 +198,27 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
       const int oij = A.plan.pair_oij[pair_off + p], oji = A.plan.pair_oji[pair_off + p];
       pi[p] = (IdxT)i; pj[p] = (IdxT)j; ppij[p] = (IdxT)pij; ppji[p] = (IdxT)pji;
       float Mi, Mj;
-      if (hp.init == GX_INIT_M0) { Mi = __ldg(A.m0 + edge_off + oij); Mj = __ldg(A.m0 + edge_off + oji); }
+      if (hp.init != GX_INIT_PHILOX) { Mi = __ldg(A.m0 + edge_off + oij); Mj = __ldg(A.m0 + edge_off + oji); }
       else {
         Mi = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)g, (uint32_t)oij);
         Mj = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)g, (uint32_t)oji);
       }
-      MM[p] = make_float2(Mi, Mj); mm[p] = make_float2(0.f, 0.f); vv[p] = make_float2(0.f, 0.f);
+      float2 m2 = make_float2(0.f, 0.f), v2 = m2;
+      if (resume) {
+        m2 = make_float2(__ldg(A.x.adam_m_in + edge_off + oij), __ldg(A.x.adam_m_in + edge_off + oji));
+        v2 = make_float2(__ldg(A.x.adam_v_in + edge_off + oij), __ldg(A.x.adam_v_in + edge_off + oji));
+      }
+      MM[p] = make_float2(Mi, Mj); mm[p] = m2; vv[p] = v2;
       const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
       SS[p] = make_float2(Si, Sj);
       const float a0 = 0.5f * (Si + Sj);
       a[pij] = a0; a[pji] = a0;
-      if (hp.iters == 0) { A.out_mask[edge_off + oij] = a0; A.out_mask[edge_off + oji] = a0; }
+      if (hp.out_iter == 0) {
+        A.out_mask[edge_off + oij] = a0; A.out_mask[edge_off + oji] = a0;
+        if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[edge_off + oij] = Mi; A.x.mask_param_out[edge_off + oji] = Mj; }
+        if (A.x.adam_m_out != nullptr) { A.x.adam_m_out[edge_off + oij] = m2.x; A.x.adam_m_out[edge_off + oji] = m2.y; }
+        if (A.x.adam_v_out != nullptr) { A.x.adam_v_out[edge_off + oij] = v2.x; A.x.adam_v_out[edge_off + oji] = v2.y; }
+      }
     }
     __syncthreads();
     // embedding of a row without edges: Y = 0 W + b -> normalize(b_l) (-> ReLU for l < 3), independent of the masks
@@ -286,6 +313,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
         for (int c = lane; c < C; c += 32) se += expf(logit[c] - mx);
         se = warp_sum(se);
         __syncwarp();
+        if (kTrace) {
+          float* const tr = s_tr + (NT / 32) * 4;
+          if (lane == 0) { const float lg = logit[gt]; tr[0] = -((lg - mx) - logf(se)); tr[1] = expf(lg - mx) / se; }
+          if (A.x.trace_pred != nullptr) {
+            float* trp = A.x.trace_pred + ((int64_t)task_id * A.x.epochs + (it - 1)) * C;
+            for (int c = lane; c < C; c += 32) trp[c] = expf(logit[c] - mx) / se;
+          }
+          float fs = 0.f;   // feat_size_loss = coeff * mean(sigmoid(feat_mask)) (explain.py:763-766)
+          for (int f = lane; f < d; f += 32) fs += sF[f];
+          fs = warp_sum(fs);
+          if (lane == 0) tr[2] = hp.c_feat_size * fs / (float)d;
+          __syncwarp();
+        }
         for (int c = lane; c < C; c += 32) logit[c] = expf(logit[c] - mx) / se - (c == gt ? 1.f : 0.f);
         __syncwarp();
         for (int k = lane; k < PD; k += 32) {
@@ -366,7 +406,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
       {
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
-        const bool last = (it == hp.iters);
+        const bool last = (it == hp.out_iter);   // the mask built after this update is the one the reference returns
         for (int f = tid; f < d; f += nthreads) {
           float gsum = 0.f;
           for (int w = 0; w < nwarps; ++w) gsum += gFp[w * dp + f];
@@ -377,8 +417,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
           vf = vf * hp.b2 + hp.one_minus_b2 * gg * gg;
           Fv = Fv - step * (mf / (sqrtf(vf) / bc2s + hp.eps));
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
-          sF[f] = sigmoid_f(Fv);
+          const float sn = sigmoid_f(Fv);
+          sF[f] = sn;
+          if (last) {
+            if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sn;
+            if (A.x.feat_state_out != nullptr) {
+              float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
+              fo[f] = Fv; fo[d + f] = mf; fo[2 * d + f] = vf;
+            }
+          }
         }
+        float trS = 0.f, trH = 0.f, trD = 0.f;   // trace: this thread's share of sum S, sum H(S), sum 2a' (no Laplacian term in graph mode)
         for (int p = tid; p < np; p += nthreads) {
           const int i = pi[p], j = pj[p];
           float Gd = dot_v4(U + i * dp, X + j * dp, D4) + dot_v4(U + j * dp, X + i * dp, D4);
@@ -387,6 +436,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
           Gd *= 0.5f;
           float2 Mv = MM[p];
           const float2 Sv = SS[p];
+          if (kTrace) { trS += Sv.x + Sv.y; trH += bern_entropy(Sv.x) + bern_entropy(Sv.y); }
           const float gi = Sv.x * (1.f - Sv.x) * (Gd + hp.c_size - ent_over_nn * Mv.x);
           const float gj = Sv.y * (1.f - Sv.y) * (Gd + hp.c_size - ent_over_nn * Mv.y);
           float2 m2 = mm[p], v2 = vv[p];
@@ -399,17 +449,31 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
           const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
+          if (kTrace) trD += 2.0f * an;
           a[ppij[p]] = an; a[ppji[p]] = an;
           if (last) {
-            A.out_mask[edge_off + A.plan.pair_oij[pair_off + p]] = an;
-            A.out_mask[edge_off + A.plan.pair_oji[pair_off + p]] = an;
+            const int64_t oij = edge_off + A.plan.pair_oij[pair_off + p], oji = edge_off + A.plan.pair_oji[pair_off + p];
+            A.out_mask[oij] = an;
+            A.out_mask[oji] = an;
+            if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[oij] = Mv.x; A.x.mask_param_out[oji] = Mv.y; }
+            if (A.x.adam_m_out != nullptr) { A.x.adam_m_out[oij] = m2.x; A.x.adam_m_out[oji] = m2.y; }
+            if (A.x.adam_v_out != nullptr) { A.x.adam_v_out[oij] = v2.x; A.x.adam_v_out[oji] = v2.y; }
           }
+        }
+        if (kTrace) {
+          trS = warp_sum(trS); trH = warp_sum(trH); trD = warp_sum(trD);
+          if (lane == 0) { s_tr[warp * 4 + 0] = trS; s_tr[warp * 4 + 1] = trH; s_tr[warp * 4 + 2] = 0.f; s_tr[warp * 4 + 3] = trD; }
         }
       }
       __syncthreads();
+      if (kTrace && tid == 0) {   // raw terms of epoch it-1 (trace_finalize_kernel assembles the columns)
+        float sS = 0.f, sH = 0.f, sD = 0.f;
+        for (int w = 0; w < nwarps; ++w) { sS += s_tr[w * 4]; sH += s_tr[w * 4 + 1]; sD += s_tr[w * 4 + 3]; }
+        float* row = A.x.trace + ((int64_t)task_id * A.x.epochs + (it - 1)) * GX_TRACE_COLS;
+        const float* const tr = s_tr + (NT / 32) * 4;
+        row[0] = sS; row[1] = tr[0]; row[2] = sH; row[3] = 0.f; row[4] = sD; row[5] = tr[2]; row[6] = 0.f; row[7] = tr[1];
+      }
     }
-    if (A.out_feat != nullptr)
-      for (int f = tid; f < d; f += nthreads) A.out_feat[(int64_t)task_id * d + f] = sF[f];
     __syncthreads();
   }
   (void)kNone;
@@ -431,14 +495,16 @@ cudaError_t gx_launch_explain_graphs(const GxExplainLaunch& cfg, const GxGraphBa
   args.order = cfg.order; args.ntasks = cfg.ntasks; args.counter = cfg.counter;
   args.pws = cfg.pws; args.pws_stride_words = cfg.pws_stride_words;
   args.gb = gb; args.m = m; args.hp = hp; args.plan = plan;
-  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat;
+  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.x = cfg.x;
+  const bool tr = cfg.x.trace != nullptr;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
     return cudaGetLastError();
   };
-  if (m.hid == 20 && m.emb == 20) return launch(explain_graph_kernel<20, 20, 128>);
-  if (m.hid == 32 && m.emb == 32) return launch(explain_graph_kernel<32, 32, 128>);   // widths <= 32, zero-padded
+  if (m.hid == 20 && m.emb == 20) return tr ? launch(explain_graph_kernel<20, 20, 128, true>) : launch(explain_graph_kernel<20, 20, 128, false>);
+  if (m.hid == 32 && m.emb == 32)   // widths <= 32, zero-padded
+    return tr ? launch(explain_graph_kernel<32, 32, 128, true>) : launch(explain_graph_kernel<32, 32, 128, false>);
   return cudaErrorInvalidValue;
 }

@@ -39,10 +39,12 @@ namespace {
 // task's epoch (profiles/r01f): written for a SHORT serial chain -- compile-time trip counts, clamped lane indices instead
 // of divergent `if (lane < ..)` blocks, one exp per class, the four 8-lane groups of the warp reduced with shuffles.
 // kWpShared only separates the two instantiations so that the pred_model pointer keeps its address space (LDS vs LDG).
-template <typename IdxT, int HID, int EMB, bool kWpShared>
+// kTrace: tr[0] = -log softmax[gt] (explain.py:750-753), tr[1] = softmax[gt]; trp (optional) receives the softmax row.
+template <typename IdxT, int HID, int EMB, bool kWpShared, bool kTrace>
 __device__ __forceinline__ void readout_phase(int lane, int C, int gt, const IdxT* irp, const IdxT* icol, const float* a,
                                               const float* Yh1, const float* Yh2, float* zs, const float* bs, const float* W3s,
-                                              const float* Wpp, const float* bpp, float* logit, float* dE, float* dZ3) {
+                                              const float* Wpp, const float* bpp, float* logit, float* dE, float* dZ3,
+                                              float* tr, float* trp) {
   constexpr int HS = HID, H4 = HID / 4, PD = 2 * HID + EMB;
   const int g = lane >> 3, q8 = lane & 7;
   // layer-3 aggregate of row 0: the four 8-lane groups walk its edges four apart, then sum across the groups
@@ -100,6 +102,10 @@ __device__ __forceinline__ void readout_phase(int lane, int C, int gt, const Idx
     const float mx = warp_max(v);
     const float ex = lane < C ? expf(v - mx) : 0.f;
     const float se = warp_sum(ex);
+    if (kTrace) {
+      if (lane == gt) { tr[0] = -((v - mx) - logf(se)); tr[1] = ex / se; }
+      if (trp != nullptr && lane < C) trp[lane] = ex / se;
+    }
     if (lane < C) logit[lane] = ex / se - (lane == gt ? 1.f : 0.f);
   } else {
     float mx = -INFINITY;
@@ -111,6 +117,12 @@ __device__ __forceinline__ void readout_phase(int lane, int C, int gt, const Idx
     for (int c = lane; c < C; c += 32) se += expf(logit[c] - mx);
     se = warp_sum(se);
     __syncwarp();
+    if (kTrace) {
+      if (lane == 0) { const float lg = logit[gt]; tr[0] = -((lg - mx) - logf(se)); tr[1] = expf(lg - mx) / se; }
+      if (trp != nullptr)
+        for (int c = lane; c < C; c += 32) trp[c] = expf(logit[c] - mx) / se;
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int c = lane; c < C; c += 32) logit[c] = expf(logit[c] - mx) / se - (c == gt ? 1.f : 0.f);
   }
@@ -132,10 +144,11 @@ __device__ __forceinline__ void readout_phase(int lane, int C, int gt, const Idx
   if (lane < HID) dZ3[lane] = dot_v4(zs, W3s + lane * EMB, EMB / 4);
 }
 
-template <typename IdxT, int HID, int EMB, int NT>
+template <typename IdxT, int HID, int EMB, int NT, bool kTrace>
 __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ int s_task;
+  __shared__ float s_tr[kTrace ? (NT / 32) * 4 + 4 : 1];   // trace: per-warp partial sums of the edge phase + (pred loss, p[gt], feat-size term)
   __shared__ GxLayout sL;
   __shared__ int s_long[3];  // number of long rows among [0,n2), among [0,n1), and rows with a long < n1 prefix
   static_assert(HID % 4 == 0 && EMB % 4 == 0, "hidden widths must be multiples of 4");
@@ -210,9 +223,22 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     for (int e = tid; e < e1; e += nthreads) icol[e] = (IdxT)A.plan.icol[edge_off + e];
     for (int i = tid; i <= n2; i += nthreads) irp[i] = (IdxT)A.plan.irowptr[rp_off + i];
     for (int i = tid; i < n; i += nthreads) yv[i] = (float)__ldg(A.g.pred_label + lo2gid[i]);
+    const bool resume = hp.init == GX_INIT_STATE && !hp.mode;   // optimiser state supplied by the caller (gx_explain_io)
     for (int f = tid; f < dp; f += nthreads) {
       sF[f] = hp.mode ? 1.0f : 0.5f;  // sigmoid(0): feat_mask is initialised to 0 (explain.py:633-643); gradient baseline: unmasked features
       Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f;
+      if (resume && A.x.feat_state_in != nullptr && f < d) {
+        const float* fs = A.x.feat_state_in + (int64_t)task_id * 3 * d;
+        Fm[f] = fs[f]; mF[f] = fs[d + f]; vF[f] = fs[2 * d + f];
+        sF[f] = sigmoid_f(fs[f]);
+      }
+      if (hp.out_iter == 0 && !hp.mode && f < d) {   // num_epochs == 1: the state that goes out is the state that came in
+        if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sF[f];
+        if (A.x.feat_state_out != nullptr) {
+          float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
+          fo[f] = Fm[f]; fo[d + f] = mF[f]; fo[2 * d + f] = vF[f];
+        }
+      }
     }
     for (int idx = tid; idx < nwarps * dp; idx += nthreads) gFp[idx] = 0.f;
     const float m0_std = sqrtf(2.0f / (float)n);  // gain('relu') * sqrt(2/(n+n)) (explain.py:647-651)
@@ -226,24 +252,32 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       float Mi, Mj;
       if (hp.mode) {
         Mi = Mj = 0.f;
-      } else if (hp.init == GX_INIT_M0) {
-        Mi = __ldg(A.m0 + edge_off + oij);
-        Mj = __ldg(A.m0 + edge_off + oji);
-      } else {
+      } else if (hp.init == GX_INIT_PHILOX) {
         Mi = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oij);
         Mj = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oji);
+      } else {
+        Mi = __ldg(A.m0 + edge_off + oij);
+        Mj = __ldg(A.m0 + edge_off + oji);
+      }
+      float2 m2 = make_float2(0.f, 0.f), v2 = m2;
+      if (resume) {
+        m2 = make_float2(__ldg(A.x.adam_m_in + edge_off + oij), __ldg(A.x.adam_m_in + edge_off + oji));
+        v2 = make_float2(__ldg(A.x.adam_v_in + edge_off + oij), __ldg(A.x.adam_v_in + edge_off + oji));
       }
       MM[p] = make_float2(Mi, Mj);
-      mm[p] = make_float2(0.f, 0.f);
-      vv[p] = make_float2(0.f, 0.f);
+      mm[p] = m2;
+      vv[p] = v2;
       const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
       SS[p] = make_float2(Si, Sj);
       const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
       if (i < n2) a[pij] = a0;
       if (j < n2) a[pji] = a0;
-      if (hp.iters == 0) {
+      if (hp.out_iter == 0 && !hp.mode) {
         A.out_mask[edge_off + oij] = a0;
         A.out_mask[edge_off + oji] = a0;
+        if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[edge_off + oij] = Mi; A.x.mask_param_out[edge_off + oji] = Mj; }
+        if (A.x.adam_m_out != nullptr) { A.x.adam_m_out[edge_off + oij] = m2.x; A.x.adam_m_out[edge_off + oji] = m2.y; }
+        if (A.x.adam_v_out != nullptr) { A.x.adam_v_out[edge_off + oij] = v2.x; A.x.adam_v_out[edge_off + oji] = v2.y; }
       }
     }
     }
@@ -374,10 +408,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const a = base + sL.a; const float* const Yh1 = base + sL.Yh1; const float* const Yh2 = base + sL.Yh2;
         float* const zs = base + sL.zs; const float* const bs = base + sL.bs; const float* const W3s = base + sL.W3s;
         float* const logit = base + sL.logit; float* const dE = base + sL.dE; float* const dZ3 = base + sL.dZ3;
+        float* const tr = kTrace ? s_tr + (NT / 32) * 4 : nullptr;
+        float* const trp = (kTrace && A.x.trace_pred != nullptr) ? A.x.trace_pred + ((int64_t)task_id * A.x.epochs + (it - 1)) * C : nullptr;
         if (C * (PD + 1) <= GX_WP_SMEM_MAX)   // pred_model.weight (C, 2h+e) + bias staged in shared memory
-          readout_phase<IdxT, HID, EMB, true>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, base + sL.Wp, base + sL.Wp + C * PD, logit, dE, dZ3);
+          readout_phase<IdxT, HID, EMB, true, kTrace>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, base + sL.Wp, base + sL.Wp + C * PD, logit, dE, dZ3, tr, trp);
         else
-          readout_phase<IdxT, HID, EMB, false>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, m.Wp, m.bp, logit, dE, dZ3);
+          readout_phase<IdxT, HID, EMB, false, kTrace>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, m.Wp, m.bp, logit, dE, dZ3, tr, trp);
+        if (kTrace) {   // feat_size_loss = coeff * mean(sigmoid(feat_mask)) with the mask this epoch's forward used (explain.py:763-766)
+          const float* const sF = base + sL.sF;
+          float fs = 0.f;
+          for (int f = lane; f < d; f += 32) fs += sF[f];
+          fs = warp_sum(fs);
+          if (lane == 0) tr[2] = hp.c_feat_size * fs / (float)d;
+        }
       }
       __syncthreads();
       GX_MARK(tS)
@@ -510,7 +553,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float* const a = base + sL.a;
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
-        const bool last = (it == hp.iters);
+        const bool last = (it == hp.out_iter);   // the mask built after this update is the one the reference returns
         // feature mask: dL/dF = sF(1-sF) (sum_i dZ1[i] U[i] + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
         // (done by the LAST warps of the CTA: the first ones carry the most pair work below, and a warp whose first lanes run this
         //  serial update would hold back its 32 pairs)
@@ -525,8 +568,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           vf = vf * hp.b2 + hp.one_minus_b2 * g * g;
           Fv = Fv - step * (mf / (sqrtf(vf) / bc2s + hp.eps));
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
-          sF[f] = sigmoid_f(Fv);
+          const float sn = sigmoid_f(Fv);
+          sF[f] = sn;
+          if (last) {
+            if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sn;
+            if (A.x.feat_state_out != nullptr) {
+              float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
+              fo[f] = Fv; fo[d + f] = mf; fo[2 * d + f] = vf;
+            }
+          }
         }
+        float trS = 0.f, trH = 0.f, trL = 0.f, trD = 0.f;   // trace: this thread's share of sum S, sum H(S), sum a (y_i-y_j)^2, sum 2a'
         if (hp.mode) {
           // gradient baseline (explain.py:125-133): mask_ij = sigmoid(|dL/dA_ij| + |dL/dA_ji|) on the edges, no regulariser, no update
           for (int p = tid; p < np; p += nthreads) {
@@ -550,6 +602,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           const int i = pi[p], j = pj[p];
           const float yd = yv[i] - yv[j];
           float Gd = lap_over_nn * yd * yd;  // d/dA_ij + d/dA_ji of y^T (D - A) y / n^2 (explain.py:780-793)
+          if (kTrace) {
+            trS += Sv.x + Sv.y; trH += bern_entropy(Sv.x) + bern_entropy(Sv.y);
+            trL += 0.5f * (Sv.x + Sv.y) * yd * yd;
+          }
           if (i < n2) Gd += dot_v4(dZ1s + i * dp, X + j * dp, D4);
           if (j < n2) Gd += dot_v4(dZ1s + j * dp, X + i * dp, D4);
           if (i < n1) Gd += dot_relu_v4(dZ2 + i * HS, Yh1 + j * HS, H4);
@@ -568,16 +624,32 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
+          if (kTrace) trD += 2.0f * an;
           const IdxT pa = ppij[p], pb = ppji[p];
           if (pa != kNone) a[pa] = an;
           if (pb != kNone) a[pb] = an;
           if (last) {
-            A.out_mask[edge_off + A.plan.pair_oij[pair_off + p]] = an;
-            A.out_mask[edge_off + A.plan.pair_oji[pair_off + p]] = an;
+            const int64_t oij = edge_off + A.plan.pair_oij[pair_off + p], oji = edge_off + A.plan.pair_oji[pair_off + p];
+            A.out_mask[oij] = an;
+            A.out_mask[oji] = an;
+            if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[oij] = Mv.x; A.x.mask_param_out[oji] = Mv.y; }
+            if (A.x.adam_m_out != nullptr) { A.x.adam_m_out[oij] = m2.x; A.x.adam_m_out[oji] = m2.y; }
+            if (A.x.adam_v_out != nullptr) { A.x.adam_v_out[oij] = v2.x; A.x.adam_v_out[oji] = v2.y; }
           }
+        }
+        if (kTrace) {
+          trS = warp_sum(trS); trH = warp_sum(trH); trL = warp_sum(trL); trD = warp_sum(trD);
+          if (lane == 0) { s_tr[warp * 4 + 0] = trS; s_tr[warp * 4 + 1] = trH; s_tr[warp * 4 + 2] = trL; s_tr[warp * 4 + 3] = trD; }
         }
       }
       __syncthreads();
+      if (kTrace && tid == 0) {   // raw terms of epoch it-1 over the INNER pairs; trace_finalize_kernel adds the outer pairs and assembles the columns
+        float sS = 0.f, sH = 0.f, sLp = 0.f, sD = 0.f;
+        for (int w = 0; w < nwarps; ++w) { sS += s_tr[w * 4]; sH += s_tr[w * 4 + 1]; sLp += s_tr[w * 4 + 2]; sD += s_tr[w * 4 + 3]; }
+        float* row = A.x.trace + ((int64_t)task_id * A.x.epochs + (it - 1)) * GX_TRACE_COLS;
+        const float* const tr = s_tr + (NT / 32) * 4;
+        row[0] = sS; row[1] = tr[0]; row[2] = sH; row[3] = sLp; row[4] = sD; row[5] = tr[2]; row[6] = 0.f; row[7] = tr[1];
+      }
       GX_MARK(tP)
     }
     if (A.dbg != nullptr && tid == 0 && qi == 0) {
@@ -592,10 +664,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       unsigned long long* tl64 = reinterpret_cast<unsigned long long*>(A.dbg + (1 << 19) + 64);
       tl64[3 * task_id + 0] = t_start_ns; tl64[3 * task_id + 1] = t_end_ns; tl64[3 * task_id + 2] = ((unsigned long long)smid << 32) | (unsigned)nthreads;
     }
-    if (A.out_feat != nullptr) {
-      const float* const sF = base + sL.sF;
-      for (int f = tid; f < d; f += nthreads) A.out_feat[(int64_t)task_id * d + f] = sF[f];
-    }
     __syncthreads();
   }
 }
@@ -604,10 +672,15 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
 // Pairs between two outermost nodes (both endpoints outside every row the forward computes): their
 // masked-adjacency value never enters the GCN, so dL/dM is regulariser-only and the whole Adam
 // trajectory is a private scalar recurrence -- one thread per pair, state in registers, no barriers.
+// kTrace: one CTA per task additionally sums, per epoch, the pairs' shares of the size / entropy / Laplacian terms and of
+// the mask density into x.tr_outer (double atomics in shared memory: the order of the adds is not fixed, the sums agree to ~1e-16).
+template <bool kTrace>
 __global__ void __launch_bounds__(256)
 outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays plan, int count,
-                   const float* __restrict__ m0, float* __restrict__ out_mask) {
+                   const float* __restrict__ m0, float* __restrict__ out_mask, const GxExtra x) {
+  extern __shared__ double s_acc[];   // kTrace: [iters][4]
   const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
+  const bool resume = hp.init == GX_INIT_STATE && !hp.mode;
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
     const GxTask* __restrict__ Tp = plan.tasks + t;
     const int np = Tp->npairs, np_in = Tp->npairs_in, n = Tp->n;
@@ -616,28 +689,47 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
     const float nn = (float)n * (float)n;
     const float ent_over_nn = hp.c_ent / nn, lap_over_nn = hp.c_lap / nn;
     const float m0_std = sqrtf(2.0f / (float)n);
+    if (kTrace) {
+      for (int k = threadIdx.x; k < hp.iters * 4; k += blockDim.x) s_acc[k] = 0.0;
+      __syncthreads();
+    }
     for (int p = np_in + threadIdx.x; p < np; p += blockDim.x) {
       const int i = plan.pair_i[pair_off + p], j = plan.pair_j[pair_off + p];
-      const int oij = plan.pair_oij[pair_off + p], oji = plan.pair_oji[pair_off + p];
+      const int64_t oij = edge_off + plan.pair_oij[pair_off + p], oji = edge_off + plan.pair_oji[pair_off + p];
       if (hp.mode) {   // gradient baseline: no gradient reaches an edge outside the receptive field -> sigmoid(0)
-        out_mask[edge_off + oij] = 0.5f;
-        out_mask[edge_off + oji] = 0.5f;
+        out_mask[oij] = 0.5f;
+        out_mask[oji] = 0.5f;
         continue;
       }
       float Mi, Mj;
-      if (hp.init == GX_INIT_M0) {
-        Mi = __ldg(m0 + edge_off + oij);
-        Mj = __ldg(m0 + edge_off + oji);
+      if (hp.init == GX_INIT_PHILOX) {
+        Mi = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)(oij - edge_off));
+        Mj = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)(oji - edge_off));
       } else {
-        Mi = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oij);
-        Mj = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oji);
+        Mi = __ldg(m0 + oij);
+        Mj = __ldg(m0 + oji);
       }
+      float mi = 0.f, mj = 0.f, vi = 0.f, vj = 0.f;
+      if (resume) { mi = __ldg(x.adam_m_in + oij); mj = __ldg(x.adam_m_in + oji); vi = __ldg(x.adam_v_in + oij); vj = __ldg(x.adam_v_in + oji); }
       const float yd = (float)__ldg(g.pred_label + lo2gid[i]) - (float)__ldg(g.pred_label + lo2gid[j]);
       const float Gd = 0.5f * (lap_over_nn * yd * yd);
       float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
-      float mi = 0.f, mj = 0.f, vi = 0.f, vj = 0.f;
+      auto emit = [&]() {
+        const float an = 0.5f * (Si + Sj);
+        out_mask[oij] = an;
+        out_mask[oji] = an;
+        if (x.mask_param_out != nullptr) { x.mask_param_out[oij] = Mi; x.mask_param_out[oji] = Mj; }
+        if (x.adam_m_out != nullptr) { x.adam_m_out[oij] = mi; x.adam_m_out[oji] = mj; }
+        if (x.adam_v_out != nullptr) { x.adam_v_out[oij] = vi; x.adam_v_out[oji] = vj; }
+      };
+      if (hp.out_iter == 0) emit();
       for (int it = 1; it <= hp.iters; ++it) {
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
+        if (kTrace) {
+          atomicAdd(&s_acc[(it - 1) * 4 + 0], (double)(Si + Sj));
+          atomicAdd(&s_acc[(it - 1) * 4 + 1], (double)(bern_entropy(Si) + bern_entropy(Sj)));
+          atomicAdd(&s_acc[(it - 1) * 4 + 2], (double)(0.5f * (Si + Sj) * yd * yd));
+        }
         const float gi = Si * (1.f - Si) * (Gd + hp.c_size - ent_over_nn * Mi);
         const float gj = Sj * (1.f - Sj) * (Gd + hp.c_size - ent_over_nn * Mj);
         mi = mi + (gi - mi) * hp.one_minus_b1;
@@ -649,21 +741,30 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
         Mj = Mj - adam_delta_fast(mj, vj, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
         Si = sigmoid_fast(Mi, ieee);
         Sj = sigmoid_fast(Mj, ieee);
+        if (kTrace) atomicAdd(&s_acc[(it - 1) * 4 + 3], (double)(Si + Sj));   // 2 a' = S_i + S_j after the step (mask_density, explain.py:148)
+        if (it == hp.out_iter) emit();
       }
-      const float an = 0.5f * (Si + Sj);
-      out_mask[edge_off + oij] = an;
-      out_mask[edge_off + oji] = an;
+    }
+    if (kTrace) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < hp.iters * 4; k += blockDim.x) x.tr_outer[(int64_t)t * x.epochs * 4 + k] = s_acc[k];
+      __syncthreads();
     }
   }
 }
 
-template <typename IdxT, int HID, int EMB, int NT>
-cudaError_t launch_one(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  auto kern = explain_node_kernel<IdxT, HID, EMB, NT>;
+template <typename IdxT, int HID, int EMB, int NT, bool kTrace>
+cudaError_t launch_one_t(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
+  auto kern = explain_node_kernel<IdxT, HID, EMB, NT, kTrace>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
   if (e != cudaSuccess) return e;
   kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
   return cudaGetLastError();
+}
+template <typename IdxT, int HID, int EMB, int NT>
+cudaError_t launch_one(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
+  if (args.x.trace != nullptr) return launch_one_t<IdxT, HID, EMB, NT, true>(cfg, args, s);
+  return launch_one_t<IdxT, HID, EMB, NT, false>(cfg, args, s);
 }
 
 template <int HID, int EMB>
@@ -678,8 +779,15 @@ cudaError_t launch_dims(const GxExplainLaunch& cfg, const ExplainArgs& args, cud
 int gx_explain_max_smem() { return 227 * 1024; }
 
 cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
-                                  const float* m0, float* out_mask, cudaStream_t s) {
-  outer_pairs_kernel<<<count < 148 * 8 ? count : 148 * 8, 256, 0, s>>>(hp, g, plan, count, m0, out_mask);
+                                  const float* m0, float* out_mask, const GxExtra& x, cudaStream_t s) {
+  const int grid = count < 148 * 8 ? count : 148 * 8;
+  if (x.trace != nullptr) {
+    const size_t smem = (size_t)(hp.iters > 0 ? hp.iters : 1) * 4 * sizeof(double);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;   // > 1536 epochs with a trace: refused by gx_explain_nodes_ex
+    outer_pairs_kernel<true><<<grid, 256, smem, s>>>(hp, g, plan, count, m0, out_mask, x);
+  } else {
+    outer_pairs_kernel<false><<<grid, 256, 0, s>>>(hp, g, plan, count, m0, out_mask, x);
+  }
   return cudaGetLastError();
 }
 
@@ -691,7 +799,7 @@ cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, c
   args.gws = cfg.gws; args.gws_stride_words = cfg.gws_stride_words;
   args.pws = cfg.pws; args.pws_stride_words = cfg.pws_stride_words;
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
-  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg;
+  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg; args.x = cfg.x;
   if (m.hid == 20 && m.emb == 20) return launch_dims<20, 20>(cfg, args, s);
   if (m.hid == 32 && m.emb == 32) return launch_dims<32, 32>(cfg, args, s);   // any width <= 32, zero-padded by gx_set_model
   return cudaErrorInvalidValue;

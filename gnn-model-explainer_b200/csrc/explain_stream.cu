@@ -320,10 +320,11 @@ __device__ __forceinline__ int prefix_below(const int32_t* __restrict__ icol, in
   return lo - r0;
 }
 
-template <int HID, int EMB, int NT>
+template <int HID, int EMB, int NT, bool kTrace>
 __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_task;
+  __shared__ float s_tr[kTrace ? (NT / 32) * 4 + 4 : 1];   // trace: per-warp partial sums of the edge phase + (pred loss, p[gt], feat-size term)
   __shared__ long long s_ph[9];   // debug: per-phase cycle sums of the CTA's first task + last stamp
   static_assert((HID == 20 || HID == 32) && EMB % 4 == 0 && EMB <= 32, "hidden width 20 or 32 (others are zero-padded to 32 by gx_set_model)");
   constexpr int HS = HID, H4 = HID / 4, PD = 2 * HID + EMB;
@@ -397,7 +398,22 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
     const float lap_over_nn = hp.c_lap / nn;
 
     // ------------------------------------------------------------------ per-task state
-    for (int f = tid; f < dp; f += NT) { sF[f] = hp.mode ? 1.0f : 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f; }  // feat_mask = 0 (explain.py:633-643)
+    const bool resume = hp.init == GX_INIT_STATE && !hp.mode;   // optimiser state supplied by the caller (gx_explain_io)
+    for (int f = tid; f < dp; f += NT) {
+      sF[f] = hp.mode ? 1.0f : 0.5f; Fm[f] = 0.f; mF[f] = 0.f; vF[f] = 0.f;   // feat_mask = 0 (explain.py:633-643)
+      if (resume && A.x.feat_state_in != nullptr && f < d) {
+        const float* fs = A.x.feat_state_in + (int64_t)task_id * 3 * d;
+        Fm[f] = fs[f]; mF[f] = fs[d + f]; vF[f] = fs[2 * d + f];
+        sF[f] = sigmoid_f(fs[f]);
+      }
+      if (hp.out_iter == 0 && !hp.mode && f < d) {
+        if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sF[f];
+        if (A.x.feat_state_out != nullptr) {
+          float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
+          fo[f] = Fm[f]; fo[d + f] = mF[f]; fo[2 * d + f] = vF[f];
+        }
+      }
+    }
     {
       const float m0_std = sqrtf(2.0f / (float)n);  // gain('relu') * sqrt(2/(n+n)) (explain.py:647-651)
       for (int p = tid; p < np; p += NT) {
@@ -405,16 +421,21 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         float Mi, Mj;
         if (hp.mode) {
           Mi = Mj = 0.f;
-        } else if (hp.init == GX_INIT_M0) {
-          Mi = __ldg(A.m0 + edge_off + oij);
-          Mj = __ldg(A.m0 + edge_off + oji);
-        } else {
+        } else if (hp.init == GX_INIT_PHILOX) {
           Mi = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oij);
           Mj = 1.0f + m0_std * philox_normal(hp.seed, (uint32_t)Tp->node, (uint32_t)oji);
+        } else {
+          Mi = __ldg(A.m0 + edge_off + oij);
+          Mj = __ldg(A.m0 + edge_off + oji);
+        }
+        float2 m2 = make_float2(0.f, 0.f), v2 = m2;
+        if (resume) {
+          m2 = make_float2(__ldg(A.x.adam_m_in + edge_off + oij), __ldg(A.x.adam_m_in + edge_off + oji));
+          v2 = make_float2(__ldg(A.x.adam_v_in + edge_off + oij), __ldg(A.x.adam_v_in + edge_off + oji));
         }
         MM[p] = make_float2(Mi, Mj);
-        mm[p] = make_float2(0.f, 0.f);
-        vv[p] = make_float2(0.f, 0.f);
+        mm[p] = m2;
+        vv[p] = v2;
         const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
         SS[p] = make_float2(Si, Sj);
         const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
@@ -424,9 +445,12 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
           const float yd = (float)__ldg(A.g.pred_label + lo2gid[pi[p]]) - (float)__ldg(A.g.pred_label + lo2gid[pj[p]]);
           lapg[p] = lap_over_nn * yd * yd;
         }
-        if (hp.iters == 0) {
+        if (hp.out_iter == 0 && !hp.mode) {
           A.out_mask[edge_off + oij] = a0;
           A.out_mask[edge_off + oji] = a0;
+          if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[edge_off + oij] = Mi; A.x.mask_param_out[edge_off + oji] = Mj; }
+          if (A.x.adam_m_out != nullptr) { A.x.adam_m_out[edge_off + oij] = m2.x; A.x.adam_m_out[edge_off + oji] = m2.y; }
+          if (A.x.adam_v_out != nullptr) { A.x.adam_v_out[edge_off + oij] = v2.x; A.x.adam_v_out[edge_off + oji] = v2.y; }
         }
       }
     }
@@ -539,6 +563,19 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         for (int c = lane; c < C; c += 32) se += expf(logit[c] - mx);
         se = warp_sum(se);
         __syncwarp();
+        if (kTrace) {
+          float* const tr = s_tr + (NT / 32) * 4;
+          if (lane == 0) { const float lg = logit[gt]; tr[0] = -((lg - mx) - logf(se)); tr[1] = expf(lg - mx) / se; }
+          if (A.x.trace_pred != nullptr) {
+            float* trp = A.x.trace_pred + ((int64_t)task_id * A.x.epochs + (it - 1)) * C;
+            for (int c = lane; c < C; c += 32) trp[c] = expf(logit[c] - mx) / se;
+          }
+          float fs = 0.f;   // feat_size_loss = coeff * mean(sigmoid(feat_mask)) (explain.py:763-766)
+          for (int f = lane; f < d; f += 32) fs += sF[f];
+          fs = warp_sum(fs);
+          if (lane == 0) tr[2] = hp.c_feat_size * fs / (float)d;
+          __syncwarp();
+        }
         for (int c = lane; c < C; c += 32)
           logit[c] = expf(logit[c] - mx) / se - (c == gt ? 1.f : 0.f);  // dL/dlogits = p - onehot(gt) (explain.py:750-753)
         __syncwarp();
@@ -650,7 +687,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
       {
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
-        const bool last = (it == hp.iters);
+        const bool last = (it == hp.out_iter);   // the mask built after this update is the one the reference returns
         // feature mask: dL/dF = sF(1-sF) (sum_j X_j (.) dX'_j + feat_size/d) ; Adam (explain.py:766, train_utils.py:10)
         for (int f = tid; f < d && !hp.mode; f += NT) {
           float gsum = 0.f;
@@ -662,8 +699,17 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
           vf = vf * hp.b2 + hp.one_minus_b2 * g * g;
           Fv = Fv - step * (mf / (sqrtf(vf) / bc2s + hp.eps));
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
-          sF[f] = sigmoid_f(Fv);
+          const float sn = sigmoid_f(Fv);
+          sF[f] = sn;
+          if (last) {
+            if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sn;
+            if (A.x.feat_state_out != nullptr) {
+              float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
+              fo[f] = Fv; fo[d + f] = mf; fo[2 * d + f] = vf;
+            }
+          }
         }
+        float trS = 0.f, trH = 0.f, trL = 0.f, trD = 0.f;   // trace: this thread's share of sum S, sum H(S), sum a (y_i-y_j)^2, sum 2a'
         // The layer-1 dots <dY1[i], P[j]> and <dY1[j], P[i]> were taken in B0 while the gathered rows were staged (gE);
         // only the few pairs touching rows < n1 (listed first) carry layer-2/3 terms.
         if (hp.mode) {
@@ -693,6 +739,10 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
           Gd *= 0.5f;  // sym_mask = (S + S^T)/2 (explain.py:671)
           float2 Mv = MM[p];
           const float2 Sv = SS[p];
+          if (kTrace) {
+            trS += Sv.x + Sv.y; trH += bern_entropy(Sv.x) + bern_entropy(Sv.y);
+            if (lap_over_nn > 0.f) trL += 0.5f * (Sv.x + Sv.y) * (lapg[p] / lap_over_nn);   // lapg = c_lap/n^2 (y_i-y_j)^2
+          }
           // size: coeff*sum(S) ; entropy: mean over n^2 of H(S), dH/dM = -M S(1-S) (explain.py:755-770)
           const float gi = Sv.x * (1.f - Sv.x) * (Gd + hp.c_size - ent_over_nn * Mv.x);
           const float gj = Sv.y * (1.f - Sv.y) * (Gd + hp.c_size - ent_over_nn * Mv.y);
@@ -706,15 +756,31 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
           const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);
+          if (kTrace) trD += 2.0f * an;
           a[sij] = an;
           a[sji] = an;
           if (last) {
-            A.out_mask[edge_off + poij[p]] = an;
-            A.out_mask[edge_off + poji[p]] = an;
+            const int64_t oij = edge_off + poij[p], oji = edge_off + poji[p];
+            A.out_mask[oij] = an;
+            A.out_mask[oji] = an;
+            if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[oij] = Mv.x; A.x.mask_param_out[oji] = Mv.y; }
+            if (A.x.adam_m_out != nullptr) { A.x.adam_m_out[oij] = m2.x; A.x.adam_m_out[oji] = m2.y; }
+            if (A.x.adam_v_out != nullptr) { A.x.adam_v_out[oij] = v2.x; A.x.adam_v_out[oji] = v2.y; }
           }
+        }
+        if (kTrace) {
+          trS = warp_sum(trS); trH = warp_sum(trH); trL = warp_sum(trL); trD = warp_sum(trD);
+          if (lane == 0) { s_tr[warp * 4 + 0] = trS; s_tr[warp * 4 + 1] = trH; s_tr[warp * 4 + 2] = trL; s_tr[warp * 4 + 3] = trD; }
         }
       }
       __syncthreads();
+      if (kTrace && tid == 0) {   // raw terms of epoch it-1 over the INNER pairs (trace_finalize_kernel assembles the columns)
+        float sS = 0.f, sH = 0.f, sLp = 0.f, sD = 0.f;
+        for (int w = 0; w < nwarps; ++w) { sS += s_tr[w * 4]; sH += s_tr[w * 4 + 1]; sLp += s_tr[w * 4 + 2]; sD += s_tr[w * 4 + 3]; }
+        float* row = A.x.trace + ((int64_t)task_id * A.x.epochs + (it - 1)) * GX_TRACE_COLS;
+        const float* const tr = s_tr + (NT / 32) * 4;
+        row[0] = sS; row[1] = tr[0]; row[2] = sH; row[3] = sLp; row[4] = sD; row[5] = tr[2]; row[6] = 0.f; row[7] = tr[1];
+      }
       GXS_MARK(7)
     }
     if (timed && tid == 0) {
@@ -722,14 +788,12 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
       for (int k = 0; k < 8; ++k) o[k] = (float)s_ph[k];
       o[8] = (float)n; o[9] = (float)n1; o[10] = (float)n2; o[11] = (float)np; o[12] = (float)e_d; o[13] = (float)NT;
     }
-    if (A.out_feat != nullptr)
-      for (int f = tid; f < d; f += NT) A.out_feat[(int64_t)task_id * d + f] = sF[f];
   }
 }
 
-template <int HID, int EMB, int NT>
+template <int HID, int EMB, int NT, bool kTrace>
 cudaError_t launch_stream_nt(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  auto kern = explain_stream_kernel<HID, EMB, NT>;
+  auto kern = explain_stream_kernel<HID, EMB, NT, kTrace>;
   const StreamSmem S = stream_smem(gx_round_up(args.m.d, 4), HID, EMB, args.m.C, NT / 32);
   const int bytes = S.total * 4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -739,7 +803,8 @@ cudaError_t launch_stream_nt(const GxExplainLaunch& cfg, const ExplainArgs& args
 }
 template <int HID, int EMB>
 cudaError_t launch_stream(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  return launch_stream_nt<HID, EMB, GX_STREAM_THREADS>(cfg, args, s);
+  if (args.x.trace != nullptr) return launch_stream_nt<HID, EMB, GX_STREAM_THREADS, true>(cfg, args, s);
+  return launch_stream_nt<HID, EMB, GX_STREAM_THREADS, false>(cfg, args, s);
 }
 
 }  // namespace
@@ -752,7 +817,7 @@ cudaError_t gx_launch_explain_stream(const GxExplainLaunch& cfg, const GxGraphDe
   args.gws = cfg.gws; args.gws_stride_words = cfg.gws_stride_words;
   args.pws = cfg.pws; args.pws_stride_words = cfg.pws_stride_words;
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
-  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg;
+  args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg; args.x = cfg.x;
   if (m.hid == 20 && m.emb == 20) return launch_stream<20, 20>(cfg, args, s);
   if (m.hid == 32 && m.emb == 32) return launch_stream<32, 32>(cfg, args, s);   // any width <= 32, zero-padded by gx_set_model
   return cudaErrorInvalidValue;

@@ -73,10 +73,11 @@ struct GxModelDev {
 };
 
 struct GxHparamsDev {
-  int32_t iters;  // num_epochs - 1 observed updates
+  int32_t iters;     // forward/backward/update iterations executed: num_epochs - 1 (the last epoch's backward is unobservable), num_epochs when a trace is requested
+  int32_t out_iter;  // the mask (and the optimiser state) is emitted after this many updates: num_epochs - 1
   float one_minus_b1, b2, one_minus_b2, eps;
   float c_size, c_feat_size, c_ent, c_lap;
-  const float2* adam_tab;  // [iters] (step_size_t = lr/(1-b1^t), sqrt(1-b2^t)), computed in double on the host
+  const float2* adam_tab;  // [iters] (step_size_t = lr/(1-b1^t), sqrt(1-b2^t)) for t = start_step + 1 .., computed in double on the host
   int32_t init;
   int32_t flags;  // GX_HP_* bits
   int32_t mode;   // 0: mask optimisation; 1: gradient baseline (explain(model="grad")): one forward/backward on the unmasked subgraph
@@ -84,6 +85,16 @@ struct GxHparamsDev {
 };
 
 #define GX_HP_IEEE_EDGE 1  // edge phase with IEEE exp/div/sqrt instead of the hardware approximations (test knob)
+
+// Optional trace / optimiser-state buffers of gx_explain_io (device pointers, nullptr = unused).
+struct GxExtra {
+  float* trace;        // [count][epochs][GX_TRACE_COLS]: the explainer kernels write raw per-epoch terms, trace_finalize_kernel assembles the columns
+  float* trace_pred;   // [count][epochs][C]
+  double* tr_outer;    // [count][epochs][4]: (sum S, sum H(S), sum a (y_i-y_j)^2, sum 2a after the step) over the outer pairs
+  int32_t epochs;      // trace rows per task (= num_epochs of the call)
+  const float* adam_m_in; const float* adam_v_in; const float* feat_state_in;
+  float* mask_param_out; float* adam_m_out; float* adam_v_out; float* feat_state_out;
+};
 
 // ---------------------------------------------------------------------------------------------
 // Shared-memory layout of one task in the explainer kernel.  Computed identically on host
@@ -260,6 +271,7 @@ struct GxExplainLaunch {
   float* pws;            // per-CTA pair-state slab: 8 floats per inner pair (M,m,v,S of both directions)
   int64_t pws_stride_words;
   float* dbg;            // debug dump buffer (device) or NULL
+  GxExtra x;             // optional trace / optimiser-state buffers
 };
 cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                               const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
@@ -281,6 +293,10 @@ cudaError_t gx_launch_explain_graphs(const GxExplainLaunch& cfg, const GxGraphBa
                                      const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0, float* out_mask,
                                      float* out_feat, cudaStream_t s);
 cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
-                                  const float* m0, float* out_mask, cudaStream_t s);
+                                  const float* m0, float* out_mask, const GxExtra& x, cudaStream_t s);
+// trace.cu
+cudaError_t gx_launch_trace_finalize(const GxHparamsDev& hp, const GxPlanArrays& plan, int count, const GxExtra& x, cudaStream_t s);
+cudaError_t gx_launch_offedge(const GxHparamsDev& hp, const GxPlanArrays& plan, int count, int epochs, const int64_t* dense_off,
+                              const float* m0_dense, double* out, cudaStream_t s);
 cudaError_t gx_launch_densify(const GxPlanArrays& plan, int count, const int64_t* dense_off,
                               const float* edge_mask, double* out, cudaStream_t s);

@@ -8,7 +8,10 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgnnx.so")
 
 GX_OK = 0
 GX_HOST, GX_DEVICE = 0, 1
-GX_INIT_M0, GX_INIT_PHILOX = 0, 1
+GX_INIT_M0, GX_INIT_PHILOX, GX_INIT_STATE = 0, 1, 2
+GX_VERSION = 200
+GX_TRACE_COLS = 8
+TR_LOSS_EDGES, TR_PRED, TR_SIZE, TR_ENT, TR_LAP, TR_FEAT, TR_DENSITY, TR_PGT = range(8)
 GX_MODEL_BN = 1
 
 EXPORTS = [
@@ -16,6 +19,8 @@ EXPORTS = [
     "gx_sync", "gx_set_model", "gx_set_graph_csr", "gx_neighborhood_rows", "gx_plan_nodes",
     "gx_plan_fetch", "gx_explain_nodes", "gx_densify", "gx_launch_count", "gx_last_explain_ms",
     "gx_set_graph_batch_csr", "gx_plan_graphs", "gx_explain_graphs", "gx_grad_nodes",
+    "gx_explain_nodes_ex", "gx_explain_graphs_ex", "gx_offedge_regularisers",
+    "gx_debug_force_stream", "gx_debug_ieee_edge", "gx_debug_set_dump",
 ]
 
 
@@ -28,7 +33,15 @@ class GxHparams(C.Structure):
     _fields_ = [("num_epochs", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("coef_size", C.c_float), ("coef_feat_size", C.c_float),
                 ("coef_ent", C.c_float), ("coef_lap", C.c_float), ("mask_act", C.c_int32),
-                ("mask_bias", C.c_int32), ("init", C.c_int32), ("seed", C.c_uint64)]
+                ("mask_bias", C.c_int32), ("init", C.c_int32), ("seed", C.c_uint64),
+                ("start_step", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GxExplainIo(C.Structure):
+    """include/gnnx.h gx_explain_io: optional trace / optimiser-state buffers (all void* here; 0 = unused)."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "m0_edges", "edge_mask", "feat_mask", "trace", "trace_pred", "adam_m_in", "adam_v_in", "feat_state_in",
+        "mask_param_out", "adam_m_out", "adam_v_out", "feat_state_out")]
 
 
 class GnnxError(RuntimeError):
@@ -68,11 +81,20 @@ def lib():
     L.gx_set_graph_batch_csr.argtypes = [vp, C.c_int32, C.c_int32, i32p, i32p, f32p, C.c_int32, i32p]
     L.gx_plan_graphs.argtypes = [vp, i32p, C.c_int32, i64p, C.POINTER(C.c_int64)]
     L.gx_explain_graphs.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, f32p, f32p]
+    L.gx_explain_nodes_ex.argtypes = [vp, C.POINTER(GxHparams), C.c_int, C.POINTER(GxExplainIo)]
+    L.gx_explain_graphs_ex.argtypes = [vp, C.POINTER(GxHparams), C.c_int, C.POINTER(GxExplainIo)]
+    L.gx_offedge_regularisers.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, vp]
+    L.gx_grad_nodes.argtypes = [vp, C.c_int, f32p]
+    L.gx_debug_force_stream.argtypes = [vp, C.c_int]
+    L.gx_debug_ieee_edge.argtypes = [vp, C.c_int]
+    L.gx_debug_set_dump.argtypes = [vp, vp]
     L.gx_launch_count.argtypes = [vp]
     L.gx_launch_count.restype = C.c_int64
     L.gx_last_explain_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here means the library does not match include/gnnx.h
+    if L.gx_version() != GX_VERSION:
+        raise ImportError("libgnnx.so is version %d, this binding expects %d -- rebuild (python __graft_entry__.py)" % (L.gx_version(), GX_VERSION))
     _lib = L
     return L
 

@@ -91,11 +91,30 @@ class Engine:
         _abi.check(self._lib.gx_sync(self._h))
 
     def set_model(self, weights, num_layers=3, bn=False):
-        """weights: dict W1,b1,W2,b2,W3,b3,Wp,bp (numpy; b* may be None)."""
+        """weights: dict W1,b1,W2,b2,W3,b3,Wp,bp (numpy; b* may be None).  Shapes are checked here: the C ABI takes bare
+        pointers, so a checkpoint whose layers do not chain (or a concat=False / MLP prediction head) must not reach it."""
         Ws = [_f32c(weights["W%d" % (l + 1)]) for l in range(num_layers)]
         bs = [None if weights.get("b%d" % (l + 1)) is None else _f32c(weights["b%d" % (l + 1)])
               for l in range(num_layers)]
         Wp, bp = _f32c(weights["Wp"]), _f32c(weights["bp"])
+        if any(w.ndim != 2 for w in Ws) or Wp.ndim != 2 or bp.ndim != 1:
+            raise ValueError("conv weights must be 2-D (in,out), pred_model.weight (C, sum of layer widths), pred_model.bias (C,)")
+        hid = Ws[0].shape[1]
+        for l in range(num_layers):
+            want_in = Ws[0].shape[0] if l == 0 else Ws[l - 1].shape[1]
+            if Ws[l].shape[0] != want_in:
+                raise ValueError("layer %d weight is %s, expected %d input features" % (l + 1, Ws[l].shape, want_in))
+            if 0 < l < num_layers - 1 and Ws[l].shape[1] != hid:
+                raise ValueError("hidden layers must share one width (models.py:193-220): layer %d is %s" % (l + 1, Ws[l].shape))
+            if bs[l] is not None and bs[l].shape != (Ws[l].shape[1],):
+                raise ValueError("layer %d bias is %s, expected (%d,)" % (l + 1, bs[l].shape, Ws[l].shape[1]))
+        pd = sum(w.shape[1] for w in Ws)
+        if Wp.shape[1] != pd:
+            if Wp.shape[1] == Ws[-1].shape[1]:
+                raise NotImplementedError("concat=False models (pred_model over the last layer only, models.py:113-116) are not built")
+            raise ValueError("pred_model.weight is %s, expected (C, %d) = concat of the layer outputs" % (Wp.shape, pd))
+        if bp.shape != (Wp.shape[0],):
+            raise ValueError("pred_model.bias is %s, expected (%d,)" % (bp.shape, Wp.shape[0]))
         dims = _abi.GxModelDims(Ws[0].shape[0], Ws[0].shape[1], Ws[-1].shape[1], Wp.shape[0], num_layers,
                                 _abi.GX_MODEL_BN if bn else 0)
         wp = (C.c_void_p * num_layers)(*[w.ctypes.data for w in Ws])
@@ -203,9 +222,34 @@ class Engine:
         _abi.check(self._lib.gx_explain_nodes(self._h, C.byref(hp), _abi.GX_HOST, _np_ptr(m0_edges),
                                               _np_ptr(edge_mask_out), _np_ptr(feat_mask_out)))
 
+    def explain_nodes_ex(self, hp, m0_edges, edge_mask_out, feat_mask_out=None, trace=None, trace_pred=None,
+                         state_in=None, state_out=None, graphs=False):
+        """gx_explain_nodes_ex / gx_explain_graphs_ex with host (numpy) buffers.  trace: float32 (count, num_epochs, 8) out;
+        trace_pred: float32 (count, num_epochs, C) out; state_in / state_out: dicts with M? (state_in: m0_edges carries M),
+        'm', 'v' (total_edges,) and 'feat' (count, 3, d) float32 arrays (state_out also 'M')."""
+        io = _abi.GxExplainIo()
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        io.m0_edges = ptr(m0_edges); io.edge_mask = ptr(edge_mask_out); io.feat_mask = ptr(feat_mask_out)
+        io.trace = ptr(trace); io.trace_pred = ptr(trace_pred)
+        if state_in is not None:
+            io.adam_m_in = ptr(state_in["m"]); io.adam_v_in = ptr(state_in["v"]); io.feat_state_in = ptr(state_in.get("feat"))
+        if state_out is not None:
+            io.mask_param_out = ptr(state_out.get("M")); io.adam_m_out = ptr(state_out.get("m")); io.adam_v_out = ptr(state_out.get("v"))
+            io.feat_state_out = ptr(state_out.get("feat"))
+        fn = self._lib.gx_explain_graphs_ex if graphs else self._lib.gx_explain_nodes_ex
+        _abi.check(fn(self._h, C.byref(hp), _abi.GX_HOST, C.byref(io)))
+
+    def offedge_regularisers(self, hp, m0_dense):
+        """(count, num_epochs, 2) float64: per epoch (sum sigmoid(M), sum H(sigmoid(M))) over the mask entries outside the
+        sub-adjacency -- the part of the reference's printed loss that never influences the result (gx_offedge_regularisers)."""
+        count = self._plan_sizes[0]
+        out = np.zeros((count, hp.num_epochs, 2), np.float64)
+        m0_dense = _f32c(m0_dense)
+        _abi.check(self._lib.gx_offedge_regularisers(self._h, C.byref(hp), _abi.GX_HOST, _np_ptr(m0_dense), _np_ptr(out)))
+        return out
+
     def grad_nodes_host(self, edge_mask_out):
         """Gradient baseline (explain(model="grad")) of every planned node into a host buffer."""
-        self._lib.gx_grad_nodes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _abi.check(self._lib.gx_grad_nodes(self._h, _abi.GX_HOST, _np_ptr(edge_mask_out)))
 
     def explain_nodes_ptr(self, hp, space, m0_ptr, out_ptr, feat_ptr=0):
@@ -219,12 +263,10 @@ class Engine:
 
     def debug_force_stream(self, on=True):
         """Test knob: plan every task into the streaming kernel (explain_stream.cu) regardless of its size."""
-        self._lib.gx_debug_force_stream.argtypes = [C.c_void_p, C.c_int]
         _abi.check(self._lib.gx_debug_force_stream(self._h, int(bool(on))))
 
     def debug_ieee_edge(self, on=True):
         """Test knob: IEEE exp/div/sqrt in the edge phase instead of the hardware approximations."""
-        self._lib.gx_debug_ieee_edge.argtypes = [C.c_void_p, C.c_int]
         _abi.check(self._lib.gx_debug_ieee_edge(self._h, int(bool(on))))
 
     def launch_count(self):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GX_VERSION 100
+#define GX_VERSION 200
 
 typedef struct gx_handle gx_handle;
 
@@ -67,9 +67,46 @@ typedef struct gx_hparams {
   int32_t mask_bias;     /* args.mask_bias: accepted; a no-op exactly as in the reference (bias stays 0: ReLU6'(0)=0) */
   int32_t init;          /* GX_INIT_*                                                     */
   uint64_t seed;         /* GX_INIT_PHILOX: stream seed                                   */
+  int32_t start_step;    /* GX_INIT_STATE: Adam steps already taken (torch's state["step"]); else 0 */
+  int32_t reserved;
 } gx_hparams;
 #define GX_INIT_M0 0     /* caller supplies M0 at the directed-edge entries (parity with torch's RNG draw) */
 #define GX_INIT_PHILOX 1 /* N(1, 2/n) drawn on device, counter = (seed, node, edge slot)                  */
+#define GX_INIT_STATE 2  /* resume / teacher forcing: mask, Adam moments and feature-mask state supplied (gx_explain_io) */
+
+/* Per-epoch log of the optimisation, one row per epoch of this call (explain.py:137-159: the values print_training
+ * prints, plus the terms they are made of).  "edges" = restricted to the E_d directed-edge entries of the mask; the
+ * reference's printed loss also sums size/entropy over the n^2 - E_d entries that never reach the result:
+ * gx_offedge_regularisers returns that remainder so that loss = GX_TR_LOSS_EDGES + c_size*S_off + c_ent*H_off/n^2. */
+#define GX_TRACE_COLS 8
+#define GX_TR_LOSS_EDGES 0 /* pred + size(edges) + lap + ent(edges) + feat_size  (explain.py:808)      */
+#define GX_TR_PRED 1       /* -log softmax(logits[node])[label]                  (explain.py:750-753)  */
+#define GX_TR_SIZE 2       /* coef_size * sum over edges of sigmoid(M)           (explain.py:755-760)  */
+#define GX_TR_ENT 3        /* coef_ent * sum over edges of H(sigmoid(M)) / n^2   (explain.py:769-770)  */
+#define GX_TR_LAP 4        /* coef_lap * y^T (D - A_m) y / n^2                   (explain.py:780-793)  */
+#define GX_TR_FEAT 5       /* coef_feat_size * mean sigmoid(feat_mask)           (explain.py:763-766)  */
+#define GX_TR_DENSITY 6    /* mask_density(): sum(A_m) / sum(A) AFTER the epoch's Adam step (explain.py:148,680-683) */
+#define GX_TR_PGT 7        /* softmax probability of the label                                          */
+
+/* Optional inputs / outputs of gx_explain_nodes_ex and gx_explain_graphs_ex (all in the call's gx_memspace; NULL = unused).
+ * Optimiser state lives at the same slots as m0_edges / edge_mask; feature-mask state is [count][3][input_dim] =
+ * (feat_mask, exp_avg, exp_avg_sq).  State out = the state edge_mask was built from, i.e. after num_epochs-1 updates:
+ * a run of E epochs equals a run of E1 epochs followed by GX_INIT_STATE with start_step = E1-1 and num_epochs = E-E1+1,
+ * bit for bit (tests/test_gpu_state.py). */
+typedef struct gx_explain_io {
+  const float* m0_edges;      /* [total_edges] GX_INIT_M0: M0; GX_INIT_STATE: the mask parameter M              */
+  float* edge_mask;           /* [total_edges] out, required: masked_adj at the sub_col slots                   */
+  float* feat_mask;           /* [count*input_dim] out: sigmoid(feat_mask)                                      */
+  float* trace;               /* [count*num_epochs*GX_TRACE_COLS] out (ExplainModule.loss / mask_density, a12)  */
+  float* trace_pred;          /* [count*num_epochs*num_classes] out: the softmax row print_training prints (explain.py:714); needs trace */
+  const float* adam_m_in;     /* [total_edges] GX_INIT_STATE: exp_avg of M                                      */
+  const float* adam_v_in;     /* [total_edges] GX_INIT_STATE: exp_avg_sq of M                                   */
+  const float* feat_state_in; /* [count*3*input_dim] GX_INIT_STATE                                              */
+  float* mask_param_out;      /* [total_edges] out: M                                                            */
+  float* adam_m_out;          /* [total_edges] out                                                               */
+  float* adam_v_out;          /* [total_edges] out                                                               */
+  float* feat_state_out;      /* [count*3*input_dim] out                                                         */
+} gx_explain_io;
 
 void gx_default_hparams(gx_hparams* hp);
 
@@ -133,6 +170,16 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
 int gx_explain_nodes(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
                      float* edge_mask, float* feat_mask);
 
+/* Same, with the optional trace / optimiser-state buffers of gx_explain_io (io->edge_mask required). */
+int gx_explain_nodes_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io);
+
+/* Regulariser sums over the mask entries OUTSIDE the sub-adjacency (non-edges and the diagonal), which the reference's
+ * printed loss includes (explain.py:755-770 sum over all n^2 entries) although they never influence the result: every such
+ * entry follows a private scalar Adam recurrence driven by size + entropy only.  m0_dense = the full (n_t, n_t) M0 of every
+ * planned node, task after task (sum_t n_t^2 floats, `space`); out[count*num_epochs*2] = per epoch (sum sigmoid(M),
+ * sum H(sigmoid(M))) over those entries, in double.  Only needed to reproduce the reference's printed loss value. */
+int gx_offedge_regularisers(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_dense, double* out);
+
 /* The gradient baseline, Explainer.explain(..., model="grad") (explain.py:125-133) with ExplainModule.adj_feat_grad
  * (explain.py:717-738), for every planned node: one forward of the frozen model on the unmasked sub-adjacency and
  * features, loss = -log softmax(logits[node])[predicted label of the node], one backward to the adjacency;
@@ -153,6 +200,7 @@ int gx_plan_graphs(gx_handle* h, const int32_t* graph_ids, int32_t count, int64_
  * m0_edges / edge_mask: [total_edges] in `space`, as for gx_explain_nodes. */
 int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, const float* m0_edges,
                       float* edge_mask, float* feat_mask);
+int gx_explain_graphs_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io);
 
 /* Expands packed edge masks to the dense (n_t, n_t) float64 arrays Explainer.explain returns
  * (explain.py:209-221), task after task, into out (sum_t n_t^2 doubles, `space`). */
@@ -162,6 +210,14 @@ int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* 
  * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);
 int gx_last_explain_ms(gx_handle* h, float* ms);
+
+/* ---- test / measurement knobs (used by tests/ and tools/ only; they never change what the product computes by default) ----
+ * gx_debug_force_stream: plan every task into the streaming kernel (explain_stream.cu) regardless of its size;
+ * gx_debug_ieee_edge:    IEEE exp / division / sqrt in the edge phase instead of the ex2/rcp/rsqrt approximations;
+ * gx_debug_set_dump:     device buffer (>= 4 MiB) receiving the shared-memory slab of the first task and phase timers. */
+int gx_debug_force_stream(gx_handle* h, int on);
+int gx_debug_ieee_edge(gx_handle* h, int on);
+int gx_debug_set_dump(gx_handle* h, float* dev_buf);
 
 #ifdef __cplusplus
 }
