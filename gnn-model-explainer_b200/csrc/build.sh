@@ -13,5 +13,6 @@ for f in api khop explain_node explain_graph explain_stream trace; do
   fi
 done
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libgnnx.so" "$OUT/api.o" "$OUT/khop.o" "$OUT/explain_node.o" "$OUT/explain_graph.o" "$OUT/explain_stream.o" "$OUT/trace.o"
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libgnnx.so.tmp" "$OUT/api.o" "$OUT/khop.o" "$OUT/explain_node.o" "$OUT/explain_graph.o" "$OUT/explain_stream.o" "$OUT/trace.o"
+mv -f "$OUT/libgnnx.so.tmp" "$OUT/libgnnx.so"   # atomic: a snapshot never sees a half-written library
 echo "built $OUT/libgnnx.so"

@@ -53,6 +53,19 @@ class Plan:
         rows = np.repeat(np.arange(len(rp) - 1, dtype=np.int64), np.diff(rp))
         return rows, col.astype(np.int64)
 
+    def flat_index(self):
+        """row * n_t + col of every directed-edge slot of the batch (int64[total_edges]): where slot e lives in the row-major
+        (n_t, n_t) dense array of its task."""
+        count = self.count
+        n_t = np.diff(self.node_off).astype(np.int64)
+        deg = np.diff(self.sub_rowptr.astype(np.int64))
+        if count > 1:
+            deg = np.delete(deg, self.node_off[1:-1] + np.arange(1, count) - 1)   # differences across task boundaries
+        row_local = np.arange(self.total_nodes, dtype=np.int64) - np.repeat(self.node_off[:-1], n_t)
+        rows = np.repeat(row_local, deg)
+        n_of_edge = np.repeat(n_t, np.diff(self.edge_off))
+        return rows * n_of_edge + self.sub_col.astype(np.int64)
+
     def dense_of(self, t, edge_values, dtype=np.float64):
         """(n,n) dense array holding edge_values of task t at the sub-adjacency entries."""
         n = self.n(t)
@@ -255,6 +268,31 @@ class Engine:
     def explain_nodes_ptr(self, hp, space, m0_ptr, out_ptr, feat_ptr=0):
         _abi.check(self._lib.gx_explain_nodes(self._h, C.byref(hp), int(space), C.c_void_p(int(m0_ptr) or None),
                                               C.c_void_p(int(out_ptr)), C.c_void_p(int(feat_ptr) or None)))
+
+    # ---------------------------------------------------------------- device-resident variants (torch CUDA tensors)
+    def explain_nodes_device(self, hp, m0=None, out=None):
+        """The planned batch with DEVICE buffers: m0 (optional torch.float32 CUDA tensor, GX_INIT_M0) -> edge masks as a
+        torch.float32 CUDA tensor [total_edges]; asynchronous on the engine's stream."""
+        import torch
+        te = self._plan_sizes[2]
+        if out is None:
+            out = torch.empty(max(te, 1), dtype=torch.float32, device=torch.device("cuda", self.device))
+        self.explain_nodes_ptr(hp, _abi.GX_DEVICE, m0.data_ptr() if m0 is not None else 0, out.data_ptr())
+        return out[:te]
+
+    def densify_device(self, edge_mask, out=None):
+        """gx_densify on device: packed float32 edge masks (CUDA tensor) -> float64 CUDA tensor [sum_t n_t^2] holding the dense
+        (n_t, n_t) arrays Explainer.explain returns, task after task."""
+        import torch
+        total = int(self._dense_total())
+        if out is None:
+            out = torch.empty(max(total, 1), dtype=torch.float64, device=edge_mask.device)
+        _abi.check(self._lib.gx_densify(self._h, _abi.GX_DEVICE, C.c_void_p(edge_mask.data_ptr()), C.c_void_p(out.data_ptr())))
+        return out[:total]
+
+    def _dense_total(self):
+        p = self._plan
+        return int(np.sum(np.diff(p.node_off).astype(np.int64) ** 2))
 
     def densify_host(self, edge_mask, total_dense):
         out = np.empty(total_dense, np.float64)

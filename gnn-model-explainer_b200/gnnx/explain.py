@@ -147,18 +147,23 @@ class Explainer:
             seed=int(getattr(a, "gnnx_seed", 0)))
         return hp, init
 
-    def _draw_m0(self, plan):
+    def _draw_m0(self, plan, keep_dense=False):
         """Per node, in call order: FloatTensor(n,n).normal_(1, std) (explain.py:645-652), gathered at the
-        directed-edge slots.  Consumes torch's global CPU RNG exactly like the reference."""
+        directed-edge slots.  Consumes torch's global CPU RNG exactly like the reference (the n^2 draw per node IS the
+        cost of this policy: ~3 ns per normal on one core; args.gnnx_init="device" has no host work).
+        keep_dense: also return the dense draws (the off-edge entries only matter for the printed loss)."""
         m0 = np.empty(plan.total_edges, dtype=np.float32)
         gain = torch.nn.init.calculate_gain("relu")
+        flat = plan.flat_index()            # row * n + col of every edge slot, whole batch at once
+        dense = [] if keep_dense else None
         for t in range(plan.count):
             n = plan.n(t)
             std = gain * math.sqrt(2.0 / (n + n))
             M = torch.FloatTensor(n, n).normal_(1.0, std).numpy()
-            rows, cols = plan.rows_cols_of(t)
-            m0[plan.edge_off[t]:plan.edge_off[t + 1]] = M[rows, cols]
-        return m0
+            np.take(M.reshape(-1), flat[plan.edge_off[t]:plan.edge_off[t + 1]], out=m0[plan.edge_off[t]:plan.edge_off[t + 1]])
+            if keep_dense:
+                dense.append(M)
+        return (m0, dense) if keep_dense else m0
 
     def _explain_batch(self, node_indices, graph_idx=0, model="exp", unconstrained=False):
         if model not in ("exp", "grad"):
@@ -176,9 +181,34 @@ class Explainer:
             self.engine.grad_nodes_host(edge_mask)
             return plan, edge_mask
         hp, init = self._hparams()
-        m0 = self._draw_m0(plan) if init == "torch" else None
-        self.engine.explain_nodes_host(hp, m0, edge_mask)
+        if not self.print_training:
+            m0 = self._draw_m0(plan) if init == "torch" else None
+            self.engine.explain_nodes_host(hp, m0, edge_mask)
+            return plan, edge_mask
+        # print_training (explain.py:148-159): the kernels log every epoch's loss terms / density / softmax row (gx_explain_io.trace)
+        m0, dense = self._draw_m0(plan, keep_dense=True) if init == "torch" else (None, None)
+        trace = np.zeros((plan.count, hp.num_epochs, _abi.GX_TRACE_COLS), np.float32)
+        pred = np.zeros((plan.count, hp.num_epochs, self.engine.num_classes), np.float32)
+        self.engine.explain_nodes_ex(hp, m0, edge_mask, trace=trace, trace_pred=pred)
+        off = self.engine.offedge_regularisers(hp, np.concatenate([D.reshape(-1) for D in dense])) if dense is not None else None
+        self.last_trace = self._print_trace(plan, hp, trace, pred, off)
         return plan, edge_mask
+
+    def _print_trace(self, plan, hp, trace, pred, off):
+        """Replays the reference's per-epoch print (explain.py:148-159).  With the torch-compatible init the loss is the
+        reference's own number (edge part from the kernels + the regulariser sums over the n^2 - E_d mask entries that never reach
+        the result, gx_offedge_regularisers); with the device init those entries are never materialised and the printed loss
+        covers the edge entries only."""
+        loss = trace[:, :, _abi.TR_LOSS_EDGES].astype(np.float64)
+        if off is not None:
+            nn = np.diff(plan.node_off).astype(np.float64)[:, None] ** 2
+            loss = loss + hp.coef_size * off[:, :, 0] + hp.coef_ent * off[:, :, 1] / nn
+        for t in range(plan.count):
+            for epoch in range(hp.num_epochs):
+                print("epoch: ", epoch, "; loss: ", float(loss[t, epoch]), "; mask density: ", float(trace[t, epoch, _abi.TR_DENSITY]),
+                      "; pred: ", torch.from_numpy(pred[t, epoch]))
+            print("finished training in ", 0.0)
+        return dict(loss=loss, density=trace[:, :, _abi.TR_DENSITY].copy(), pred=pred, terms=trace)
 
     def _save(self, masked_adj, node_idx):
         fname = "masked_adj_" + gen_explainer_prefix(self.args) + (
@@ -242,10 +272,37 @@ class Explainer:
             print("Saved adjacency matrix to ", fname)
         return masked_adj
 
-    def explain_nodes(self, node_indices, args=None, graph_idx=0, save=True):
-        """explain.py:225-292 -> list of masked adjacencies in input order (one batched launch)."""
-        plan, edge_mask = self._explain_batch(node_indices, graph_idx)
-        out = [plan.dense_of(t, edge_mask, dtype=np.float64) for t in range(plan.count)]
+    def explain_nodes(self, node_indices, args=None, graph_idx=0, save=True, copy=True):
+        """explain.py:225-292 -> list of (n,n) float64 masked adjacencies in input order.  One batched launch; the dense arrays are
+        built ON DEVICE (gx_densify) and come back in one transfer -- the list entries are views of that one buffer:
+          copy=True  (default) a fresh host array per call (independent results, like the reference's);
+          copy=False a pinned buffer owned by the Explainer, overwritten by the next call (zero host copies).
+        save=True writes the reference's per-node .npy files (explain.py:216-220), which at ~0.4 MB per node dominates the call;
+        args.gnnx_init="device" removes the n^2 host normals per node of the torch-compatible init."""
+        if self.print_training or graph_idx not in (0, -1):
+            plan, edge_mask = self._explain_batch(node_indices, graph_idx)
+            out = [plan.dense_of(t, edge_mask, dtype=np.float64) for t in range(plan.count)]
+        else:
+            nodes = [int(i) for i in node_indices]
+            eng = self.engine
+            plan = eng.plan_nodes(nodes, self.n_hops)
+            hp, init = self._hparams()
+            dev = torch.device("cuda", eng.device)
+            m0_dev = None
+            if init == "torch":
+                m0_dev = torch.from_numpy(self._draw_m0(plan)).to(dev, non_blocking=False)
+            mask_dev = eng.explain_nodes_device(hp, m0_dev)
+            dense_dev = eng.densify_device(mask_dev)
+            if copy:
+                host = dense_dev.cpu().numpy()
+            else:
+                if getattr(self, "_pinned", None) is None or self._pinned.numel() < dense_dev.numel():
+                    self._pinned = torch.empty(max(dense_dev.numel(), 1), dtype=torch.float64).pin_memory()
+                self._pinned[:dense_dev.numel()].copy_(dense_dev)
+                host = self._pinned.numpy()
+            n_t = np.diff(plan.node_off).astype(np.int64)
+            offs = np.concatenate([[0], np.cumsum(n_t * n_t)])
+            out = [host[offs[t]:offs[t + 1]].reshape(n_t[t], n_t[t]) for t in range(plan.count)]
         if save:
             for t, node in enumerate(node_indices):
                 self._save(out[t], int(node))

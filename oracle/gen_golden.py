@@ -392,6 +392,98 @@ def gen_variants(R, epochs=30):
     print("  variants golden written")
 
 
+def _load_fixture_model(R, which, **eargs_over):
+    """(explainer, graph npz, golden npz) of a committed fixture: the reference Explainer on the fixture's graph and weights."""
+    g = np.load(os.path.join(OUT, which + "_graph.npz"))
+    gold = np.load(os.path.join(OUT, which + "_golden.npz"))
+    N = int(g["N"]); d = g["feat"].shape[1]; C = g["Wp"].shape[0]
+    adj = np.zeros((1, N, N)); e = g["edges"]; adj[0, e[:, 0], e[:, 1]] = 1; adj[0, e[:, 1], e[:, 0]] = 1
+    model = R.models.GcnEncoderNode(d, 20, 20, C, 3, bn=False, args=train_args(input_dim=d))
+    sd = {"conv_first.weight": g["W1"], "conv_first.bias": g["b1"], "conv_block.0.weight": g["W2"], "conv_block.0.bias": g["b2"],
+          "conv_last.weight": g["W3"], "conv_last.bias": g["b3"], "pred_model.weight": g["Wp"], "pred_model.bias": g["bp"]}
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    model.eval()
+
+    def make(print_training=False, **over):
+        args = ref_harness.explainer_args(dataset=which, **{**eargs_over, **over})
+        with ref_harness.quiet():
+            return R.explain.Explainer(model=model, adj=adj, feat=g["feat"][None].astype(np.float64), label=g["label"][None], pred=g["pred"][None],
+                                       train_idx=list(range(N)), args=args, writer=None, print_training=print_training, graph_idx=-1)
+    return make, g, gold
+
+
+def gen_teacher(R, steps=(25, 50, 75)):
+    """Teacher-forcing fixtures (immune to chaotic trajectories): the optimiser state of the UNMODIFIED reference after t0 Adam steps
+    and after t0+1, captured by wrapping torch.optim.Adam.step while Explainer.explain runs (nothing in the reference is modified).
+    A kernel that is handed the state at t0 must reproduce the state at t0+1 to rounding, on the chaotic syn1 nodes too.
+    -> tests/golden/teacher_golden.npz: per (fixture, node, t0): M / exp_avg / exp_avg_sq at the edge slots, feat_mask state (3,d),
+    and after one more step: M at the edges, sigmoid-symmetrised mask at the edges (what forward() builds), sigmoid(feat_mask)."""
+    out = {"steps": np.asarray(steps, np.int64)}
+    orig = torch.optim.Adam.step
+    for which, nodes in (("syn1", [0, 3, 33, 163, 293, 300, 683]), ("rand", [0, 33, 149])):
+        make, g, gold = _load_fixture_model(R, which)
+        ex = make()
+        out[which + "_nodes"] = np.asarray(nodes, np.int64)
+        for node in nodes:
+            cap = {}
+
+            def hooked(self, *a, **k):
+                r = orig(self, *a, **k)
+                ps = self.param_groups[0]["params"]
+                t = int(self.state[ps[0]]["step"])
+                if t in steps or (t - 1) in steps:
+                    cap[t] = [(p.detach().clone().numpy(), self.state[p]["exp_avg"].clone().numpy(), self.state[p]["exp_avg_sq"].clone().numpy()) for p in ps]
+                return r
+            torch.optim.Adam.step = hooked
+            try:
+                torch.manual_seed(int(gold["n%d_seed" % node]))
+                with ref_harness.quiet():
+                    masked = np.asarray(ex.explain(node, graph_idx=0))
+                    _, sub_adj, _, _, nbrs = ex.extract_neighborhood(node, 0)
+            finally:
+                torch.optim.Adam.step = orig
+            ei, ej = np.nonzero(sub_adj)
+            assert np.abs(masked[ei, ej] - gold["n%d_mask" % node]).max() == 0, "instrumented run differs from the golden run"
+            for t0 in steps:
+                (M, m, v), (F, mF, vF) = cap[t0]
+                (M1, _, _), (F1, _, _) = cap[t0 + 1]
+                key = "%s_n%d_t%d_" % (which, node, t0)
+                out[key + "M"] = M[ei, ej].astype(np.float32); out[key + "m"] = m[ei, ej].astype(np.float32); out[key + "v"] = v[ei, ej].astype(np.float32)
+                out[key + "feat"] = np.stack([F, mF, vF]).astype(np.float32)
+                out[key + "M_next"] = M1[ei, ej].astype(np.float32)
+                S = torch.sigmoid(torch.tensor(M1))
+                out[key + "mask_next"] = ((S + S.t()) / 2).numpy()[ei, ej].astype(np.float32)      # explain.py:665-678
+                out[key + "sF_next"] = torch.sigmoid(torch.tensor(F1)).numpy().astype(np.float32)
+        print("  teacher: %s %d nodes x %d steps" % (which, len(nodes), len(steps)))
+    np.savez_compressed(os.path.join(OUT, "teacher_golden.npz"), **out)
+
+
+def gen_trace(R, epochs=12):
+    """what print_training=True prints every epoch (explain.py:148-159) -- loss, mask density, softmax row --
+    parsed from the stdout of the UNMODIFIED reference.  M0 is not stored: the test regenerates the (n,n) draw from the seed.
+    -> tests/golden/trace_golden.npz"""
+    import contextlib, io, re
+    out = {"num_epochs": np.int64(epochs)}
+    for which, nodes in (("syn1", [300, 683, 13]), ("rand", [0, 33])):
+        make, g, gold = _load_fixture_model(R, which, num_epochs=epochs)
+        ex = make(print_training=True)
+        out[which + "_nodes"] = np.asarray(nodes, np.int64)
+        for node in nodes:
+            buf = io.StringIO()
+            torch.manual_seed(int(gold["n%d_seed" % node]))
+            torch.set_printoptions(precision=8, sci_mode=False)
+            with contextlib.redirect_stdout(buf):
+                ex.explain(node, graph_idx=0)
+            rows = []
+            for mt in re.finditer(r"epoch:\s+(\d+)\s+; loss:\s+(\S+)\s+; mask density:\s+(\S+)\s+; pred:\s+tensor\(\[([^\]]*)\]", buf.getvalue()):
+                rows.append([float(mt.group(2)), float(mt.group(3))] + [float(x) for x in mt.group(4).replace("\n", " ").split(",")])
+            assert len(rows) == epochs, (which, node, len(rows), buf.getvalue()[:300])
+            out["%s_n%d_trace" % (which, node)] = np.asarray(rows, np.float64)      # [epoch] = (loss, density, softmax row)
+        print("  trace: %s %d nodes x %d epochs" % (which, len(nodes), epochs))
+    torch.set_printoptions(profile="default")
+    np.savez_compressed(os.path.join(OUT, "trace_golden.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -402,6 +494,14 @@ def main():
         return
     if a.only == "grad":
         gen_grad(ref_harness.load())
+        return
+    if a.only == "teacher":
+        torch.set_num_threads(8)
+        gen_teacher(ref_harness.load())
+        return
+    if a.only == "trace":
+        torch.set_num_threads(8)
+        gen_trace(ref_harness.load())
         return
     if a.only == "variants":
         torch.set_num_threads(8)

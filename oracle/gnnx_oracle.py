@@ -243,12 +243,21 @@ def explain_dense_torch(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
             Lm = D - masked_adj[-1]                                             # explain.py:781-782
             lap_loss = hp.lap * (pred_label_t @ Lm @ pred_label_t) / adj.numel()  # explain.py:789-793
         loss = pred_loss + size_loss + lap_loss + mask_ent_loss + feat_size_loss  # explain.py:808
+        m_used, ent_used = m.detach(), mask_ent.detach()
         loss.backward()                                                         # explain.py:142
         opt.step()                                                              # explain.py:144
         with torch.no_grad():
             density = torch.sum(masked_adj_fn()) / torch.sum(adj)               # explain.py:148,680-683
         if trace is not None:
-            trace.append((float(loss), float(density)))
+            # what print_training prints (explain.py:148-159) plus the terms it is made of; "edges" = restricted to the entries of
+            # the sub-adjacency (the only mask entries that can reach the result), the complement is the "off" part
+            with torch.no_grad():
+                on = adj[0] > 0
+                trace.append(dict(loss=float(loss), density=float(density), pred=res.detach().numpy().copy(),
+                                  pred_loss=float(pred_loss), lap=float(lap_loss), feat_size=float(feat_size_loss),
+                                  size_edges=float(hp.size * torch.sum(m_used[on])), size_off=float(hp.size * torch.sum(m_used[~on])),
+                                  ent_edges=float(hp.ent * torch.sum(ent_used[on]) / adj.numel()),
+                                  ent_off=float(hp.ent * torch.sum(ent_used[~on]) / adj.numel())))
     return masked_adj[0].detach().numpy() * np.asarray(sub_adj, dtype=np.float64)   # explain.py:209-211
 
 
@@ -280,7 +289,7 @@ def _sigmoid(x):
 
 
 def explain_closed_form(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, weights, M0,
-                        hp=None, graph_mode=False, dtype=np.float64, return_state=False, bn=False):
+                        hp=None, graph_mode=False, dtype=np.float64, return_state=False, bn=False, init_state=None):
     """Hand-derived forward/backward, any number of layers; bn=True adds the per-node
     standardisation of models.py:222-228 after every hidden layer's ReLU (forward and its backward).  Dense numpy arrays are used for
     brevity, but only the edge entries of M carry information: off-edge entries never influence
@@ -308,6 +317,11 @@ def explain_closed_form(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
     M = np.asarray(M0, dtype=f).copy()
     mM = np.zeros_like(M); vM = np.zeros_like(M)
     F = np.zeros(d, f); mF = np.zeros(d, f); vF = np.zeros(d, f)
+    step0 = 0
+    if init_state is not None:     # resume / teacher forcing: (m, v) dense like M0, feat = (3,d) [F, exp_avg, exp_avg_sq], step = Adam steps taken
+        mM = np.asarray(init_state["m"], dtype=f).copy(); vM = np.asarray(init_state["v"], dtype=f).copy()
+        F, mF, vF = (np.asarray(init_state["feat"][k], dtype=f).copy() for k in range(3))
+        step0 = int(init_state["step"])
     if not graph_mode:
         y = np.asarray(pred_label, dtype=f)
         lapA = (y[None, :] ** 2 - y[:, None] * y[None, :]) / f(n * n) * f(hp.lap)   # d/dA_ij of y^T(D-A)y/n^2
@@ -371,7 +385,7 @@ def explain_closed_form(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
         gF = sF * (1 - sF) * ((X * dH).sum(0) + f(hp.feat_size) / f(d))              # explain.py:766 mean -> 1/d
         # masked_adj = A * (S + S^T)/2 ; size = c*sum(S) ; ent = mean(H(S)) over ALL n^2 entries
         gM = S * (1 - S) * ((A * dA + (A * dA).T) / 2 + f(hp.size) - f(hp.ent) * M / f(n * n))
-        b1t = 1 - hp.beta1 ** t; b2t = 1 - hp.beta2 ** t
+        b1t = 1 - hp.beta1 ** (step0 + t); b2t = 1 - hp.beta2 ** (step0 + t)
         step = f(hp.lr / b1t); b2s = f(math.sqrt(b2t))
         for P, G, m_, v_ in ((M, gM, mM, vM), (F, gF, mF, vF)):
             m_ += (G - m_) * f(1 - hp.beta1)                                         # exp_avg.lerp_
