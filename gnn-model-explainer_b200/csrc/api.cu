@@ -92,6 +92,7 @@ struct gx_handle {
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
   DevBuf d_trace, d_trpred, d_trouter, d_min, d_vin, d_fsin, d_Mout, d_mout, d_vout, d_fsout, d_m0dense, d_offedge;   // gx_explain_io staging (GX_HOST)
+  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals;
   int32_t label_min = 0, label_max = 0, pred_min = 0, pred_max = 0;   // ranges of the uploaded labels (checked against num_classes at plan time)
   bool has_label = false;
   GxPlanArrays plan{};
@@ -233,7 +234,8 @@ int gx_destroy(gx_handle* h) {
                     &h->d_tasks, &h->d_nbrs, &h->d_lo2gid, &h->d_srp, &h->d_scol, &h->d_irp, &h->d_icol,
                     &h->d_pairs, &h->d_order, &h->d_counters, &h->gb_rowptr, &h->gb_col, &h->gb_feat, &h->gb_label, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
                     &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf, &h->d_trace, &h->d_trpred, &h->d_trouter, &h->d_min, &h->d_vin,
-                    &h->d_fsin, &h->d_Mout, &h->d_mout, &h->d_vout, &h->d_fsout, &h->d_m0dense, &h->d_offedge};
+                    &h->d_fsin, &h->d_Mout, &h->d_mout, &h->d_vout, &h->d_fsout, &h->d_m0dense, &h->d_offedge,
+                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < kNumStreams; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -982,6 +984,37 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
 
 int gx_explain_graphs_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io) {
   return explain_graphs_impl(h, hp, space, io);
+}
+
+int gx_denoise_topk(gx_handle* h, gx_memspace space, const float* edge_mask, int32_t threshold_num, int32_t cap,
+                    float* out_threshold, int32_t* out_count, int32_t* out_slots, float* out_vals) {
+  if (!h || !edge_mask || !out_threshold || !out_count || !out_slots) { gx_set_error("gx_denoise_topk: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_plan) { gx_set_error("gx_denoise_topk: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
+  if (threshold_num < 1 || cap < 1) { gx_set_error("gx_denoise_topk: threshold_num and cap must be >= 1"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const int count = h->count;
+  const float* em = edge_mask;
+  float* thr = out_threshold; int32_t* cnt = out_count; int32_t* slots = out_slots; float* vals = out_vals;
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(h->d_out.reserve((size_t)std::max<int64_t>(h->total_e, 1) * 4));
+    GX_CUDA_CHECK(cudaMemcpyAsync(h->d_out.p, edge_mask, (size_t)h->total_e * 4, cudaMemcpyHostToDevice, h->stream));
+    GX_CUDA_CHECK(h->d_dn_thr.reserve((size_t)count * 4)); GX_CUDA_CHECK(h->d_dn_cnt.reserve((size_t)count * 4));
+    GX_CUDA_CHECK(h->d_dn_slots.reserve((size_t)count * cap * 4));
+    if (out_vals) GX_CUDA_CHECK(h->d_dn_vals.reserve((size_t)count * cap * 4));
+    em = h->d_out.as<float>(); thr = h->d_dn_thr.as<float>(); cnt = h->d_dn_cnt.as<int32_t>(); slots = h->d_dn_slots.as<int32_t>();
+    vals = out_vals ? h->d_dn_vals.as<float>() : nullptr;
+  }
+  GX_CUDA_CHECK(cudaMemsetAsync(slots, 0xFF, (size_t)count * cap * 4, h->stream));   // unused entries read as -1
+  GX_CUDA_CHECK(gx_launch_denoise_topk(h->plan, count, em, 2 * threshold_num, cap, thr, cnt, slots, vals, h->stream));
+  h->launches += 1;
+  if (space == GX_HOST) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(out_threshold, thr, (size_t)count * 4, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaMemcpyAsync(out_count, cnt, (size_t)count * 4, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaMemcpyAsync(out_slots, slots, (size_t)count * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_vals) GX_CUDA_CHECK(cudaMemcpyAsync(out_vals, vals, (size_t)count * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return GX_OK;
 }
 
 int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* out) {

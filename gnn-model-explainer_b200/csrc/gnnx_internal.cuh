@@ -294,6 +294,8 @@ cudaError_t gx_launch_explain_graphs(const GxExplainLaunch& cfg, const GxGraphBa
                                      float* out_feat, cudaStream_t s);
 cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
                                   const float* m0, float* out_mask, const GxExtra& x, cudaStream_t s);
+cudaError_t gx_launch_denoise_topk(const GxPlanArrays& plan, int count, const float* edge_mask, int k2, int cap, float* out_thr,
+                                   int32_t* out_cnt, int32_t* out_slots, float* out_vals, cudaStream_t s);
 // trace.cu
 cudaError_t gx_launch_trace_finalize(const GxHparamsDev& hp, const GxPlanArrays& plan, int count, const GxExtra& x, cudaStream_t s);
 cudaError_t gx_launch_offedge(const GxHparamsDev& hp, const GxPlanArrays& plan, int count, int epochs, const int64_t* dense_off,

@@ -20,7 +20,7 @@ EXPORTS = [
     "gx_plan_fetch", "gx_explain_nodes", "gx_densify", "gx_launch_count", "gx_last_explain_ms",
     "gx_set_graph_batch_csr", "gx_plan_graphs", "gx_explain_graphs", "gx_grad_nodes",
     "gx_explain_nodes_ex", "gx_explain_graphs_ex", "gx_offedge_regularisers",
-    "gx_debug_force_stream", "gx_debug_ieee_edge", "gx_debug_set_dump",
+    "gx_debug_force_stream", "gx_debug_ieee_edge", "gx_debug_set_dump", "gx_denoise_topk",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
     L.gx_explain_graphs_ex.argtypes = [vp, C.POINTER(GxHparams), C.c_int, C.POINTER(GxExplainIo)]
     L.gx_offedge_regularisers.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, vp]
     L.gx_grad_nodes.argtypes = [vp, C.c_int, f32p]
+    L.gx_denoise_topk.argtypes = [vp, C.c_int, f32p, C.c_int32, C.c_int32, f32p, i32p, i32p, f32p]
     L.gx_debug_force_stream.argtypes = [vp, C.c_int]
     L.gx_debug_ieee_edge.argtypes = [vp, C.c_int]
     L.gx_debug_set_dump.argtypes = [vp, vp]

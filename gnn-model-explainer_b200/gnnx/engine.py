@@ -294,6 +294,17 @@ class Engine:
         p = self._plan
         return int(np.sum(np.diff(p.node_off).astype(np.int64) ** 2))
 
+    def denoise_topk(self, edge_mask, threshold_num=20, cap=None):
+        """io_utils.denoise_graph's thresholding (utils/io_utils.py:193-231) of every planned node on device: returns
+        (threshold[count], count[count], slots[count,cap], vals[count,cap]); slots are task-local edge slots (ascending), -1 padded."""
+        count = self._plan_sizes[0]
+        cap = int(cap or 2 * threshold_num + 16)
+        thr = np.zeros(count, np.float32); cnt = np.zeros(count, np.int32)
+        slots = np.zeros((count, cap), np.int32); vals = np.zeros((count, cap), np.float32)
+        _abi.check(self._lib.gx_denoise_topk(self._h, _abi.GX_HOST, _np_ptr(_f32c(edge_mask)), int(threshold_num), cap,
+                                             _np_ptr(thr), _np_ptr(cnt), _np_ptr(slots), _np_ptr(vals)))
+        return thr, cnt, slots, vals
+
     def densify_host(self, edge_mask, total_dense):
         out = np.empty(total_dense, np.float64)
         _abi.check(self._lib.gx_densify(self._h, _abi.GX_HOST, _np_ptr(_f32c(edge_mask)), _np_ptr(out)))

@@ -342,11 +342,47 @@ class Explainer:
         for t in range(plan.count):
             pred, real = self.make_pred_real(masked_adjs[t], int(plan.node_idx_new[t]))
             pred_all.append(pred); real_all.append(real)
-        self.auc = float(roc_auc_score(np.concatenate(real_all), np.concatenate(pred_all)))
+        real_cat, pred_cat = np.concatenate(real_all), np.concatenate(pred_all)
+        self.auc = float(roc_auc_score(real_cat, pred_cat))
         os.makedirs(os.path.join("log", "pr"), exist_ok=True)
+        # explain.py:308,329-335: the denoised graphs (threshold_num=20) and the precision/recall curve.  The reference draws both
+        # (tensorboard / matplotlib); here the graphs are kept on the object and the curve is written as arrays (+ PNG if matplotlib exists)
+        self.denoised, _ = self.denoise_nodes(plan, edge_mask, threshold_num=20, with_feat=True)
+        from sklearn.metrics import precision_recall_curve
+        precision, recall, thresholds = precision_recall_curve(real_cat, pred_cat)
+        self.pr_curve = (precision, recall, thresholds)
+        np.savez(os.path.join("log", "pr", "pr_" + self.args.dataset + "_" + model + ".npz"), precision=precision, recall=recall, thresholds=thresholds)
+        try:
+            import matplotlib
+            matplotlib.use("agg")
+            import matplotlib.pyplot as plt
+            plt.plot(recall, precision)
+            plt.savefig(os.path.join("log", "pr", "pr_" + self.args.dataset + "_" + model + ".png"))
+            plt.close()
+        except ImportError:
+            pass
         with open(os.path.join("log", "pr", "auc_" + self.args.dataset + "_" + model + ".txt"), "w") as f:
             f.write("dataset: {}, model: {}, auc: {}\n".format(self.args.dataset, "exp", str(self.auc)))
         return masked_adjs
+
+    def denoise_nodes(self, plan, edge_mask, threshold_num=20, max_component=True, with_feat=False):
+        """io_utils.denoise_graph(masked_adj, node_idx_new, feat, threshold_num=20) (explain.py:308, utils/io_utils.py:193-245) for
+        every node of a packed result: the 2*threshold_num-largest threshold and the surviving edges are computed on device
+        (gx_denoise_topk); only those <= ~40 edges per node come back, the networkx object is assembled from them."""
+        from . import io_utils
+        thr, cnt, slots, vals = self.engine.denoise_topk(edge_mask, threshold_num)
+        cap = slots.shape[1]
+        if int(cnt.max(initial=0)) > cap:          # many values tie at the threshold: fetch again with room for all of them
+            thr, cnt, slots, vals = self.engine.denoise_topk(edge_mask, threshold_num, cap=int(cnt.max()))
+        flat = plan.flat_index()
+        out = []
+        for t in range(plan.count):
+            n = plan.n(t)
+            k = int(cnt[t])
+            f = flat[plan.edge_off[t] + slots[t, :k]]
+            feat = np.asarray(self.feat)[0, plan.neighbors_of(t)] if with_feat else None
+            out.append(io_utils.graph_from_edges(n, int(plan.node_idx_new[t]), f // n, f % n, vals[t, :k], feat, None, max_component))
+        return out, thr
 
     def explain_nodes_packed(self, node_indices, graph_idx=0):
         """Same computation, returning (plan, edge_mask) without densifying: edge_mask[edge_off[t]:

@@ -53,3 +53,42 @@ def read_tu_dataset(datadir, dataname, max_nodes=100):
     if node_labels is not None:
         out["feat"] = np.stack(feats)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# denoise_graph: the step every consumer of the masks runs next (explain.py:238-288,308; utils/io_utils.py:193-245)
+# ------------------------------------------------------------------------------------------------
+def graph_from_edges(num_nodes, node_idx, ei, ej, w, feat=None, label=None, max_component=True):
+    """networkx graph of the thresholded edges, exactly the object denoise_graph returns (io_utils.py:207-245): all
+    `num_nodes` nodes exist first (node_idx carries self=1, optional feat/label attributes), then either the largest
+    connected component or the non-isolated nodes are kept."""
+    import networkx as nx
+    G = nx.Graph()
+    G.add_nodes_from(range(num_nodes))
+    G.nodes[node_idx]["self"] = 1
+    if feat is not None:
+        for node in G.nodes():
+            G.nodes[node]["feat"] = feat[node]
+    if label is not None:
+        for node in G.nodes():
+            G.nodes[node]["label"] = label[node]
+    G.add_weighted_edges_from(zip((int(i) for i in ei), (int(j) for j in ej), (float(x) for x in w)))
+    if max_component:
+        largest_cc = max(nx.connected_components(G), key=len)
+        return G.subgraph(largest_cc).copy()
+    G.remove_nodes_from(list(nx.isolates(G)))
+    return G
+
+
+def denoise_graph(adj, node_idx, feat=None, label=None, threshold=None, threshold_num=None, max_component=True):
+    """Same signature and result as the reference's io_utils.denoise_graph for a DENSE (n,n) mask (API compatibility for
+    callers that hold dense arrays).  Explainer.denoise_nodes is the batched path: the threshold select and the edge
+    compaction run on device on the packed masks (gx_denoise_topk)."""
+    adj = np.asarray(adj)
+    n = adj.shape[-1]
+    if threshold_num is not None:
+        pos = adj[adj > 0]
+        k = min(len(pos), 2 * threshold_num)          # symmetric: every edge appears twice
+        threshold = np.partition(pos, len(pos) - k)[len(pos) - k]
+    ei, ej = np.nonzero(adj >= threshold) if threshold is not None else np.nonzero(adj > 1e-6)
+    return graph_from_edges(n, node_idx, ei, ej, adj[ei, ej], feat, label, max_component)

@@ -206,6 +206,16 @@ int gx_explain_graphs_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, 
  * (explain.py:209-221), task after task, into out (sum_t n_t^2 doubles, `space`). */
 int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* out);
 
+/* The thresholding step of io_utils.denoise_graph(masked_adj, node_idx, threshold_num=k) (utils/io_utils.py:193-231; called on
+ * every explained node by explain.py:238-288,308) on the packed masks of the planned nodes, on device: per node
+ *   out_threshold[t] = the min(2k, #positive)-th largest positive mask value ("edges are repeated twice in adj"), +inf if none
+ *   out_count[t]     = number of directed slots with value >= threshold (>= 2k when values tie at the threshold)
+ *   out_slots[t*cap ..] = those slots (task-local indices into the node's sub_col / edge_mask slice), ascending, first `cap`
+ *   out_vals[t*cap ..]  = their mask values (may be NULL)
+ * This is also what a multi-GPU run gathers when the full masks are too large to gather (BASELINE configs[4]). */
+int gx_denoise_topk(gx_handle* h, gx_memspace space, const float* edge_mask, int32_t threshold_num, int32_t cap,
+                    float* out_threshold, int32_t* out_count, int32_t* out_slots, float* out_vals);
+
 /* Counters for bench.py: number of kernels this handle has launched so far, and the device time
  * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);

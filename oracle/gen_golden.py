@@ -484,6 +484,39 @@ def gen_trace(R, epochs=12):
     np.savez_compressed(os.path.join(OUT, "trace_golden.npz"), **out)
 
 
+def gen_denoise(R, k=20):
+    """io_utils.denoise_graph(masked_adj, node_idx_new, threshold_num=20) of the UNMODIFIED reference (utils/io_utils.py:193-245) on
+    its own golden masks -> tests/golden/denoise_golden.npz: per node the thresholded edge list (max_component=False) and the node
+    set of the largest component (max_component=True), plus precision_recall_curve of the six motif-start nodes (explain.py:329)."""
+    from sklearn.metrics import precision_recall_curve
+    out = {"threshold_num": np.int64(k)}
+    for which, nodes in (("syn1", [300, 350, 400, 450, 550, 620, 0, 13]), ("syn4", [511, 512])):
+        gold = np.load(os.path.join(OUT, which + "_golden.npz"))
+        g = np.load(os.path.join(OUT, which + "_graph.npz"))
+        N = int(g["N"])
+        A = np.zeros((N, N)); A[g["edges"][:, 0], g["edges"][:, 1]] = 1; A[g["edges"][:, 1], g["edges"][:, 0]] = 1
+        nodes = [n for n in nodes if ("n%d_mask" % n) in gold]
+        out[which + "_nodes"] = np.asarray(nodes, np.int64)
+        for node in nodes:
+            nbrs = gold["n%d_nbrs" % node]
+            sub = A[nbrs][:, nbrs]
+            ei, ej = np.nonzero(sub)
+            M = np.zeros_like(sub); M[ei, ej] = gold["n%d_mask" % node]
+            idx = int(gold["n%d_idx_new" % node])
+            G0 = R.io_utils.denoise_graph(M.copy(), idx, threshold_num=k, max_component=False)
+            G1 = R.io_utils.denoise_graph(M.copy(), idx, threshold_num=k, max_component=True)
+            e = np.array(sorted((min(u, v), max(u, v)) for u, v in G0.edges()), np.int32).reshape(-1, 2)
+            out["%s_n%d_edges" % (which, node)] = e
+            out["%s_n%d_weights" % (which, node)] = np.array([G0[u][v]["weight"] for u, v in e], np.float32)
+            out["%s_n%d_cc" % (which, node)] = np.array(sorted(G1.nodes()), np.int32)
+    au = np.load(os.path.join(OUT, "auc_golden.npz"))
+    real = np.concatenate([au["syn1_n%d_real" % n] for n in au["syn1_nodes"]]); pred = np.concatenate([au["syn1_n%d_pred" % n] for n in au["syn1_nodes"]])
+    pr, rc, th = precision_recall_curve(real, pred)
+    out["syn1_pr_precision"] = pr; out["syn1_pr_recall"] = rc; out["syn1_pr_thresholds"] = th
+    np.savez_compressed(os.path.join(OUT, "denoise_golden.npz"), **out)
+    print("  denoise golden written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -494,6 +527,9 @@ def main():
         return
     if a.only == "grad":
         gen_grad(ref_harness.load())
+        return
+    if a.only == "denoise":
+        gen_denoise(ref_harness.load())
         return
     if a.only == "teacher":
         torch.set_num_threads(8)

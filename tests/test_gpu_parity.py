@@ -443,3 +443,55 @@ def test_grad_baseline_matches_reference(which, tmp_path):
         idx_new, sub_adj, _, _, _ = ex.extract_neighborhood(300)
         ei, ej = np.nonzero(sub_adj)
         assert util.rel_l2(masked[ei, ej], g["syn1_n300_mask"]) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------ denoise_graph thresholding on device
+@pytest.mark.parametrize("which", ["syn1", "syn4"])
+def test_denoise_topk_matches_reference(which, tmp_path):
+    """gx_denoise_topk + Explainer.denoise_nodes on the reference's own golden masks (so the values are identical) against the
+    UNMODIFIED reference's denoise_graph(threshold_num=20) output: thresholded edge set, weights, largest component (bit-exact)."""
+    fx = util.load_fixture(which)
+    dg = np.load(util.GOLDEN + "/denoise_golden.npz")
+    nodes = [int(x) for x in dg[which + "_nodes"]]
+    ex, args = _explainer(fx, tmp_path)
+    plan = ex.engine.plan_nodes(nodes, 3)
+    mask = np.concatenate([fx.gold["n%d_mask" % n] for n in nodes]).astype(np.float32)
+    G0s, thr = ex.denoise_nodes(plan, mask, threshold_num=int(dg["threshold_num"]), max_component=False)
+    G1s, _ = ex.denoise_nodes(plan, mask, threshold_num=int(dg["threshold_num"]), max_component=True)
+    for t, node in enumerate(nodes):
+        e = np.array(sorted((min(u, v), max(u, v)) for u, v in G0s[t].edges()), np.int32).reshape(-1, 2)
+        assert np.array_equal(e, dg["%s_n%d_edges" % (which, node)]), (which, node)
+        assert np.array_equal(np.array([G0s[t][u][v]["weight"] for u, v in e], np.float32), dg["%s_n%d_weights" % (which, node)])
+        assert sorted(G1s[t].nodes()) == list(dg["%s_n%d_cc" % (which, node)])
+        assert thr[t] == dg["%s_n%d_weights" % (which, node)].min()
+
+
+def test_denoise_topk_properties_random():
+    """Random packed values incl. ties, zeros and a capacity smaller than the number of survivors, against numpy."""
+    fx = util.load_fixture("syn1")
+    eng = util.make_engine(fx)
+    nodes = [0, 3, 300, 683, 13, 699]
+    plan = eng.plan_nodes(nodes, 3)
+    rng = np.random.default_rng(5)
+    vals = rng.random(plan.total_edges).astype(np.float32)
+    vals[rng.random(plan.total_edges) < 0.1] = 0.0
+    sl = slice(plan.edge_off[2], plan.edge_off[3])
+    vals[sl] = np.round(vals[sl] * 8) / 8                      # heavy ties
+    vals[plan.edge_off[4]:plan.edge_off[5]] = 0.0              # a task without positive entries
+    for k, cap in ((20, 64), (5, 8), (3, 4096)):
+        thr, cnt, slots, out_vals = eng.denoise_topk(vals, k, cap=cap)
+        for t in range(plan.count):
+            v = vals[plan.edge_off[t]:plan.edge_off[t + 1]]
+            pos = v[v > 0]
+            if len(pos) == 0:
+                assert cnt[t] == 0 and np.isinf(thr[t])
+                continue
+            kk = min(len(pos), 2 * k)
+            want_thr = np.sort(pos)[-kk]
+            assert thr[t] == want_thr
+            keep = np.nonzero(v >= want_thr)[0]
+            assert cnt[t] == len(keep)
+            m = min(len(keep), cap)
+            assert np.array_equal(slots[t, :m], keep[:m]) and np.array_equal(out_vals[t, :m], v[keep[:m]])
+            assert np.all(slots[t, m:] == -1)
+    eng.close()

@@ -10,6 +10,8 @@ from gnnx import graph_utils as gx_gu
 from gnnx.dist import shard_indices
 from gnnx.engine import Plan
 import gnnx_oracle as O
+import os
+import util
 
 
 def test_csr_from_dense_matches_oracle():
@@ -177,3 +179,26 @@ def test_iter_explain_nodes_packed_chunks_without_gpu():
     assert [len(c[2]) for c in out] == [4, 4, 2]
     with pytest.raises(ValueError):
         list(ex.iter_explain_nodes_packed([1, 2], 0))
+
+
+def test_denoise_graph_matches_reference():
+    """gnnx.io_utils.denoise_graph (dense API mirror) against the UNMODIFIED reference's denoise_graph on its own golden masks
+    (tests/golden/denoise_golden.npz, oracle/gen_golden.py --only denoise): thresholded edges, weights, largest component."""
+    import gnnx_oracle as O
+    from gnnx import io_utils
+    dg = np.load(os.path.join(util.GOLDEN, "denoise_golden.npz"))
+    k = int(dg["threshold_num"])
+    for which in ("syn1", "syn4"):
+        fx = util.load_fixture(which)
+        for node in [int(x) for x in dg[which + "_nodes"]]:
+            idx, srp, scol, _, _, nbrs = O.extract_neighborhood(fx.rowptr, fx.col, fx.feat, fx.label, node, 3)
+            A = O.dense_from_csr(srp, scol)
+            ei, ej = np.nonzero(A)
+            M = np.zeros_like(A); M[ei, ej] = fx.gold["n%d_mask" % node]
+            G0 = io_utils.denoise_graph(M, idx, threshold_num=k, max_component=False)
+            e = np.array(sorted((min(u, v), max(u, v)) for u, v in G0.edges()), np.int32).reshape(-1, 2)
+            assert np.array_equal(e, dg["%s_n%d_edges" % (which, node)]), (which, node)
+            assert np.allclose([G0[u][v]["weight"] for u, v in e], dg["%s_n%d_weights" % (which, node)], rtol=0, atol=0)
+            G1 = io_utils.denoise_graph(M, idx, threshold_num=k, max_component=True)
+            assert sorted(G1.nodes()) == list(dg["%s_n%d_cc" % (which, node)])
+            assert G1.nodes[idx].get("self") == 1 if idx in G1 else True

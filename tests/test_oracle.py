@@ -250,3 +250,23 @@ def test_pruned_edge_list_spec_is_exact_for_every_variant(L, bn):
         got, st = KS.explain_pruned_edges(srp, scol, sfeat, slabel[idx], pred_label[nbrs], idx, w, M0[ei, ej], num_epochs=20, bn=bn)
         assert O.rel_l2(got, ref[ei, ej]) < 1e-10, (L, bn, node, O.rel_l2(got, ref[ei, ej]))
         assert st["rows_per_layer"][-1] == 1 and st["rows_per_layer"][0] <= n and st["inner_slots"] <= st["E"]
+
+
+def test_sparse_large_scale_spec_equals_the_edge_list_spec():
+    """kernel_spec.explain_pruned_edges_sparse (scipy SpMM / chunked SDDMM: what bench.py --workload c5 checks the streaming kernel
+    against at n ~ 10^5) is the same mathematics as explain_pruned_edges, which is pinned to the dense closed form above."""
+    import networkx as nx
+    import kernel_spec as KS
+    rng = np.random.default_rng(3)
+    G = nx.barabasi_albert_graph(120, 3, seed=9)
+    N, d, C = 120, 16, 4
+    rowptr, col = O.csr_from_edges(N, np.array(G.edges(), dtype=np.int64))
+    feat = rng.normal(size=(N, d)); label = rng.integers(0, C, N); pred_label = rng.integers(0, C, N)
+    sc = lambda *s: rng.normal(size=s) * 0.5
+    w = dict(W1=sc(d, 20), b1=sc(20), W2=sc(20, 20), b2=sc(20), W3=sc(20, 20), b3=sc(20), Wp=sc(C, 60), bp=sc(C))
+    for node in (0, 57):
+        idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(rowptr, col, feat, label, node, 3)
+        m0 = 1 + 0.2 * rng.normal(size=len(scol))
+        a1, _ = KS.explain_pruned_edges(srp, scol, sfeat, slabel[idx], pred_label[nbrs], idx, w, m0, num_epochs=8)
+        a2 = KS.explain_pruned_edges_sparse(srp, scol, sfeat, slabel[idx], pred_label[nbrs], idx, w, m0, num_epochs=8, chunk=64)
+        assert O.rel_l2(a2, a1) < 1e-12, O.rel_l2(a2, a1)
