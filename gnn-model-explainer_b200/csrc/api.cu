@@ -92,7 +92,8 @@ struct gx_handle {
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
   DevBuf d_trace, d_trpred, d_trouter, d_min, d_vin, d_fsin, d_Mout, d_mout, d_vout, d_fsout, d_m0dense, d_offedge;   // gx_explain_io staging (GX_HOST)
-  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals;
+  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals, d_send, d_us;
+  GxComm* comm = nullptr;
   int32_t label_min = 0, label_max = 0, pred_min = 0, pred_max = 0;   // ranges of the uploaded labels (checked against num_classes at plan time)
   bool has_label = false;
   GxPlanArrays plan{};
@@ -235,7 +236,9 @@ int gx_destroy(gx_handle* h) {
                     &h->d_pairs, &h->d_order, &h->d_counters, &h->gb_rowptr, &h->gb_col, &h->gb_feat, &h->gb_label, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
                     &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf, &h->d_trace, &h->d_trpred, &h->d_trouter, &h->d_min, &h->d_vin,
                     &h->d_fsin, &h->d_Mout, &h->d_mout, &h->d_vout, &h->d_fsout, &h->d_m0dense, &h->d_offedge,
-                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals};
+                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals, &h->d_send, &h->d_us};
+  gx_comm_impl_destroy(h->comm);
+  h->comm = nullptr;
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < kNumStreams; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
@@ -691,6 +694,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   fill_hparams(h, hp, mode, D.x.trace != nullptr, &hd);
   rc = upload_adam_table(h, hp, hd.iters, mode == 0 ? hp->start_step : 0);
   if (rc != GX_OK) return rc;
+  hd.adam_tab = h->d_adam.as<float2>();   // (the buffer may have been (re)allocated by the upload)
   const float* m0_dev = D.m0;
   float* out_dev = D.out;
   float* feat_dev = D.feat;
@@ -814,6 +818,7 @@ int gx_offedge_regularisers(gx_handle* h, const gx_hparams* hp, gx_memspace spac
   fill_hparams(h, hp, 0, false, &hd);
   int rc = upload_adam_table(h, hp, E, 0);
   if (rc != GX_OK) return rc;
+  hd.adam_tab = h->d_adam.as<float2>();
   const float* m0d = m0_dense;
   double* od = out;
   const size_t nout = (size_t)count * E * 2;
@@ -950,6 +955,7 @@ static int explain_graphs_impl(gx_handle* h, const gx_hparams* hp, gx_memspace s
   hd.c_lap = 0.f;           // lap_loss = 0 in graph mode (explain.py:787-788)
   rc = upload_adam_table(h, hp, hd.iters, hp->start_step);
   if (rc != GX_OK) return rc;
+  hd.adam_tab = h->d_adam.as<float2>();
   GxExplainLaunch cfg;
   cfg.order = h->d_order.as<int32_t>(); cfg.ntasks = count; cfg.counter = h->d_counters.as<int32_t>();
   cfg.smem_bytes = std::max(h->g_max_smem, 1024);
@@ -984,6 +990,82 @@ int gx_explain_graphs(gx_handle* h, const gx_hparams* hp, gx_memspace space, con
 
 int gx_explain_graphs_ex(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_explain_io* io) {
   return explain_graphs_impl(h, hp, space, io);
+}
+
+int gx_comm_unique_id(char id[128]) {
+  if (!id) { gx_set_error("gx_comm_unique_id: NULL argument"); return GX_ERR_INVALID; }
+  return gx_comm_impl_unique_id(id);
+}
+
+int gx_comm_init(gx_handle* h, int32_t world, int32_t rank, const char id[128]) {
+  if (!h || !id) { gx_set_error("gx_comm_init: NULL argument"); return GX_ERR_INVALID; }
+  if (world < 1 || rank < 0 || rank >= world) { gx_set_error("gx_comm_init: rank %d outside [0,%d)", rank, world); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  gx_comm_impl_destroy(h->comm);
+  h->comm = nullptr;
+  return gx_comm_impl_init(&h->comm, world, rank, id);
+}
+
+int gx_comm_destroy(gx_handle* h) {
+  if (!h) return GX_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  gx_comm_impl_destroy(h->comm);
+  h->comm = nullptr;
+  return GX_OK;
+}
+
+int gx_count_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_hops, int32_t* n_out, int32_t* e_out) {
+  if (!h || !nodes) { gx_set_error("gx_count_nodes: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_graph) { gx_set_error("gx_count_nodes: call gx_set_graph_csr first"); return GX_ERR_INVALID; }
+  if (n_hops < 1 || n_hops >= GX_MAX_LEVELS) { gx_set_error("gx_count_nodes: n_hops=%d outside [1,%d]", n_hops, GX_MAX_LEVELS - 1); return GX_ERR_INVALID; }
+  if (count <= 0) return GX_OK;
+  for (int t = 0; t < count; ++t)
+    if (nodes[t] < 0 || nodes[t] >= h->g.N) { gx_set_error("gx_count_nodes: node %d out of range", nodes[t]); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc = ensure_slot_ws(h);
+  if (rc != GX_OK) return rc;
+  h->has_plan = false;     // the task buffer is shared with the plan
+  GX_CUDA_CHECK(h->d_nodes.reserve((size_t)count * 4));
+  GX_CUDA_CHECK(h->d_tasks.reserve((size_t)count * sizeof(GxTask)));
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_nodes.p, nodes, (size_t)count * 4, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(gx_launch_khop_count(h->g, h->d_nodes.as<int32_t>(), count, n_hops, h->has_model ? h->m.L - 1 : 2, h->ws, h->d_tasks.as<GxTask>(), h->stream));
+  h->launches += 1;
+  std::vector<GxTask> tk(count);
+  GX_CUDA_CHECK(cudaMemcpyAsync(tk.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
+  GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int t = 0; t < count; ++t) { if (n_out) n_out[t] = tk[t].n; if (e_out) e_out[t] = tk[t].e_d; }
+  return GX_OK;
+}
+
+int gx_allgather_masks(gx_handle* h, const float* local_dev, int64_t local_floats, int64_t slot_floats, float* gathered_dev) {
+  if (!h || !gathered_dev || (local_floats > 0 && !local_dev)) { gx_set_error("gx_allgather_masks: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->comm) { gx_set_error("gx_allgather_masks: no communicator (call gx_comm_init)"); return GX_ERR_INVALID; }
+  if (local_floats < 0 || slot_floats < local_floats || slot_floats < 1) { gx_set_error("gx_allgather_masks: need 0 <= local_floats <= slot_floats"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  // the send slot: this rank's values, zero padded to the common slot size (in place inside the receive buffer: NCCL's in-place all-gather)
+  float* mine = gathered_dev + (int64_t)gx_comm_impl_rank(h->comm) * slot_floats;
+  if (local_floats > 0 && mine != local_dev)
+    GX_CUDA_CHECK(cudaMemcpyAsync(mine, local_dev, (size_t)local_floats * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if (slot_floats > local_floats)
+    GX_CUDA_CHECK(cudaMemsetAsync(mine + local_floats, 0, (size_t)(slot_floats - local_floats) * 4, h->stream));
+  return gx_comm_impl_allgather(h->comm, mine, gathered_dev, (size_t)slot_floats, h->stream);
+}
+
+int gx_unshard_masks(gx_handle* h, const float* gathered_dev, int32_t items, const int64_t* src_off, const int64_t* dst_off,
+                     const int32_t* sizes, float* out_dev) {
+  if (!h || !gathered_dev || !src_off || !dst_off || !sizes || !out_dev) { gx_set_error("gx_unshard_masks: NULL argument"); return GX_ERR_INVALID; }
+  if (items <= 0) return GX_OK;
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const size_t b64 = (size_t)items * 8, b32 = (size_t)items * 4;
+  GX_CUDA_CHECK(h->d_us.reserve(2 * b64 + b32));
+  char* b = h->d_us.as<char>();
+  GX_CUDA_CHECK(cudaMemcpyAsync(b, src_off, b64, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(b + b64, dst_off, b64, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(cudaMemcpyAsync(b + 2 * b64, sizes, b32, cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(gx_launch_unshard(gathered_dev, items, (const int64_t*)b, (const int64_t*)(b + b64), (const int32_t*)(b + 2 * b64), out_dev, h->stream));
+  h->launches += 1;
+  return GX_OK;
 }
 
 int gx_denoise_topk(gx_handle* h, gx_memspace space, const float* edge_mask, int32_t threshold_num, int32_t cap,

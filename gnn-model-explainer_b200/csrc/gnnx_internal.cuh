@@ -296,6 +296,15 @@ cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, c
                                   const float* m0, float* out_mask, const GxExtra& x, cudaStream_t s);
 cudaError_t gx_launch_denoise_topk(const GxPlanArrays& plan, int count, const float* edge_mask, int k2, int cap, float* out_thr,
                                    int32_t* out_cnt, int32_t* out_slots, float* out_vals, cudaStream_t s);
+// comm.cu
+struct GxComm;
+int gx_comm_impl_unique_id(char* id128);
+int gx_comm_impl_init(GxComm** out, int world, int rank, const char* id128);
+void gx_comm_impl_destroy(GxComm* c);
+int gx_comm_impl_world(const GxComm* c);
+int gx_comm_impl_rank(const GxComm* c);
+int gx_comm_impl_allgather(GxComm* c, const float* send, float* recv, size_t slot_floats, cudaStream_t s);
+cudaError_t gx_launch_unshard(const float* gathered, int items, const int64_t* src, const int64_t* dst, const int32_t* sz, float* out, cudaStream_t s);
 // trace.cu
 cudaError_t gx_launch_trace_finalize(const GxHparamsDev& hp, const GxPlanArrays& plan, int count, const GxExtra& x, cudaStream_t s);
 cudaError_t gx_launch_offedge(const GxHparamsDev& hp, const GxPlanArrays& plan, int count, int epochs, const int64_t* dense_off,

@@ -21,6 +21,7 @@ EXPORTS = [
     "gx_set_graph_batch_csr", "gx_plan_graphs", "gx_explain_graphs", "gx_grad_nodes",
     "gx_explain_nodes_ex", "gx_explain_graphs_ex", "gx_offedge_regularisers",
     "gx_debug_force_stream", "gx_debug_ieee_edge", "gx_debug_set_dump", "gx_denoise_topk",
+    "gx_comm_unique_id", "gx_comm_init", "gx_comm_destroy", "gx_count_nodes", "gx_allgather_masks", "gx_unshard_masks",
 ]
 
 
@@ -86,6 +87,12 @@ def lib():
     L.gx_offedge_regularisers.argtypes = [vp, C.POINTER(GxHparams), C.c_int, f32p, vp]
     L.gx_grad_nodes.argtypes = [vp, C.c_int, f32p]
     L.gx_denoise_topk.argtypes = [vp, C.c_int, f32p, C.c_int32, C.c_int32, f32p, i32p, i32p, f32p]
+    L.gx_comm_unique_id.argtypes = [C.c_char_p]
+    L.gx_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
+    L.gx_comm_destroy.argtypes = [vp]
+    L.gx_count_nodes.argtypes = [vp, i32p, C.c_int32, C.c_int32, i32p, i32p]
+    L.gx_allgather_masks.argtypes = [vp, f32p, C.c_int64, C.c_int64, f32p]
+    L.gx_unshard_masks.argtypes = [vp, f32p, C.c_int32, i64p, i64p, i32p, f32p]
     L.gx_debug_force_stream.argtypes = [vp, C.c_int]
     L.gx_debug_ieee_edge.argtypes = [vp, C.c_int]
     L.gx_debug_set_dump.argtypes = [vp, vp]

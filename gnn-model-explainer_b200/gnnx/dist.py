@@ -1,9 +1,16 @@
-"""Multi-GPU plumbing: nodes-to-explain are independent units, so they are dealt across ranks
-(one process per GPU) with NO data-path collective; the only exchange is ONE all-gather of the
-packed edge masks at the end (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""Multi-GPU plumbing: nodes-to-explain are independent units, so they are dealt across ranks (one process per GPU) with
+NO data-path collective; the only exchange is ONE all-gather of the packed edge masks at the end.
 
-Per-node arithmetic never crosses a GPU, so results are bit-identical to the 1-GPU run
-(tests/test_gpu_parity.py::test_sharding_is_bit_identical, tests/test_dist_gloo.py)."""
+How one collective suffices: every rank counts the k-hop subgraph of EVERY node of the list first (gx_count_nodes: the
+integer frontier expansion without building a plan, ~0.2 ms for 700 nodes), so the shard assignment (cost balanced), every
+rank's payload size and every item's offset are known everywhere without a metadata exchange.  Each rank pads its packed masks to
+the largest per-rank payload, ONE all-gather moves the slots (NCCL over NVLink through the library's own communicator,
+gx_allgather_masks; torch.distributed -- gloo in the CPU tests -- when no engine communicator exists), and a device kernel
+(gx_unshard_masks) scatters the slots into input order.  The masks never leave the device between the explainer kernels and
+the collective.
+
+Per-node arithmetic never crosses a GPU, so results are bit-identical to the 1-GPU run (tests/test_gpu_dist.py,
+tests/test_dist_gloo.py, bench.py "shard_bit_identical")."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -19,72 +26,78 @@ def shard_indices(num_items, world, rank, costs=None):
     return np.sort(order[rank::world])
 
 
-def allgather_packed(local_vals, local_sizes, positions, num_items, device=None, group=None):
-    """All-gather ragged per-item float32 payloads.
+def shard_layout(sizes_all, world, costs=None):
+    """Everything a rank needs to know about the exchange, computed identically on every rank from the per-item sizes:
+    shards[r] = positions of rank r; slot = floats per rank in the all-gather (largest payload); src_off[p] = where item p sits in
+    the gathered [world*slot] buffer; offsets[p] = where it goes in input order."""
+    sizes_all = np.asarray(sizes_all, np.int64)
+    num = len(sizes_all)
+    shards = [shard_indices(num, world, r, sizes_all if costs is None else costs) for r in range(world)]
+    slot = max(1, max(int(sizes_all[s].sum()) for s in shards))
+    offsets = np.concatenate([[0], np.cumsum(sizes_all)]).astype(np.int64)
+    src_off = np.zeros(num, np.int64)
+    for r, s in enumerate(shards):
+        if len(s):
+            src_off[s] = r * slot + np.concatenate([[0], np.cumsum(sizes_all[s])[:-1]])
+    return shards, slot, src_off, offsets
 
-    local_vals : 1-D float32 tensor, concatenation of this rank's item payloads
-    local_sizes: 1-D int64 tensor, payload length per local item
-    positions  : 1-D int64 tensor, global position of each local item
-    Returns (values, offsets): values = payloads of ALL items concatenated in global position
-    order (1-D float32 tensor on `device`), offsets int64[num_items+1]."""
-    world = dist.get_world_size(group)
-    device = device if device is not None else local_vals.device
-    local_vals = local_vals.to(device=device, dtype=torch.float32).contiguous()
-    local_sizes = local_sizes.to(device=device, dtype=torch.int64)
-    positions = positions.to(device=device, dtype=torch.int64)
-    # 1) tiny metadata exchange: how many items / payload floats each rank holds
-    meta = torch.tensor([local_sizes.numel(), local_vals.numel()], dtype=torch.int64, device=device)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    metas = torch.stack(metas).cpu()
-    max_items, max_vals = int(metas[:, 0].max()), int(metas[:, 1].max())
-    # 2) item tables (position, size), padded to the per-rank maximum
-    tab = torch.full((max_items, 2), -1, dtype=torch.int64, device=device)
-    tab[: local_sizes.numel(), 0] = positions
-    tab[: local_sizes.numel(), 1] = local_sizes
-    tabs = torch.empty((world, max_items, 2), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(tabs.view(-1), tab.view(-1), group=group)
-    # 3) THE all-gather of the masks (padded to the per-rank maximum payload)
-    pay = torch.zeros(max_vals, dtype=torch.float32, device=device)
-    pay[: local_vals.numel()] = local_vals
-    pays = torch.empty((world, max_vals), dtype=torch.float32, device=device)
-    dist.all_gather_into_tensor(pays.view(-1), pay, group=group)
-    # 4) reorder into global position order (pure indexing)
-    sizes = torch.zeros(num_items, dtype=torch.int64, device=device)
-    src_rank = torch.zeros(num_items, dtype=torch.int64, device=device)
-    src_off = torch.zeros(num_items, dtype=torch.int64, device=device)
-    for r in range(world):
-        k = int(metas[r, 0])
-        if k == 0:
-            continue
-        pos_r, sz_r = tabs[r, :k, 0], tabs[r, :k, 1]
-        sizes[pos_r] = sz_r
-        src_rank[pos_r] = r
-        src_off[pos_r] = torch.cumsum(sz_r, 0) - sz_r
-    offsets = torch.zeros(num_items + 1, dtype=torch.int64, device=device)
-    offsets[1:] = torch.cumsum(sizes, 0)
+
+def allgather_packed(local_vals, sizes_all, rank, world, costs=None, group=None, engine=None, out=None):
+    """ONE all-gather of ragged per-item float32 payloads.
+    local_vals : 1-D float32 tensor = this rank's items (positions shard_layout(...)[0][rank], ascending) concatenated
+    sizes_all  : payload length of EVERY item of the list (known on every rank: gx_count_nodes)
+    Returns (values, offsets): all payloads concatenated in input order, int64 offsets[num_items+1]."""
+    shards, slot, src_off, offsets = shard_layout(sizes_all, world, costs)
+    sizes_all = np.asarray(sizes_all, np.int64)
+    device = local_vals.device
     total = int(offsets[-1])
-    item_of = torch.repeat_interleave(torch.arange(num_items, device=device), sizes, output_size=total)
-    within = torch.arange(total, device=device) - offsets[:-1][item_of]
-    values = pays[src_rank[item_of], src_off[item_of] + within]
-    return values, offsets
+    assert local_vals.numel() == int(sizes_all[shards[rank]].sum()), "local payload does not match the shard layout"
+    if engine is not None and getattr(engine, "comm_world", None) == world and device.type == "cuda":
+        gathered = engine.allgather_masks(local_vals.contiguous(), slot)                 # gx_allgather_masks: one ncclAllGather
+        values = out if out is not None else torch.empty(max(total, 1), dtype=torch.float32, device=device)
+        engine.unshard_masks(gathered, src_off, offsets[:-1], sizes_all, values)         # gx_unshard_masks: device scatter
+        return values[:total], offsets
+    pay = torch.zeros(slot, dtype=torch.float32, device=device)
+    pay[: local_vals.numel()] = local_vals
+    gathered = torch.empty(world * slot, dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, pay, group=group)                               # THE collective (gloo / torch's NCCL)
+    item_of = np.repeat(np.arange(len(sizes_all)), sizes_all)
+    idx = torch.from_numpy(src_off[item_of] + (np.arange(total) - offsets[:-1][item_of])).to(device)
+    return gathered[idx], offsets
 
 
-def explain_nodes_sharded(explainer, node_indices, costs=None, group=None):
-    """Explainer.explain_nodes across all ranks of the default process group.
-    Every rank returns the packed masks of ALL nodes: (values float32 tensor, offsets int64
-    tensor, local (plan, positions)); values[offsets[t]:offsets[t+1]] are the masked_adj entries
-    of node_indices[t] at the row-major sub-adjacency slots."""
+def ensure_comm(engine, group=None):
+    """Bootstraps the engine's own NCCL communicator (gx_comm_init) once per process group: rank 0 creates the id, one
+    broadcast_object_list transports it."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if getattr(engine, "comm_world", None) == world:
+        return
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.comm_init(world, rank, box[0])
+
+
+def explain_nodes_sharded(explainer, node_indices, costs=None, group=None, use_engine_comm=True):
+    """Explainer.explain_nodes across all ranks of the default process group.
+    Every rank returns the packed masks of ALL nodes: (values float32 tensor, offsets int64 array, (local plan, local positions));
+    values[offsets[t]:offsets[t+1]] are the masked_adj entries of node_indices[t] at the row-major sub-adjacency slots."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    eng = explainer.engine
     nodes = np.asarray(node_indices)
-    pos = shard_indices(len(nodes), world, rank, costs)
-    dev = torch.device("cuda", explainer.engine.device) if torch.cuda.is_available() else torch.device("cpu")
+    dev = torch.device("cuda", eng.device)
+    n_all, e_all = eng.count_nodes(nodes, explainer.n_hops)
+    shards = shard_layout(e_all, world, costs)[0]
+    pos = shards[rank]
+    hp, init = explainer._hparams()
     if len(pos):
-        plan, edge_mask = explainer.explain_nodes_packed(nodes[pos])
-        sizes = torch.from_numpy(np.diff(plan.edge_off).astype(np.int64))
-        vals = torch.from_numpy(edge_mask)
+        plan = eng.plan_nodes(nodes[pos], explainer.n_hops)
+        m0_dev = None
+        if init == "torch":   # every rank walks the whole list so that torch's RNG is consumed exactly as one process would
+            m0_dev = torch.from_numpy(explainer._draw_m0_subset(plan, n_all, pos)).to(dev)
+        local = eng.explain_nodes_device(hp, m0_dev)
     else:
-        plan, sizes, vals = None, torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.float32)
-    values, offsets = allgather_packed(vals, sizes, torch.from_numpy(pos.astype(np.int64)), len(nodes),
-                                       device=dev, group=group)
+        plan, local = None, torch.zeros(0, dtype=torch.float32, device=dev)
+    if use_engine_comm:
+        ensure_comm(eng, group)
+    values, offsets = allgather_packed(local, e_all, rank, world, costs, group=group, engine=eng if use_engine_comm else None)
     return values, offsets, (plan, pos)

@@ -294,6 +294,44 @@ class Engine:
         p = self._plan
         return int(np.sum(np.diff(p.node_off).astype(np.int64) ** 2))
 
+    # ---------------------------------------------------------------- multi-GPU (one all-gather of the masks)
+    def count_nodes(self, nodes, n_hops):
+        """(n[count], e_d[count]) of every node's k-hop subgraph without building a plan (gx_count_nodes)."""
+        nodes = _i32c(nodes)
+        n = np.zeros(len(nodes), np.int32); e = np.zeros(len(nodes), np.int32)
+        if len(nodes):
+            _abi.check(self._lib.gx_count_nodes(self._h, _np_ptr(nodes), len(nodes), int(n_hops), _np_ptr(n), _np_ptr(e)))
+        return n, e
+
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        _abi.check(_abi.lib().gx_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, world, rank, unique_id):
+        _abi.check(self._lib.gx_comm_init(self._h, int(world), int(rank), C.c_char_p(bytes(unique_id))))
+        self.comm_world, self.comm_rank = int(world), int(rank)
+
+    def comm_destroy(self):
+        self._lib.gx_comm_destroy(self._h)
+        self.comm_world = None
+
+    def allgather_masks(self, local, slot_floats, gathered=None):
+        """ONE ncclAllGather (gx_allgather_masks) of this rank's packed mask values (CUDA float32 tensor) -> [world, slot_floats]."""
+        import torch
+        if gathered is None:
+            gathered = torch.empty((self.comm_world, int(slot_floats)), dtype=torch.float32, device=local.device)
+        _abi.check(self._lib.gx_allgather_masks(self._h, C.c_void_p(local.data_ptr() if local.numel() else None), int(local.numel()),
+                                                int(slot_floats), C.c_void_p(gathered.data_ptr())))
+        return gathered
+
+    def unshard_masks(self, gathered, src_off, dst_off, sizes, out):
+        src_off = np.ascontiguousarray(src_off, np.int64); dst_off = np.ascontiguousarray(dst_off, np.int64); sizes = _i32c(sizes)
+        _abi.check(self._lib.gx_unshard_masks(self._h, C.c_void_p(gathered.data_ptr()), len(sizes), _np_ptr(src_off), _np_ptr(dst_off),
+                                              _np_ptr(sizes), C.c_void_p(out.data_ptr())))
+        return out
+
     def denoise_topk(self, edge_mask, threshold_num=20, cap=None):
         """io_utils.denoise_graph's thresholding (utils/io_utils.py:193-231) of every planned node on device: returns
         (threshold[count], count[count], slots[count,cap], vals[count,cap]); slots are task-local edge slots (ascending), -1 padded."""

@@ -165,6 +165,22 @@ class Explainer:
                 dense.append(M)
         return (m0, dense) if keep_dense else m0
 
+    def _draw_m0_subset(self, plan, n_all, positions):
+        """Sharded runs with the torch-compatible init: walk the WHOLE node list in order (n_all[p] = sub-graph size of list entry
+        p, from gx_count_nodes) drawing every node's n^2 normals like one process would, and keep the edge entries of the entries
+        this rank owns (`positions`, ascending; `plan` is the plan of exactly those nodes)."""
+        m0 = np.empty(plan.total_edges, dtype=np.float32)
+        gain = torch.nn.init.calculate_gain("relu")
+        flat = plan.flat_index()
+        mine = {int(p): t for t, p in enumerate(positions)}
+        for p, n in enumerate(n_all):
+            n = int(n)
+            M = torch.FloatTensor(n, n).normal_(1.0, gain * math.sqrt(2.0 / (n + n)))
+            t = mine.get(p)
+            if t is not None:
+                np.take(M.numpy().reshape(-1), flat[plan.edge_off[t]:plan.edge_off[t + 1]], out=m0[plan.edge_off[t]:plan.edge_off[t + 1]])
+        return m0
+
     def _explain_batch(self, node_indices, graph_idx=0, model="exp", unconstrained=False):
         if model not in ("exp", "grad"):
             raise NotImplementedError("model=%r (att) is not built" % model)

@@ -216,6 +216,26 @@ int gx_densify(gx_handle* h, gx_memspace space, const float* edge_mask, double* 
 int gx_denoise_topk(gx_handle* h, gx_memspace space, const float* edge_mask, int32_t threshold_num, int32_t cap,
                     float* out_threshold, int32_t* out_count, int32_t* out_slots, float* out_vals);
 
+/* ---- multi-GPU: one process per GPU, explained nodes dealt across ranks, ONE all-gather of the packed masks ----
+ * The reference's node loop (explain.py:225-236) is sequential and has no exchange step; results of different nodes never
+ * interact, so the only collective is the final delivery.  NCCL is loaded at run time (dlopen libnccl.so.2).
+ *   gx_comm_unique_id : rank 0 creates the 128-byte bootstrap id; the caller transports it to the other ranks
+ *                       (torch.distributed broadcast, MPI, a file);
+ *   gx_comm_init      : ncclCommInitRank on the handle's device; gx_comm_destroy releases it;
+ *   gx_count_nodes    : |k-hop set| and directed sub-adjacency entries of each node WITHOUT building a plan -- every rank
+ *                       calls it for the whole node list, so shard sizes and offsets are known everywhere with no metadata exchange;
+ *   gx_allgather_masks: ONE ncclAllGather on the handle's stream; every rank contributes `slot_floats` floats (its
+ *                       `local_floats` packed mask values, zero padded), gathered_dev receives world*slot_floats floats (device pointers);
+ *   gx_unshard_masks  : scatters the gathered slots into the caller's global item order on device: item p (sizes[p] floats)
+ *                       is read at gathered_dev[src_off[p]] and written at out_dev[dst_off[p]] (offset arrays are host pointers). */
+int gx_comm_unique_id(char id[128]);
+int gx_comm_init(gx_handle* h, int32_t world, int32_t rank, const char id[128]);
+int gx_comm_destroy(gx_handle* h);
+int gx_count_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_hops, int32_t* n_out, int32_t* e_out);
+int gx_allgather_masks(gx_handle* h, const float* local_dev, int64_t local_floats, int64_t slot_floats, float* gathered_dev);
+int gx_unshard_masks(gx_handle* h, const float* gathered_dev, int32_t items, const int64_t* src_off, const int64_t* dst_off,
+                     const int32_t* sizes, float* out_dev);
+
 /* Counters for bench.py: number of kernels this handle has launched so far, and the device time
  * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);

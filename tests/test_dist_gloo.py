@@ -22,14 +22,16 @@ def _worker(rank, world, port, num_items, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import conftest  # noqa: F401  (sys.path)
-    from gnnx.dist import shard_indices, allgather_packed
-    costs = [len(_payload(i)) for i in range(num_items)]
-    pos = shard_indices(num_items, world, rank, costs)
+    from gnnx.dist import shard_layout, allgather_packed
+    sizes_all = np.array([len(_payload(i)) for i in range(num_items)], np.int64)      # known on every rank (gx_count_nodes on the GPU path)
+    pos = shard_layout(sizes_all, world)[0][rank]
     vals = np.concatenate([_payload(i) for i in pos]) if len(pos) else np.zeros(0, np.float32)
-    sizes = np.array([len(_payload(i)) for i in pos], np.int64)
-    values, offsets = allgather_packed(torch.from_numpy(vals), torch.from_numpy(sizes),
-                                       torch.from_numpy(pos.astype(np.int64)), num_items)
-    q.put((rank, values.numpy(), offsets.numpy()))
+    calls = []
+    orig = dist.all_gather_into_tensor
+    dist.all_gather_into_tensor = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    values, offsets = allgather_packed(torch.from_numpy(vals), sizes_all, rank, world)
+    assert len(calls) == 1, "the exchange must be ONE collective"
+    q.put((rank, values.numpy(), np.asarray(offsets)))
     dist.barrier()
     dist.destroy_process_group()
 

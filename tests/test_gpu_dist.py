@@ -39,10 +39,12 @@ def _worker(rank, world, port, q):
     ex = gnnx.Explainer(model=model, adj=A[None], feat=fx.feat[None], label=fx.label[None], pred=fx.pred[None],
                         train_idx=[], args=args, writer=None, print_training=False, graph_idx=-1, device=rank)
     nodes = np.arange(0, 700, 3)
-    values, offsets, _ = explain_nodes_sharded(ex, nodes, costs=None)
+    values, offsets, _ = explain_nodes_sharded(ex, nodes)                 # gx_allgather_masks: the library's own NCCL communicator
+    v2, o2, _ = explain_nodes_sharded(ex, nodes, use_engine_comm=False)   # torch.distributed's NCCL, same layout
+    assert torch.equal(values, v2) and np.array_equal(offsets, o2)
     if rank == 0:
         plan, full = ex.explain_nodes_packed(nodes)      # the same list on one GPU
-        q.put((values.cpu().numpy(), offsets.cpu().numpy(), full, plan.edge_off.copy()))
+        q.put((values.cpu().numpy(), np.asarray(offsets), full, plan.edge_off.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
