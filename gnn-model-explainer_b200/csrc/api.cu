@@ -54,8 +54,15 @@ struct LaunchClass {
 // k CTAs per SM share 227 KB (1 KB per CTA is reserved by the system)
 static LaunchClass kClasses[] = {
     {13 * 1024, 128, 16}, {27 * 1024, 256, 8}, {55 * 1024, 256, 4},
-    {112 * 1024, 512, 2}, {226 * 1024, 512, 1}, {0, 512, 1}};
+    {112 * 1024, 512, 2}, {226 * 1024, 512, 1}, {0, 512, 1}, {226 * 1024, 512, 1}};
 constexpr int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
+constexpr int kStreamClass = 5;    // explain_stream.cu: state in a global slab
+constexpr int kClusterClass = 6;   // explain_node.cu with a thread-block cluster per task: the most expensive shared-memory tasks
+constexpr int kOneClass = 4, kTwoClass = 3;
+// A shared-memory task whose cost exceeds g_cluster_cost runs on a cluster of g_cluster_size CTAs (a function of the task alone, so a
+// sharded run computes every task exactly like the single-GPU run).  GNNX_CLUSTER_SIZE = 1 disables the class.
+static int g_cluster_size = 4;
+static int64_t g_cluster_cost = 150000;
 constexpr int kNumStreams = kNumClasses;
 
 }  // namespace
@@ -148,7 +155,7 @@ int ensure_slot_ws(gx_handle* h) {
 int task_smem_class(const GxTask& T, const GxModelDev& m, bool force_stream, int* bytes_out) {
   // shared-memory classes always use 16-bit indices: a task with n or e1 >= 65535 cannot fit 227 KB anyway
   const bool small_idx = !force_stream && T.n < 65535 && T.e1 < 65535;
-  for (int c = 0; small_idx && c < kNumClasses - 1; ++c) {
+  for (int c = 0; small_idx && c < kStreamClass; ++c) {
     const int nwarps = kClasses[c].threads / 32;
     const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, m.d, m.hid, m.emb, m.C, nwarps, 2);
     const int64_t bytes = (int64_t)L.total_words * 4;
@@ -158,7 +165,7 @@ int task_smem_class(const GxTask& T, const GxModelDev& m, bool force_stream, int
     }
   }
   *bytes_out = 0;  // streaming class (explain_stream.cu): state in a global slab, sized by gx_make_stream_layout
-  return kNumClasses - 1;
+  return kStreamClass;
 }
 
 }  // namespace
@@ -205,6 +212,8 @@ int gx_create(int device, gx_handle** out) {
     gx_set_error("gx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     return GX_ERR_CUDA;
   }
+  if (const char* env = getenv("GNNX_CLUSTER_SIZE")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) g_cluster_size = v; }
+  if (const char* env = getenv("GNNX_CLUSTER_COST")) { const long long v = atoll(env); if (v > 0) g_cluster_cost = v; }
   if (const char* env = getenv("GNNX_CLASS_THREADS")) {   // tuning knob: threads per launch class, comma separated
     int v[kNumClasses], k = 0;
     const char* p = env;
@@ -451,6 +460,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   int64_t tn = 0, te = 0, tp = 0;
   for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
   int64_t gws_words = 0;
+  auto cost = [&](int32_t t) { const GxTask& T = h->tasks[t]; return (int64_t)T.e1 * (h->m.d + 2 * h->m.hid) + (int64_t)T.n2 * 600 + (int64_t)T.npairs * 60; };
   for (int t = 0; t < count; ++t) {
     GxTask& T = h->tasks[t];
     if (T.status != 0) {
@@ -461,14 +471,18 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
     tn += T.n; te += T.e_d; tp += T.npairs;
     int bytes = 0;
-    const int cls = task_smem_class(T, h->m, h->force_stream, &bytes);
+    int cls = task_smem_class(T, h->m, h->force_stream, &bytes);
+    if (cls < kStreamClass && g_cluster_size > 1 && cost(t) > g_cluster_cost) {
+      // expensive task: one thread-block cluster (explain_node.cu, CS CTAs share the rows and pairs); decided by the task alone
+      const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, h->m.d, h->m.hid, h->m.emb, h->m.C, kClasses[kClusterClass].threads / 32, 2, g_cluster_size);
+      if ((int64_t)L.total_words * 4 <= kClasses[kClusterClass].cap_bytes) { cls = kClusterClass; bytes = L.total_words * 4; }
+    }
     T.smem_bytes = bytes;
-    if (cls == kNumClasses - 1)
+    if (cls == kStreamClass)
       gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, T.npairs_in, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
     h->class_order[cls].push_back(t);
   }
   h->gws_stride_words = (gws_words + 3) / 4 * 4;
-  auto cost = [&](int32_t t) { const GxTask& T = h->tasks[t]; return (int64_t)T.e1 * (h->m.d + 2 * h->m.hid) + (int64_t)T.n2 * 600 + (int64_t)T.npairs * 60; };
   std::vector<int32_t> order_all;
   for (int c = 0; c < kNumClasses; ++c) {
     auto& v = h->class_order[c];
@@ -480,8 +494,8 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     // class therefore run alone on an SM (moved to the 1-per-SM class, which requests the whole shared memory).
     static int topk = -1;
     if (topk < 0) { const char* e = getenv("GNNX_EXCLUSIVE_TOPK"); topk = e ? atoi(e) : 12; }
-    auto& two = h->class_order[kNumClasses - 3];
-    auto& one = h->class_order[kNumClasses - 2];
+    auto& two = h->class_order[kTwoClass];
+    auto& one = h->class_order[kOneClass];
     // only when the 2-per-SM class really pairs up tasks, and the exclusive SMs still leave everything in one wave
     int k = 0;
     if ((int)two.size() > h->num_sms) {
@@ -700,11 +714,11 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   float* feat_dev = D.feat;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
   int stream_grid = 0;
-  if (!h->class_order[kNumClasses - 1].empty()) {
+  if (!h->class_order[kStreamClass].empty()) {
     // streaming class: one CTA per SM, fewer when the per-CTA slabs (node/edge state + 32 B per inner pair) would not fit
-    stream_grid = std::min<int>((int)h->class_order[kNumClasses - 1].size(), h->num_sms);
+    stream_grid = std::min<int>((int)h->class_order[kStreamClass].size(), h->num_sms);
     int maxnp = 0;
-    for (int32_t t : h->class_order[kNumClasses - 1]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
+    for (int32_t t : h->class_order[kStreamClass]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
     const int64_t per_cta = (h->gws_stride_words + (int64_t)maxnp * 8 + 4) * 4;
     size_t free_b = 0, total_b = 0;
     GX_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -723,9 +737,10 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
       int maxnp = 0;
       for (int32_t t : h->class_order[c]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
       pws_stride[c] = ((int64_t)maxnp * 8 + 3) / 4 * 4;
-      grids[c] = c == kNumClasses - 1 ? stream_grid : std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
+      grids[c] = c == kStreamClass ? stream_grid : std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
+      if (c == kClusterClass) grids[c] = std::min<int>(nt, h->num_sms / g_cluster_size) * g_cluster_size;   // CTAs; one pair slab per cluster
       pws_off[c] = acc_words;
-      acc_words += pws_stride[c] * std::max(grids[c], 0);
+      acc_words += pws_stride[c] * std::max(c == kClusterClass ? grids[c] / g_cluster_size : grids[c], 0);
     }
     pws_off[kNumClasses] = acc_words;
     GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(acc_words, 4) * 4));
@@ -753,14 +768,15 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     cfg.pws = h->d_pws.as<float>() + pws_off[c];
     cfg.pws_stride_words = pws_stride[c];
     cfg.grid = grids[c];
-    if (c != kNumClasses - 1) {
+    cfg.cluster = c == kClusterClass ? g_cluster_size : 1;
+    if (c != kStreamClass) {
       // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)
       int need = 0;
       for (int32_t t : h->class_order[c]) need = std::max(need, h->tasks[t].smem_bytes);
-      cfg.smem_bytes = c == kNumClasses - 2 ? kClasses[c].cap_bytes : std::max(need, 1024);
+      cfg.smem_bytes = c == kOneClass ? kClasses[c].cap_bytes : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
-    if (c == kNumClasses - 1) GX_CUDA_CHECK(gx_launch_explain_stream(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    if (c == kStreamClass) GX_CUDA_CHECK(gx_launch_explain_stream(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
     else GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
     h->launches += 1;
     GX_CUDA_CHECK(cudaEventRecord(h->ev_join[c], h->side[c]));

@@ -105,6 +105,63 @@ struct ExplainArgs {
   GxExtra x;   // optional trace / optimiser-state buffers (gx_explain_io)
 };
 
+// ---------------------------------------------------------------------------------------------
+// Thread-block clusters (explain_node.cu, cluster launch class): the CS CTAs of a cluster work on ONE task.  Every CTA keeps a
+// full copy of the task's shared-memory state; a row (or pair) is computed by exactly one CTA, which stores the result into
+// every CTA's copy (st.shared::cluster through the DSMEM window), so all reads stay local.  Phases are separated by the
+// hardware cluster barrier (release/acquire makes the remote stores visible).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CS> __device__ __forceinline__ void phase_sync() {
+  if (CS == 1) __syncthreads(); else cluster_sync_all();
+}
+// Peer<CS>: byte offsets from this CTA's shared window to the other CTAs' windows (shared::cluster addresses)
+template <int CS> struct Peer {
+  uint32_t delta[CS > 1 ? CS - 1 : 1];
+  __device__ __forceinline__ void init(const void* any_smem, uint32_t crank) {
+    if (CS > 1) {
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(any_smem);
+#pragma unroll
+      for (int k = 1; k < CS; ++k) {
+        const uint32_t r = (crank + k) % CS;
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(r));
+        delta[k - 1] = ra - a;
+      }
+    }
+  }
+  // store to the local copy and to every peer's copy
+  __device__ __forceinline__ void st4(float* p, const float4 v) const {
+    *reinterpret_cast<float4*>(p) = v;
+    if (CS > 1) {
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+#pragma unroll
+      for (int k = 0; k < CS - 1; ++k)
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + delta[k]), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+  }
+  __device__ __forceinline__ void st1(float* p, const float v) const {
+    *p = v;
+    if (CS > 1) {
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+#pragma unroll
+      for (int k = 0; k < CS - 1; ++k) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a + delta[k]), "f"(v) : "memory");
+    }
+  }
+  __device__ __forceinline__ void sti(int* p, const int v) const {
+    *p = v;
+    if (CS > 1) {
+      const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+#pragma unroll
+      for (int k = 0; k < CS - 1; ++k) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a + delta[k]), "r"(v) : "memory");
+    }
+  }
+};
+
 // entropy of a Bernoulli(s) in nats, as the reference writes it (explain.py:769): no guard at s -> 0/1, like torch
 __device__ __forceinline__ float bern_entropy(float s) { return -s * logf(s) - (1.0f - s) * logf(1.0f - s); }
 

@@ -144,11 +144,14 @@ __device__ __forceinline__ void readout_phase(int lane, int C, int gt, const Idx
   if (lane < HID) dZ3[lane] = dot_v4(zs, W3s + lane * EMB, EMB / 4);
 }
 
-template <typename IdxT, int HID, int EMB, int NT, bool kTrace>
+// CS > 1: cluster launch class -- the CS CTAs of a thread-block cluster share one task (rows and pairs dealt over the cluster's
+// warps, results stored into every CTA's copy of the state through DSMEM, hardware cluster barrier between phases; phases S and
+// B2 concern a handful of rows and are computed redundantly by every CTA, which saves two cluster barriers per epoch).
+template <typename IdxT, int HID, int EMB, int NT, bool kTrace, int CS>
 __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float smem_dyn[];
   __shared__ int s_task;
-  __shared__ float s_tr[kTrace ? (NT / 32) * 4 + 4 : 1];   // trace: per-warp partial sums of the edge phase + (pred loss, p[gt], feat-size term)
+  __shared__ float s_tr[kTrace ? (NT / 32) * CS * 4 + 4 : 1];   // trace: per-warp partial sums of the edge phase + (pred loss, p[gt], feat-size term)
   __shared__ GxLayout sL;
   __shared__ int s_long[3];  // number of long rows among [0,n2), among [0,n1), and rows with a long < n1 prefix
   static_assert(HID % 4 == 0 && EMB % 4 == 0, "hidden widths must be multiples of 4");
@@ -158,17 +161,23 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
   constexpr int PD = 2 * HID + EMB;  // pred_model input width (concat of the three layers)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;        // this CTA's rank in its cluster
+  const int cid = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;   // cluster id = index of the per-task pair-state slab
+  const int cwarp = warp * CS + crank, cnwarps = nwarps * CS;   // warp id / warp count over the whole cluster (consecutive ids on different CTAs)
+  Peer<CS> peer;
+  peer.init(smem_dyn, (uint32_t)crank);
   float* const base = smem_dyn;
+  if (CS > 1) cluster_sync_all();   // every CTA of the cluster is running before anyone stores into a peer's shared memory
   const GxModelDev& m = A.m;
   const GxHparamsDev& hp = A.hp;
   const int d = m.d, C = m.C;
   const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
 
   for (;;) {
-    if (tid == 0) s_task = atomicAdd(A.counter, 1);
-    __syncthreads();
+    if (tid == 0 && crank == 0) peer.sti(&s_task, atomicAdd(A.counter, 1));
+    phase_sync<CS>();
     const int qi = s_task;
-    __syncthreads();
+    phase_sync<CS>();
     if (qi >= A.ntasks) break;
     const int task_id = A.order[qi];
     unsigned long long t_start_ns = 0;
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
     // gradient baseline: the loss is taken at the node's PREDICTED label (explain.py:130), otherwise at label[node] (explain.py:750-753)
     const int gt = hp.mode ? __ldg(A.g.pred_label + Tp->node) : Tp->gt_label;
     const int64_t node_off = Tp->node_off, rp_off = Tp->rp_off, edge_off = Tp->edge_off, pair_off = Tp->pair_off;
-    if (tid == 0) sL = gx_make_layout(n, n1, n2, e1, np, d, HID, EMB, C, nwarps, (int)sizeof(IdxT));
+    if (tid == 0) sL = gx_make_layout(n, n1, n2, e1, np, d, HID, EMB, C, nwarps, (int)sizeof(IdxT), CS);
     __syncthreads();
     const int dp = sL.dp, D4 = dp / 4;
     const int32_t* __restrict__ lo2gid = A.plan.lo2gid + node_off;
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
       float* const X = base + sL.X; float* const W1s = base + sL.W1s; float* const W2s = base + sL.W2s; float* const W3s = base + sL.W3s;
       float* const bs = base + sL.bs; float* const sF = base + sL.sF; float* const Fm = base + sL.F; float* const mF = base + sL.mF;
       float* const vF = base + sL.vF; float* const gFp = base + sL.gFp; float* const a = base + sL.a; float* const yv = base + sL.y;
-      float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)blockIdx.x * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
+      float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)cid * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
       IdxT* const icol = reinterpret_cast<IdxT*>(base + sL.icol); IdxT* const irp = reinterpret_cast<IdxT*>(base + sL.irp);
       IdxT* const pi = reinterpret_cast<IdxT*>(base + sL.pi); IdxT* const pj = reinterpret_cast<IdxT*>(base + sL.pj);
       IdxT* const ppij = reinterpret_cast<IdxT*>(base + sL.ppij); IdxT* const ppji = reinterpret_cast<IdxT*>(base + sL.ppji);
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
       }
     }
-    for (int idx = tid; idx < nwarps * dp; idx += nthreads) gFp[idx] = 0.f;
+    for (int idx = tid; idx < cnwarps * dp; idx += nthreads) gFp[idx] = 0.f;
     const float m0_std = sqrtf(2.0f / (float)n);  // gain('relu') * sqrt(2/(n+n)) (explain.py:647-651)
     for (int p = tid; p < np; p += nthreads) {
       const int i = A.plan.pair_i[pair_off + p], j = A.plan.pair_j[pair_off + p];
@@ -264,15 +273,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         m2 = make_float2(__ldg(A.x.adam_m_in + edge_off + oij), __ldg(A.x.adam_m_in + edge_off + oji));
         v2 = make_float2(__ldg(A.x.adam_v_in + edge_off + oij), __ldg(A.x.adam_v_in + edge_off + oji));
       }
-      MM[p] = make_float2(Mi, Mj);
-      mm[p] = m2;
-      vv[p] = v2;
+      const bool mine = CS == 1 || ((p >> 5) % CS) == crank;   // the CTA that owns this pair in the edge phase
       const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
-      SS[p] = make_float2(Si, Sj);
+      if (mine) {
+        MM[p] = make_float2(Mi, Mj);
+        mm[p] = m2;
+        vv[p] = v2;
+        SS[p] = make_float2(Si, Sj);
+      }
       const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
       if (i < n2) a[pij] = a0;
       if (j < n2) a[pji] = a0;
-      if (hp.out_iter == 0 && !hp.mode) {
+      if (mine && hp.out_iter == 0 && !hp.mode) {
         A.out_mask[edge_off + oij] = a0;
         A.out_mask[edge_off + oji] = a0;
         if (A.x.mask_param_out != nullptr) { A.x.mask_param_out[edge_off + oij] = Mi; A.x.mask_param_out[edge_off + oji] = Mj; }
@@ -352,12 +364,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const sF = base + sL.sF; const float* const W1s = base + sL.W1s;
         float* const Yh1 = base + sL.Yh1; float* const q1 = base + sL.q1;
         const int ntask = nlongF1 + (n2 + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
+        for (int t = cwarp; t < ntask; t += cnwarps) {
           float4 z;
           const int i = row_task_gather<IdxT, false, (NT >= 512 ? 4 : GX_SHORT_DEPTH)>(t, nlongF1, llist, n2, G, D4, irp, icol, a, X, dp, (const IdxT*)nullptr, zs, z);
           const bool act = i >= 0;
           if (act && q < D4) {
-            st4(U + i * dp + 4 * q, z);
+            peer.st4(U + i * dp + 4 * q, z);
             const float4 s4 = ld4(sF + 4 * q);   // x * sigmoid(feat_mask) (explain.py:707), linear in x
             st4(zs + lane * 4, make_float4(z.x * s4.x, z.y * s4.y, z.z * s4.z, z.w * s4.w));
           }
@@ -367,12 +379,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
           const float qn = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(p=2, dim=2), eps 1e-12
           const float rq = 1.0f / qn;   // one division per row; the row is scaled by (and the backward reuses) the reciprocal
-          if (act && q < H4) st4(Yh1 + i * HS + 4 * q, make_float4(y.x * rq, y.y * rq, y.z * rq, y.w * rq));
-          if (act && q == 0) q1[i] = rq;
+          if (act && q < H4) peer.st4(Yh1 + i * HS + 4 * q, make_float4(y.x * rq, y.y * rq, y.z * rq, y.w * rq));
+          if (act && q == 0) peer.st1(q1 + i, rq);
           __syncwarp();
         }
       }
-      __syncthreads();
+      phase_sync<CS>();
       GX_MARK(tF1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
       {
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float* const zs = base + sL.zs + warp * 128; const float* const bs = base + sL.bs;
         const float* const W2s = base + sL.W2s; float* const Yh2 = base + sL.Yh2; float* const q2 = base + sL.q2;
         const int ntask = nlongF2 + (n1 + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
+        for (int t = cwarp; t < ntask; t += cnwarps) {
           float4 z;
           const int i = row_task_gather<IdxT, true, (NT >= 512 ? 4 : GX_SHORT_DEPTH)>(t, nlongF2, llist, n1, G, H4, irp, icol, a, Yh1, HS, (const IdxT*)nullptr, zs, z);
           const bool act = i >= 0;
@@ -394,12 +406,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           const float ss = group_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, G);
           const float qn = fmaxf(sqrtf(ss), 1e-12f);
           const float rq = 1.0f / qn;
-          if (act && q < H4) st4(Yh2 + i * HS + 4 * q, make_float4(y.x * rq, y.y * rq, y.z * rq, y.w * rq));
-          if (act && q == 0) q2[i] = rq;
+          if (act && q < H4) peer.st4(Yh2 + i * HS + 4 * q, make_float4(y.x * rq, y.y * rq, y.z * rq, y.w * rq));
+          if (act && q == 0) peer.st1(q2 + i, rq);
           __syncwarp();
         }
       }
-      __syncthreads();
+      phase_sync<CS>();
       GX_MARK(tF2)
       // ---- S: row r (= level-order id 0): layer 3, readout, softmax, -log p[gt], layer-3 backward
       if (warp == 0) {
@@ -408,8 +420,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const float* const a = base + sL.a; const float* const Yh1 = base + sL.Yh1; const float* const Yh2 = base + sL.Yh2;
         float* const zs = base + sL.zs; const float* const bs = base + sL.bs; const float* const W3s = base + sL.W3s;
         float* const logit = base + sL.logit; float* const dE = base + sL.dE; float* const dZ3 = base + sL.dZ3;
-        float* const tr = kTrace ? s_tr + (NT / 32) * 4 : nullptr;
-        float* const trp = (kTrace && A.x.trace_pred != nullptr) ? A.x.trace_pred + ((int64_t)task_id * A.x.epochs + (it - 1)) * C : nullptr;
+        float* const tr = kTrace ? s_tr + (NT / 32) * CS * 4 : nullptr;
+        float* const trp = (kTrace && A.x.trace_pred != nullptr && crank == 0) ? A.x.trace_pred + ((int64_t)task_id * A.x.epochs + (it - 1)) * C : nullptr;
         if (C * (PD + 1) <= GX_WP_SMEM_MAX)   // pred_model.weight (C, 2h+e) + bias staged in shared memory
           readout_phase<IdxT, HID, EMB, true, kTrace>(lane, C, gt, irp, icol, a, Yh1, Yh2, zs, bs, W3s, base + sL.Wp, base + sL.Wp + C * PD, logit, dE, dZ3, tr, trp);
         else
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float* const gFp = base + sL.gFp; float* const zs = base + sL.zs + warp * 128;
         float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int ntask = nlongB1 + (n2 + epi - 1) / epi;
-        for (int t = warp; t < ntask; t += nwarps) {
+        for (int t = cwarp; t < ntask; t += cnwarps) {
           float4 dh;
           const int i = row_task_gather<IdxT, false, (NT >= 512 ? 1 : GX_SHORT_DEPTH)>(t, nlongB1, llistB, n2, G, H4, irp, icol, a, dZ2, HS, cnt1, zs, dh);
           const bool act = i >= 0;
@@ -507,7 +519,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
             const float4 s4 = ld4(sF + 4 * q);
             gacc.x = fmaf(o.x, u.x, gacc.x); gacc.y = fmaf(o.y, u.y, gacc.y);
             gacc.z = fmaf(o.z, u.z, gacc.z); gacc.w = fmaf(o.w, u.w, gacc.w);
-            st4(dZ1s + i * dp + 4 * q, make_float4(o.x * s4.x, o.y * s4.y, o.z * s4.z, o.w * s4.w));
+            peer.st4(dZ1s + i * dp + 4 * q, make_float4(o.x * s4.x, o.y * s4.y, o.z * s4.z, o.w * s4.w));
           }
           __syncwarp();
         }
@@ -520,13 +532,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
             const float4 o = ld4(zs + (g2 * G.GW + q) * 4);
             tsum.x += o.x; tsum.y += o.y; tsum.z += o.z; tsum.w += o.w;
           }
-          st4(gFp + warp * dp + 4 * q, tsum);
+          peer.st4(gFp + cwarp * dp + 4 * q, tsum);
         }
         __syncwarp();
       }
-      __syncthreads();
+      phase_sync<CS>();
       GX_MARK(tB1)
-      if (A.dbg != nullptr && it == 1 && qi == 0) {   // debug: [header 16 floats][whole task slab]
+      if (A.dbg != nullptr && it == 1 && qi == 0 && crank == 0) {   // debug: [header 16 floats][whole task slab]
         if (tid == 0) {
           A.dbg[0] = (float)sL.total_words; A.dbg[1] = (float)sL.X; A.dbg[2] = (float)sL.U; A.dbg[3] = (float)sL.Yh1;
           A.dbg[4] = (float)sL.q1; A.dbg[5] = (float)sL.Yh2; A.dbg[6] = (float)sL.q2; A.dbg[7] = (float)sL.dZ2;
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float* const Yh1 = base + sL.Yh1;
         float* const dZ3 = base + sL.dZ3;
         float* const Yh2 = base + sL.Yh2;
-        float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)blockIdx.x * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
+        float2* const MM = reinterpret_cast<float2*>(A.pws + (int64_t)cid * A.pws_stride_words); float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
         float* const a = base + sL.a;
         const float2 tab = __ldg(hp.adam_tab + (it - 1));
         const float step = tab.x, bc2s = tab.y, bc2s_inv = 1.0f / tab.y;
@@ -560,7 +572,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const int fthreads = min(nthreads, gx_round_up(d, 32));
         for (int f = tid - (nthreads - fthreads); f >= 0 && f < d && !hp.mode; f += fthreads) {
           float gsum = 0.f;
-          for (int w = 0; w < nwarps; ++w) gsum += gFp[w * dp + f];
+          for (int w = 0; w < cnwarps; ++w) gsum += gFp[w * dp + f];
           const float s = sF[f];
           const float g = s * (1.f - s) * (gsum + hp.c_feat_size / (float)d);
           float mf = mF[f], vf = vF[f], Fv = Fm[f];
@@ -570,7 +582,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
           const float sn = sigmoid_f(Fv);
           sF[f] = sn;
-          if (last) {
+          if (last && crank == 0) {
             if (A.out_feat != nullptr) A.out_feat[(int64_t)task_id * d + f] = sn;
             if (A.x.feat_state_out != nullptr) {
               float* fo = A.x.feat_state_out + (int64_t)task_id * 3 * d;
@@ -581,7 +593,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         float trS = 0.f, trH = 0.f, trL = 0.f, trD = 0.f;   // trace: this thread's share of sum S, sum H(S), sum a (y_i-y_j)^2, sum 2a'
         if (hp.mode) {
           // gradient baseline (explain.py:125-133): mask_ij = sigmoid(|dL/dA_ij| + |dL/dA_ji|) on the edges, no regulariser, no update
-          for (int p = tid; p < np; p += nthreads) {
+          for (int p = cwarp * 32 + lane; p < np; p += nthreads * CS) {
             const int i = pi[p], j = pj[p];
             float gij = 0.f, gji = 0.f;
             if (i < n2) gij += dot_v4(dZ1s + i * dp, X + j * dp, D4);
@@ -594,7 +606,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
             A.out_mask[edge_off + A.plan.pair_oji[pair_off + p]] = an;
           }
         } else
-        for (int p = tid; p < np; p += nthreads) {
+        for (int p = cwarp * 32 + lane; p < np; p += nthreads * CS) {
           // optimiser state of the pair (L2-resident slab): issued first so that the L2 round trip overlaps the dots below
           float2 Mv = MM[p];
           const float2 Sv = SS[p];
@@ -626,8 +638,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
           const float an = 0.5f * (Sn.x + Sn.y);
           if (kTrace) trD += 2.0f * an;
           const IdxT pa = ppij[p], pb = ppji[p];
-          if (pa != kNone) a[pa] = an;
-          if (pb != kNone) a[pb] = an;
+          if (pa != kNone) peer.st1(a + pa, an);
+          if (pb != kNone) peer.st1(a + pb, an);
           if (last) {
             const int64_t oij = edge_off + A.plan.pair_oij[pair_off + p], oji = edge_off + A.plan.pair_oji[pair_off + p];
             A.out_mask[oij] = an;
@@ -639,32 +651,32 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
         if (kTrace) {
           trS = warp_sum(trS); trH = warp_sum(trH); trL = warp_sum(trL); trD = warp_sum(trD);
-          if (lane == 0) { s_tr[warp * 4 + 0] = trS; s_tr[warp * 4 + 1] = trH; s_tr[warp * 4 + 2] = trL; s_tr[warp * 4 + 3] = trD; }
+          if (lane == 0) { peer.st1(s_tr + cwarp * 4 + 0, trS); peer.st1(s_tr + cwarp * 4 + 1, trH); peer.st1(s_tr + cwarp * 4 + 2, trL); peer.st1(s_tr + cwarp * 4 + 3, trD); }
         }
       }
-      __syncthreads();
-      if (kTrace && tid == 0) {   // raw terms of epoch it-1 over the INNER pairs; trace_finalize_kernel adds the outer pairs and assembles the columns
+      phase_sync<CS>();
+      if (kTrace && tid == 0 && crank == 0) {   // raw terms of epoch it-1 over the INNER pairs; trace_finalize_kernel adds the outer pairs and assembles the columns
         float sS = 0.f, sH = 0.f, sLp = 0.f, sD = 0.f;
-        for (int w = 0; w < nwarps; ++w) { sS += s_tr[w * 4]; sH += s_tr[w * 4 + 1]; sLp += s_tr[w * 4 + 2]; sD += s_tr[w * 4 + 3]; }
+        for (int w = 0; w < cnwarps; ++w) { sS += s_tr[w * 4]; sH += s_tr[w * 4 + 1]; sLp += s_tr[w * 4 + 2]; sD += s_tr[w * 4 + 3]; }
         float* row = A.x.trace + ((int64_t)task_id * A.x.epochs + (it - 1)) * GX_TRACE_COLS;
-        const float* const tr = s_tr + (NT / 32) * 4;
+        const float* const tr = s_tr + (NT / 32) * CS * 4;
         row[0] = sS; row[1] = tr[0]; row[2] = sH; row[3] = sLp; row[4] = sD; row[5] = tr[2]; row[6] = 0.f; row[7] = tr[1];
       }
       GX_MARK(tP)
     }
-    if (A.dbg != nullptr && tid == 0 && qi == 0) {
+    if (A.dbg != nullptr && tid == 0 && qi == 0 && crank == 0) {
       float* o = A.dbg + (1 << 19);
       o[0] = (float)tF1; o[1] = (float)tF2; o[2] = (float)tS; o[3] = (float)tB2; o[4] = (float)tB1; o[5] = (float)tP;
       o[6] = (float)n; o[7] = (float)n1; o[8] = (float)n2; o[9] = (float)np; o[10] = (float)e1; o[11] = (float)nthreads;
     }
-    if (A.dbg != nullptr && tid == 0) {
+    if (A.dbg != nullptr && tid == 0 && crank == 0) {
       unsigned long long t_end_ns; unsigned smid;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       unsigned long long* tl64 = reinterpret_cast<unsigned long long*>(A.dbg + (1 << 19) + 64);
       tl64[3 * task_id + 0] = t_start_ns; tl64[3 * task_id + 1] = t_end_ns; tl64[3 * task_id + 2] = ((unsigned long long)smid << 32) | (unsigned)nthreads;
     }
-    __syncthreads();
+    phase_sync<CS>();
   }
 }
 
@@ -753,25 +765,41 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
   }
 }
 
-template <typename IdxT, int HID, int EMB, int NT, bool kTrace>
+template <typename IdxT, int HID, int EMB, int NT, bool kTrace, int CS>
 cudaError_t launch_one_t(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  auto kern = explain_node_kernel<IdxT, HID, EMB, NT, kTrace>;
+  auto kern = explain_node_kernel<IdxT, HID, EMB, NT, kTrace, CS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
-  return cudaGetLastError();
+  if (CS == 1) {
+    kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
+    return cudaGetLastError();
+  }
+  // cluster launch class: cfg.grid counts CTAs (a multiple of CS); one task per cluster
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)cfg.grid, 1, 1);
+  lc.blockDim = dim3((unsigned)cfg.threads, 1, 1);
+  lc.dynamicSmemBytes = (size_t)cfg.smem_bytes;
+  lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, kern, args);
 }
-template <typename IdxT, int HID, int EMB, int NT>
+template <typename IdxT, int HID, int EMB, int NT, int CS>
 cudaError_t launch_one(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
-  if (args.x.trace != nullptr) return launch_one_t<IdxT, HID, EMB, NT, true>(cfg, args, s);
-  return launch_one_t<IdxT, HID, EMB, NT, false>(cfg, args, s);
+  if (args.x.trace != nullptr) return launch_one_t<IdxT, HID, EMB, NT, true, CS>(cfg, args, s);
+  return launch_one_t<IdxT, HID, EMB, NT, false, CS>(cfg, args, s);
 }
 
 template <int HID, int EMB>
 cudaError_t launch_dims(const GxExplainLaunch& cfg, const ExplainArgs& args, cudaStream_t s) {
   if (cfg.smem_bytes <= 0) return cudaErrorInvalidValue;  // tasks that do not fit shared memory belong to explain_stream.cu
-  if (cfg.threads <= 256) return launch_one<uint16_t, HID, EMB, 256>(cfg, args, s);
-  return launch_one<uint16_t, HID, EMB, 512>(cfg, args, s);
+  if (cfg.cluster == 4) return launch_one<uint16_t, HID, EMB, 512, 4>(cfg, args, s);
+  if (cfg.cluster == 2) return launch_one<uint16_t, HID, EMB, 512, 2>(cfg, args, s);
+  if (cfg.cluster != 1) return cudaErrorInvalidValue;
+  if (cfg.threads <= 256) return launch_one<uint16_t, HID, EMB, 256, 1>(cfg, args, s);
+  return launch_one<uint16_t, HID, EMB, 512, 1>(cfg, args, s);
 }
 
 }  // namespace

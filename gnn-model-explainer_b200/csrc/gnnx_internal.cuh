@@ -117,7 +117,7 @@ struct GxLayout {
 // idx_bytes = sizeof(IdxT) (2 or 4).  hid/emb must be multiples of 4.
 __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1, int np_in, int d,
                                                    int hid, int emb, int C, int nwarps,
-                                                   int idx_bytes) {
+                                                   int idx_bytes, int cs = 1) {
   GxLayout L;
   const int dp = gx_round_up(d, 4);
   L.dp = dp;
@@ -143,7 +143,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.F = takef(dp);
   L.mF = takef(dp);
   L.vF = takef(dp);
-  L.gFp = takef(nwarps * dp);
+  L.gFp = takef(nwarps * cs * dp);   // per-warp dL/dsF partials of every CTA of the cluster (cs = cluster size)
   L.zs = takef(nwarps * 128);
   L.dE = takef(2 * hid);
   L.dZ3 = takef(hid);
@@ -266,6 +266,7 @@ struct GxExplainLaunch {
   int32_t smem_bytes;    // dynamic shared memory per CTA (shared-memory classes)
   int32_t threads;
   int32_t grid;
+  int32_t cluster = 1;   // CTAs per task (thread-block cluster size): 1, 2 or 4 (explain_node.cu cluster class)
   float* gws;            // per-CTA global slab of the streaming class
   int64_t gws_stride_words;
   float* pws;            // per-CTA pair-state slab: 8 floats per inner pair (M,m,v,S of both directions)

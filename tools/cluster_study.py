@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Cluster launch class study (GPU box): for cluster size / cost-threshold settings, parity of the golden nodes against the
+reference masks and against the single-CTA result, and the device time of the 700-node syn1 batch (and syn4).
+    python tools/cluster_study.py [syn1|syn4] """
+import os
+import sys
+import json
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("gnn-model-explainer_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import util  # noqa: E402
+from gnnx import _abi  # noqa: E402
+
+
+def run(name, cs, cost, reps=6):
+    os.environ["GNNX_CLUSTER_SIZE"] = str(cs)
+    os.environ["GNNX_CLUSTER_COST"] = str(cost)
+    fx = util.load_fixture(name)
+    eng = util.make_engine(fx)
+    plan = eng.plan_nodes(fx.nodes, 3)
+    out = np.zeros(plan.total_edges, np.float32)
+    eng.explain_nodes_host(eng.make_hparams(), util.golden_m0(fx, plan), out)
+    errs = np.array([util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], fx.gold["n%d_mask" % node]) for t, node in enumerate(fx.nodes)])
+    N = fx.rowptr.shape[0] - 1
+    allnodes = np.arange(N, dtype=np.int32)
+    hp = eng.make_hparams(init=_abi.GX_INIT_PHILOX, seed=7)
+    ms = []
+    eng.plan_nodes(allnodes, 3, fetch=False)
+    import torch
+    te = eng._plan_sizes[2]
+    dev_out = torch.empty(te, dtype=torch.float32, device="cuda")
+    for _ in range(reps):
+        eng.explain_nodes_device(hp, None, dev_out)
+        eng.sync()
+        ms.append(eng.last_explain_ms())
+    res = dict(fixture=name, cluster=cs, cost=cost, kernel_ms_min=min(ms), kernel_ms_med=float(np.median(ms)), within_1e4=int((errs <= 1e-4).sum()), nodes=len(errs),
+               max_err=float(errs.max()), checksum=float(dev_out.double().sum().item()))
+    eng.close()
+    return res, out
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "syn1"
+    base, out1 = run(name, 1, 1)
+    print(json.dumps(base), flush=True)
+    rows = [base]
+    for cs in (2, 4):
+        for cost in (40000, 80000, 150000, 300000, 600000):
+            r, o = run(name, cs, cost)
+            r["max_rel_vs_cs1"] = float(max(util.rel_l2(o, out1), 0.0))
+            print(json.dumps(r), flush=True)
+            rows.append(r)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "cluster_study_%s.json" % name), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
