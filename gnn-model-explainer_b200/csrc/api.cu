@@ -59,10 +59,8 @@ constexpr int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 constexpr int kStreamClass = 5;    // explain_stream.cu: state in a global slab
 constexpr int kClusterClass = 6;   // explain_node.cu with a thread-block cluster per task: the most expensive shared-memory tasks
 constexpr int kOneClass = 4, kTwoClass = 3;
-// A shared-memory task whose cost exceeds g_cluster_cost runs on a cluster of g_cluster_size CTAs (a function of the task alone, so a
-// sharded run computes every task exactly like the single-GPU run).  GNNX_CLUSTER_SIZE = 1 disables the class.
-static int g_cluster_size = 4;
-static int64_t g_cluster_cost = 150000;
+// A shared-memory task whose cost exceeds the handle's cluster_cost runs on a cluster of cluster_size CTAs (gx_debug_set_cluster;
+// off by default: a 700-node batch is throughput bound, splitting its tasks only adds barrier and DSMEM overhead -- profiles/r02_cluster.md).
 constexpr int kNumStreams = kNumClasses;
 
 }  // namespace
@@ -77,6 +75,10 @@ struct gx_handle {
   bool timed = false;
   float* dbg = nullptr;
   bool ieee_edge = false;     // test knob (gx_debug_ieee_edge / GNNX_IEEE_EDGE): IEEE arithmetic in the edge phase
+  int gang_override = 0;      // test knob (gx_debug_set_gang / GNNX_GANG): CTAs per task of explain_gang.cu, 0 = automatic, -1 = explain_stream.cu
+  int cluster_size = 0;       // test knob (gx_debug_set_cluster): 0 = automatic
+  int64_t cluster_cost = 0;
+  int plan_cluster = 1;       // cluster size the current plan was classified with
   bool force_stream = false;  // test knob (gx_debug_force_stream / GNNX_FORCE_STREAM): every task goes to the streaming class
   cudaEvent_t ev_join[kNumStreams] = {};
   int64_t launches = 0;
@@ -99,7 +101,7 @@ struct gx_handle {
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
   DevBuf d_trace, d_trpred, d_trouter, d_min, d_vin, d_fsin, d_Mout, d_mout, d_vout, d_fsout, d_m0dense, d_offedge;   // gx_explain_io staging (GX_HOST)
-  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals, d_send, d_us;
+  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals, d_send, d_us, d_gang;
   GxComm* comm = nullptr;
   int32_t label_min = 0, label_max = 0, pred_min = 0, pred_max = 0;   // ranges of the uploaded labels (checked against num_classes at plan time)
   bool has_label = false;
@@ -212,8 +214,6 @@ int gx_create(int device, gx_handle** out) {
     gx_set_error("gx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     return GX_ERR_CUDA;
   }
-  if (const char* env = getenv("GNNX_CLUSTER_SIZE")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) g_cluster_size = v; }
-  if (const char* env = getenv("GNNX_CLUSTER_COST")) { const long long v = atoll(env); if (v > 0) g_cluster_cost = v; }
   if (const char* env = getenv("GNNX_CLASS_THREADS")) {   // tuning knob: threads per launch class, comma separated
     int v[kNumClasses], k = 0;
     const char* p = env;
@@ -224,6 +224,9 @@ int gx_create(int device, gx_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* env = getenv("GNNX_FORCE_STREAM")) h->force_stream = atoi(env) != 0;
+  if (const char* env = getenv("GNNX_GANG")) h->gang_override = atoi(env);
+  if (const char* env = getenv("GNNX_CLUSTER_SIZE")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) h->cluster_size = v; }
+  if (const char* env = getenv("GNNX_CLUSTER_COST")) { const long long v = atoll(env); if (v > 0) h->cluster_cost = v; }
   if (const char* env = getenv("GNNX_IEEE_EDGE")) h->ieee_edge = atoi(env) != 0;
   for (int i = 0; i < kNumStreams; ++i) {
     GX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
@@ -245,7 +248,7 @@ int gx_destroy(gx_handle* h) {
                     &h->d_pairs, &h->d_order, &h->d_counters, &h->gb_rowptr, &h->gb_col, &h->gb_feat, &h->gb_label, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
                     &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf, &h->d_trace, &h->d_trpred, &h->d_trouter, &h->d_min, &h->d_vin,
                     &h->d_fsin, &h->d_Mout, &h->d_mout, &h->d_vout, &h->d_fsout, &h->d_m0dense, &h->d_offedge,
-                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals, &h->d_send, &h->d_us};
+                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals, &h->d_send, &h->d_us, &h->d_gang};
   gx_comm_impl_destroy(h->comm);
   h->comm = nullptr;
   for (DevBuf* b : bufs) b->release();
@@ -282,6 +285,12 @@ int gx_debug_set_dump(gx_handle* h, float* dev_buf) { if (!h) return GX_ERR_INVA
 int gx_debug_ieee_edge(gx_handle* h, int on) { if (!h) return GX_ERR_INVALID; h->ieee_edge = on != 0; return GX_OK; }
 
 /* debug only (not in gnnx.h): plan every task into the streaming class (explain_stream.cu) regardless of its size */
+int gx_debug_set_gang(gx_handle* h, int ctas_per_task) { if (!h) return GX_ERR_INVALID; h->gang_override = ctas_per_task; return GX_OK; }
+int gx_debug_set_cluster(gx_handle* h, int cluster_size, int64_t min_cost) {
+  if (!h || !(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4)) return GX_ERR_INVALID;
+  h->cluster_size = cluster_size; h->cluster_cost = min_cost; h->has_plan = false;
+  return GX_OK;
+}
 int gx_debug_force_stream(gx_handle* h, int on) { if (!h) return GX_ERR_INVALID; h->force_stream = on != 0; h->has_plan = false; return GX_OK; }
 
 int gx_last_explain_ms(gx_handle* h, float* ms) {
@@ -461,6 +470,9 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
   int64_t gws_words = 0;
   auto cost = [&](int32_t t) { const GxTask& T = h->tasks[t]; return (int64_t)T.e1 * (h->m.d + 2 * h->m.hid) + (int64_t)T.n2 * 600 + (int64_t)T.npairs * 60; };
+  const int g_cluster_size = h->cluster_size > 1 ? h->cluster_size : 1;
+  const int64_t g_cluster_cost = h->cluster_cost;
+  h->plan_cluster = g_cluster_size;
   for (int t = 0; t < count; ++t) {
     GxTask& T = h->tasks[t];
     if (T.status != 0) {
@@ -713,12 +725,26 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   float* out_dev = D.out;
   float* feat_dev = D.feat;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
-  int stream_grid = 0;
+  int stream_grid = 0;   // slabs of the streaming class = tasks in flight (CTAs of explain_stream.cu / gangs of explain_gang.cu)
+  int gang = 0;          // > 0: explain_gang.cu with this many CTAs per task
   if (!h->class_order[kStreamClass].empty()) {
     // streaming class: one CTA per SM, fewer when the per-CTA slabs (node/edge state + 32 B per inner pair) would not fit
     stream_grid = std::min<int>((int)h->class_order[kStreamClass].size(), h->num_sms);
     int maxnp = 0;
     for (int32_t t : h->class_order[kStreamClass]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
+    const int gang_env = h->gang_override;
+    if (gang_env >= 0 && h->m.d <= 128 && gx_gang_smem_bytes(h->m.d, h->m.hid, h->m.C) <= gx_explain_max_smem()) {
+      // explain_gang.cu: G co-resident CTAs per task.  As many tasks in flight as keep their randomly accessed state
+      // (a, gE: 8 B per directed edge; P, dP, dY1: 240 B per node) inside the L2, the SMs divided evenly among them.
+      int64_t ws = 1;
+      for (int32_t t : h->class_order[kStreamClass]) ws = std::max<int64_t>(ws, (int64_t)h->tasks[t].e_d * 8 + (int64_t)h->tasks[t].n * 240);
+      const int64_t l2_budget = (int64_t)80 << 20;
+      int ngangs = (int)std::max<int64_t>(1, std::min<int64_t>(stream_grid, l2_budget / ws));
+      gang = std::max(1, std::min(h->num_sms / ngangs, GX_MAX_GANG));
+      if (gang_env > 0) gang = std::min(std::min(gang_env, h->num_sms), GX_MAX_GANG);
+      ngangs = std::max(1, std::min(ngangs, h->num_sms / gang));
+      stream_grid = std::min(stream_grid, ngangs);
+    }
     const int64_t per_cta = (h->gws_stride_words + (int64_t)maxnp * 8 + 4) * 4;
     size_t free_b = 0, total_b = 0;
     GX_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -738,6 +764,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
       for (int32_t t : h->class_order[c]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
       pws_stride[c] = ((int64_t)maxnp * 8 + 3) / 4 * 4;
       grids[c] = c == kStreamClass ? stream_grid : std::min<int>(nt, h->num_sms * kClasses[c].ctas_per_sm);
+      const int g_cluster_size = h->plan_cluster;
       if (c == kClusterClass) grids[c] = std::min<int>(nt, h->num_sms / g_cluster_size) * g_cluster_size;   // CTAs; one pair slab per cluster
       pws_off[c] = acc_words;
       acc_words += pws_stride[c] * std::max(c == kClusterClass ? grids[c] / g_cluster_size : grids[c], 0);
@@ -768,7 +795,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     cfg.pws = h->d_pws.as<float>() + pws_off[c];
     cfg.pws_stride_words = pws_stride[c];
     cfg.grid = grids[c];
-    cfg.cluster = c == kClusterClass ? g_cluster_size : 1;
+    cfg.cluster = c == kClusterClass ? h->plan_cluster : 1;
     if (c != kStreamClass) {
       // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)
       int need = 0;
@@ -776,7 +803,15 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
       cfg.smem_bytes = c == kOneClass ? kClasses[c].cap_bytes : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
-    if (c == kStreamClass) GX_CUDA_CHECK(gx_launch_explain_stream(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    if (c == kStreamClass && gang > 0) {
+      cfg.gang = gang;
+      cfg.grid = stream_grid * gang;
+      GX_CUDA_CHECK(h->d_gang.reserve((size_t)stream_grid * 16));
+      GX_CUDA_CHECK(cudaMemsetAsync(h->d_gang.p, 0, (size_t)stream_grid * 16, h->side[c]));
+      cfg.gang_bars = h->d_gang.as<unsigned long long>();
+      cfg.gang_mail = reinterpret_cast<int32_t*>(h->d_gang.as<char>() + (size_t)stream_grid * 8);
+      GX_CUDA_CHECK(gx_launch_explain_gang(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    } else if (c == kStreamClass) GX_CUDA_CHECK(gx_launch_explain_stream(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
     else GX_CUDA_CHECK(gx_launch_explain(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
     h->launches += 1;
     GX_CUDA_CHECK(cudaEventRecord(h->ev_join[c], h->side[c]));

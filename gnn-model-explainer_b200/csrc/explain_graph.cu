@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_graph_kernel(const Grap
         v2 = make_float2(__ldg(A.x.adam_v_in + edge_off + oij), __ldg(A.x.adam_v_in + edge_off + oji));
       }
       MM[p] = make_float2(Mi, Mj); mm[p] = m2; vv[p] = v2;
-      const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
+      // a resumed state came out of the edge phase: same sigmoid as there, so that a split run equals the straight one bit for bit
+      const float Si = resume ? sigmoid_fast(Mi, ieee) : sigmoid_f(Mi), Sj = resume ? sigmoid_fast(Mj, ieee) : sigmoid_f(Mj);
       SS[p] = make_float2(Si, Sj);
       const float a0 = 0.5f * (Si + Sj);
       a[pij] = a0; a[pji] = a0;

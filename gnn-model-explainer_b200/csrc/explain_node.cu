@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         v2 = make_float2(__ldg(A.x.adam_v_in + edge_off + oij), __ldg(A.x.adam_v_in + edge_off + oji));
       }
       const bool mine = CS == 1 || ((p >> 5) % CS) == crank;   // the CTA that owns this pair in the edge phase
-      const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
+      const float Si = resume ? sigmoid_fast(Mi, ieee) : sigmoid_f(Mi), Sj = resume ? sigmoid_fast(Mj, ieee) : sigmoid_f(Mj);   // a resumed state came out of the edge phase: same sigmoid as there, so that a split run equals the straight one bit for bit
       if (mine) {
         MM[p] = make_float2(Mi, Mj);
         mm[p] = m2;
@@ -725,7 +725,7 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
       if (resume) { mi = __ldg(x.adam_m_in + oij); mj = __ldg(x.adam_m_in + oji); vi = __ldg(x.adam_v_in + oij); vj = __ldg(x.adam_v_in + oji); }
       const float yd = (float)__ldg(g.pred_label + lo2gid[i]) - (float)__ldg(g.pred_label + lo2gid[j]);
       const float Gd = 0.5f * (lap_over_nn * yd * yd);
-      float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
+      float Si = resume ? sigmoid_fast(Mi, ieee) : sigmoid_f(Mi), Sj = resume ? sigmoid_fast(Mj, ieee) : sigmoid_f(Mj);
       auto emit = [&]() {
         const float an = 0.5f * (Si + Sj);
         out_mask[oij] = an;

@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(NT, 1) explain_stream_kernel(const ExplainArgs
         MM[p] = make_float2(Mi, Mj);
         mm[p] = m2;
         vv[p] = v2;
-        const float Si = sigmoid_f(Mi), Sj = sigmoid_f(Mj);
+        const float Si = resume ? sigmoid_fast(Mi, ieee) : sigmoid_f(Mi), Sj = resume ? sigmoid_fast(Mj, ieee) : sigmoid_f(Mj);   // a resumed state came out of the edge phase: same sigmoid as there, so that a split run equals the straight one bit for bit
         SS[p] = make_float2(Si, Sj);
         const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
         a[ppij[p]] = a0;

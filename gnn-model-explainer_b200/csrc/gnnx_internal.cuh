@@ -8,6 +8,7 @@
 
 #define GX_MAX_LEVELS 8  // n_hops <= 7
 #define GX_NONE16 0xFFFFu
+#define GX_MAX_GANG 160   // CTAs that may share one task in explain_gang.cu (<= number of SMs)
 #define GX_WP_SMEM_MAX 2048  // floats: pred_model (C x (2h+e) + C) is kept in shared memory up to this size
 
 // One explained node ("task").  Counts are produced by khop_count_kernel, offsets by the host
@@ -165,7 +166,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
 // Global-memory slab of one task in the streaming kernel (explain_stream.cu: tasks whose state does not fit
 // shared memory).  Offsets in 4-byte words; the CSR / pair index arrays are read straight from the plan.
 struct GxStreamLayout {
-  int64_t a, gE, P, dP, Yh1, q1, dY1, Yh2, q2, dZ2, lapg, cnt1, cnt2, gFp;
+  int64_t a, gE, P, dP, Yh1, q1, dY1, Yh2, q2, dZ2, lapg, cnt1, cnt2, gFp, gFb, longlist, trw;
   int64_t total_words;
   int dp;
 };
@@ -185,6 +186,10 @@ __host__ __device__ inline GxStreamLayout gx_make_stream_layout(int n, int n1, i
   L.cnt1 = take(n2);                   // per row < n2: leading columns < n1
   L.cnt2 = take(n);                    // per row: leading columns < n2
   L.gFp = take((int64_t)nwarps * dp);
+  // explain_gang.cu: dL/dsF partials of the 128-node blocks, rows sliced over a whole CTA, per-warp trace partials of a gang
+  L.gFb = take((int64_t)((n + 127) / 128) * dp);
+  L.longlist = take(n);
+  L.trw = take(GX_MAX_GANG * 32 * 4);
   L.total_words = o;
   return L;
 }
@@ -267,6 +272,9 @@ struct GxExplainLaunch {
   int32_t threads;
   int32_t grid;
   int32_t cluster = 1;   // CTAs per task (thread-block cluster size): 1, 2 or 4 (explain_node.cu cluster class)
+  int32_t gang = 1;      // explain_gang.cu: co-resident CTAs per task (grid = gangs * gang)
+  unsigned long long* gang_bars = nullptr;   // [gangs] barrier counters, zeroed
+  int32_t* gang_mail = nullptr;              // [gangs * 2]
   float* gws;            // per-CTA global slab of the streaming class
   int64_t gws_stride_words;
   float* pws;            // per-CTA pair-state slab: 8 floats per inner pair (M,m,v,S of both directions)
@@ -280,6 +288,10 @@ cudaError_t gx_launch_explain(const GxExplainLaunch& cfg, const GxGraphDev& g, c
 cudaError_t gx_launch_explain_stream(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                                      const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                                      float* out_mask, float* out_feat, cudaStream_t s);
+cudaError_t gx_launch_explain_gang(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
+                                   const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
+                                   float* out_mask, float* out_feat, cudaStream_t s);
+int gx_gang_smem_bytes(int d, int hid, int C);
 constexpr int GX_STREAM_THREADS = 768;  // 24 warps: 80 registers per thread, 5 KB of cp.async staging per warp
 int gx_explain_max_smem();
 struct GxGraphBatchDev {

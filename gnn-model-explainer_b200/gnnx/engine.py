@@ -352,6 +352,14 @@ class Engine:
         """Test knob: plan every task into the streaming kernel (explain_stream.cu) regardless of its size."""
         _abi.check(self._lib.gx_debug_force_stream(self._h, int(bool(on))))
 
+    def debug_gang(self, ctas_per_task=0):
+        """Test knob: CTAs per task of the streaming kernel (0 automatic, -1 first-generation kernel)."""
+        _abi.check(self._lib.gx_debug_set_gang(self._h, int(ctas_per_task)))
+
+    def debug_cluster(self, size=0, min_cost=0):
+        """Test knob: cluster size (1/2/4, 0 automatic) and cost threshold of the shared-memory kernel's cluster class."""
+        _abi.check(self._lib.gx_debug_set_cluster(self._h, int(size), int(min_cost)))
+
     def debug_ieee_edge(self, on=True):
         """Test knob: IEEE exp/div/sqrt in the edge phase instead of the hardware approximations."""
         _abi.check(self._lib.gx_debug_ieee_edge(self._h, int(bool(on))))

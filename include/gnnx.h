@@ -244,7 +244,13 @@ int gx_last_explain_ms(gx_handle* h, float* ms);
 /* ---- test / measurement knobs (used by tests/ and tools/ only; they never change what the product computes by default) ----
  * gx_debug_force_stream: plan every task into the streaming kernel (explain_stream.cu) regardless of its size;
  * gx_debug_ieee_edge:    IEEE exp / division / sqrt in the edge phase instead of the ex2/rcp/rsqrt approximations;
- * gx_debug_set_dump:     device buffer (>= 4 MiB) receiving the shared-memory slab of the first task and phase timers. */
+ * gx_debug_set_dump:     device buffer (>= 4 MiB) receiving the shared-memory slab of the first task and phase timers;
+ * gx_debug_set_gang:     CTAs per task of the streaming kernel explain_gang.cu (0 = automatic: the tasks in flight keep their
+ *                        scattered state L2 resident; -1 = the first-generation kernel explain_stream.cu);
+ * gx_debug_set_cluster:  thread-block cluster size (1, 2, 4; 0 = automatic) and cost threshold of the shared-memory kernel's
+ *                        cluster class.  Neither knob changes a single bit of the result (tests/test_gpu_stream.py, test_gpu_cluster.py). */
+int gx_debug_set_gang(gx_handle* h, int ctas_per_task);
+int gx_debug_set_cluster(gx_handle* h, int cluster_size, int64_t min_cost);
 int gx_debug_force_stream(gx_handle* h, int on);
 int gx_debug_ieee_edge(gx_handle* h, int on);
 int gx_debug_set_dump(gx_handle* h, float* dev_buf);

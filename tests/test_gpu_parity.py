@@ -31,9 +31,6 @@ def syn1():
     return util.load_fixture("syn1")
 
 
-def tolerances(name):
-    cond = np.load(util.GOLDEN + "/%s_cond.npz" % name)
-    return {int(n): max(1e-4, 3 * max(a, b)) for n, a, b in zip(cond["nodes"], cond["err_closed64"], cond["err_closed32"])}
 
 
 # ------------------------------------------------------------------------------------ k-hop (integer, bit-exact)
@@ -105,33 +102,26 @@ def test_masks_match_reference_golden_10_epochs(fx):
 
 
 def test_masks_match_reference_golden_30_epochs(fx):
-    """30 epochs: >= 95% of the nodes within 1e-4, every node within 2e-3 (the first chaotic syn1
-    trajectories start to separate here: two nodes sit at 1.3e-4 / 1.4e-4 with this kernel, the fp32
-    closed-form CPU restatement has one at 3e-5)."""
+    """30 epochs, PER NODE: within 1e-4 of the reference wherever the reference itself is reproducible under +-1 ulp input
+    noise (79 of the 81 syn1 nodes, every syn4 / rand node), within 3x the reference's own spread on the two syn1 nodes whose
+    trajectories have started to separate (293, 533: tests/golden/syn1_sens.npz)."""
     errs = _errs_vs(fx, "%s_golden_e30.npz" % fx.name, 30)
-    vals = np.array(list(errs.values()))
-    assert (vals <= 1e-4).mean() >= 0.95, sorted(errs.items(), key=lambda kv: -kv[1])[:8]
-    assert vals.max() < 2e-3, max(errs.items(), key=lambda kv: kv[1])
-    assert np.median(vals) < 2e-6
-    if fx.name != "syn1":
-        assert vals.max() <= 1e-4
+    tol = util.assert_per_node(errs, fx.name, 30)
+    assert sum(t > 1e-4 for t in tol.values()) <= (2 if fx.name == "syn1" else 0)
+    assert np.median(list(errs.values())) < 2e-6
 
 
 def test_masks_match_reference_golden_100_epochs(fx):
-    """Full horizon (the reference default, 100 epochs).  A few syn1 trajectories are chaotic: a relu
-    kink crossed one epoch earlier or later under a different fp summation order moves the final mask
-    by 1e-3..1e-1 (the reference's own result is not reproducible there: tests/golden/*_cond.npz shows
-    two CPU restatements of the same mathematics landing up to 6.6e-2 apart).  Bar: >= 90% of the nodes
-    within the north-star 1e-4, median < 1e-5, every node bounded."""
+    """Full horizon (the reference default, 100 epochs), PER NODE.  Six syn1 trajectories are chaotic (0, 3, 23, 33, 163, 293: a relu
+    kink crossed one epoch earlier or later moves the final mask by 1e-4..7e-2; the bit-exact port of the reference does that to
+    ITSELF when M0 is nudged by one ulp, tests/golden/syn1_sens.npz): there the bar is 3x the reference's own spread.  Every other
+    node -- 73 of 81 on syn1 (two more sit at 3.6e-5 / 5.2e-5 spread), all of syn4 and rand -- must be within the north-star 1e-4."""
     plan, out = _run_golden(fx, 100)
     errs = {node: util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], fx.gold["n%d_mask" % node])
             for t, node in enumerate(fx.nodes)}
-    vals = np.array(list(errs.values()))
-    assert (vals <= 1e-4).mean() >= 0.9, sorted(errs.items(), key=lambda kv: -kv[1])[:10]
-    assert np.median(vals) < 1e-5
-    assert vals.max() < 0.2, max(errs.items(), key=lambda kv: kv[1])
-    if fx.name != "syn1":
-        assert vals.max() <= 1e-4          # syn4 / rand: no chaotic node
+    tol = util.assert_per_node(errs, fx.name, 100)
+    assert sum(t > 1e-4 for t in tol.values()) <= (8 if fx.name == "syn1" else 0)
+    assert np.median(list(errs.values())) < 1e-5
 
 
 def _random_case(seed, n_nodes, m, d, C, graph="ba"):

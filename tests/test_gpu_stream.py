@@ -18,21 +18,41 @@ def _stream_engine(fx):
     return eng
 
 
-@pytest.mark.parametrize("name,epochs,golden", [("syn1", 10, "syn1_golden_e10.npz"), ("syn4", 30, "syn4_golden_e30.npz"),
-                                                 ("rand", 30, "rand_golden_e30.npz")])
-def test_stream_matches_reference_golden(name, epochs, golden):
+@pytest.mark.parametrize("gang", [0, -1], ids=["gang", "stream1"])
+@pytest.mark.parametrize("name,epochs,golden", [("syn1", 10, "syn1_golden_e10.npz"), ("syn1", 30, "syn1_golden_e30.npz"), ("syn1", 100, "syn1_golden.npz"),
+                                                 ("syn4", 30, "syn4_golden_e30.npz"), ("syn4", 100, "syn4_golden.npz"), ("rand", 30, "rand_golden_e30.npz")])
+def test_stream_matches_reference_golden(name, epochs, golden, gang):
+    """Both streaming kernels (explain_gang.cu and the first-generation explain_stream.cu) against the reference goldens, per node
+    (util.node_tolerances: 1e-4 wherever the reference itself is reproducible)."""
     fx = util.load_fixture(name)
     g = np.load(util.GOLDEN + "/" + golden)
     eng = _stream_engine(fx)
+    eng.debug_gang(gang)
     plan = eng.plan_nodes(fx.nodes, 3)
     out = np.zeros(plan.total_edges, np.float32)
     eng.explain_nodes_host(eng.make_hparams(num_epochs=epochs), util.golden_m0(fx, plan), out)
     eng.close()
     errs = {node: util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], g["n%d_mask" % node]) for t, node in enumerate(fx.nodes)}
-    vals = np.array(list(errs.values()))
-    if epochs == 10 or name != "syn1":
-        assert vals.max() <= 1e-4, sorted(errs.items(), key=lambda kv: -kv[1])[:8]
-    assert np.median(vals) < 2e-6
+    util.assert_per_node(errs, name, epochs)
+    assert np.median(list(errs.values())) < 2e-6
+
+
+def test_gang_size_does_not_change_a_bit():
+    """explain_gang.cu: the number of CTAs that share a task is a scheduling decision -- masks and feature masks are
+    bit-identical for 1, 3, 16 CTAs per task and the automatic choice (what keeps sharded multi-GPU runs bit-identical)."""
+    fx = util.load_fixture("rand")
+    res = []
+    for gang in (1, 3, 16, 0):
+        eng = _stream_engine(fx)
+        eng.debug_gang(gang)
+        plan = eng.plan_nodes(fx.nodes, 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        fm = np.zeros((plan.count, fx.feat.shape[1]), np.float32)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=12), util.golden_m0(fx, plan), out, fm)
+        eng.close()
+        res.append((out, fm))
+    for out, fm in res[1:]:
+        assert np.array_equal(out, res[0][0]) and np.array_equal(fm, res[0][1])
 
 
 @pytest.mark.parametrize("seed,n_nodes,m,d,C,graph", [
