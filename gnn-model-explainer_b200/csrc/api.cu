@@ -305,11 +305,10 @@ int gx_last_explain_ms(gx_handle* h, float* ms) {
 int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* conv_w,
                  const float* const* conv_b, const float* pred_w, const float* pred_b) {
   if (!h || !dims || !conv_w || !pred_w || !pred_b) { gx_set_error("gx_set_model: NULL argument"); return GX_ERR_INVALID; }
-  if (dims->num_layers != 3) {
-    gx_set_error("gx_set_model: num_layers=%d; this build implements the reference default num_gc_layers=3", dims->num_layers);
+  if (dims->num_layers < 2 || dims->num_layers > GX_MAX_LAYERS) {
+    gx_set_error("gx_set_model: num_layers=%d outside [2,%d]", dims->num_layers, GX_MAX_LAYERS);
     return GX_ERR_UNSUPPORTED;
   }
-  if (dims->flags & GX_MODEL_BN) { gx_set_error("gx_set_model: --bn (models.py:222-228) is not built"); return GX_ERR_UNSUPPORTED; }
   if (dims->hidden_dim < 1 || dims->embed_dim < 1 || dims->hidden_dim > 32 || dims->embed_dim > 32) {
     gx_set_error("gx_set_model: hidden_dim=%d output_dim=%d; this build supports widths up to 32", dims->hidden_dim, dims->embed_dim);
     return GX_ERR_UNSUPPORTED;
@@ -320,6 +319,38 @@ int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* co
   }
   if (dims->num_classes < 1) { gx_set_error("gx_set_model: num_classes < 1"); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
+  if (dims->num_layers != 3 || (dims->flags & GX_MODEL_BN)) {
+    // Model variant (num_gc_layers 2 / 4, --bn): explain_var.cu, true widths (a zero-padded column would enter the bn statistics).
+    const int L = dims->num_layers, d = dims->input_dim, hid0 = dims->hidden_dim, emb0 = dims->embed_dim, C = dims->num_classes;
+    if (gx_var_smem_bytes(d, L, hid0, emb0, C) > gx_explain_max_smem()) { gx_set_error("gx_set_model: model variant does not fit shared memory"); return GX_ERR_UNSUPPORTED; }
+    std::vector<float> host;
+    size_t offW[GX_MAX_LAYERS], offb[GX_MAX_LAYERS];
+    auto al4 = [&]() { while (host.size() % 4) host.push_back(0.f); };
+    for (int l = 0; l < L; ++l) {
+      if (!conv_w[l]) { gx_set_error("gx_set_model: conv_w[%d] is NULL", l); return GX_ERR_INVALID; }
+      const int win = l == 0 ? d : hid0, wout = l == L - 1 ? emb0 : hid0;
+      al4(); offW[l] = host.size();
+      host.insert(host.end(), conv_w[l], conv_w[l] + (size_t)win * wout);
+      al4(); offb[l] = host.size();
+      for (int c = 0; c < wout; ++c) host.push_back((conv_b && conv_b[l]) ? conv_b[l][c] : 0.f);
+    }
+    const int PD0 = hid0 * (L - 1) + emb0;
+    al4(); const size_t offWp = host.size();
+    host.insert(host.end(), pred_w, pred_w + (size_t)C * PD0);
+    al4(); const size_t offbp = host.size();
+    host.insert(host.end(), pred_b, pred_b + C);
+    GX_CUDA_CHECK(h->m_buf.reserve(host.size() * 4));
+    GX_CUDA_CHECK(cudaMemcpyAsync(h->m_buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    float* b = h->m_buf.as<float>();
+    h->m = GxModelDev{};
+    h->m.d = d; h->m.hid = hid0; h->m.emb = emb0; h->m.C = C; h->m.L = L;
+    h->m.bn = (dims->flags & GX_MODEL_BN) ? 1 : 0; h->m.variant = 1;
+    for (int l = 0; l < L; ++l) { h->m.W[l] = b + offW[l]; h->m.Wt[l] = nullptr; h->m.b[l] = b + offb[l]; }
+    h->m.Wp = b + offWp; h->m.bp = b + offbp;
+    h->has_model = true; h->has_plan = false;
+    return GX_OK;
+  }
   // The kernels are instantiated for the reference default 20/20 and for 32/32; any other width <= 32 is
   // zero-padded to 32.  Padding is exact: a padded output column is 0*W + 0 = 0, contributes nothing to the
   // row norm, stays 0 through normalise/ReLU, and its pred_model column is 0 (forward and backward).
@@ -355,6 +386,7 @@ int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* co
   GX_CUDA_CHECK(cudaMemcpyAsync(h->m_buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, h->stream));
   GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float* b = h->m_buf.as<float>();
+  h->m = GxModelDev{};
   h->m.d = d; h->m.hid = hid; h->m.emb = emb; h->m.C = C; h->m.L = 3;
   for (int l = 0; l < 3; ++l) { h->m.W[l] = b + offW[l]; h->m.Wt[l] = b + offWt[l]; h->m.b[l] = b + offb[l]; }
   h->m.Wp = b + offWp;
@@ -483,14 +515,17 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
     tn += T.n; te += T.e_d; tp += T.npairs;
     int bytes = 0;
-    int cls = task_smem_class(T, h->m, h->force_stream, &bytes);
+    int cls = h->m.variant ? kStreamClass : task_smem_class(T, h->m, h->force_stream, &bytes);
+    if (h->m.variant) bytes = 0;
     if (cls < kStreamClass && g_cluster_size > 1 && cost(t) > g_cluster_cost) {
       // expensive task: one thread-block cluster (explain_node.cu, CS CTAs share the rows and pairs); decided by the task alone
       const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, h->m.d, h->m.hid, h->m.emb, h->m.C, kClasses[kClusterClass].threads / 32, 2, g_cluster_size);
       if ((int64_t)L.total_words * 4 <= kClasses[kClusterClass].cap_bytes) { cls = kClusterClass; bytes = L.total_words * 4; }
     }
     T.smem_bytes = bytes;
-    if (cls == kStreamClass)
+    if (cls == kStreamClass && h->m.variant)
+      gws_words = std::max<int64_t>(gws_words, gx_make_var_layout(T.n, T.n2, T.e1, T.npairs_in, h->m.d, h->m.L).total_words);
+    else if (cls == kStreamClass)
       gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, T.npairs_in, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
     h->class_order[cls].push_back(t);
   }
@@ -709,6 +744,10 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   // moves it and the result equals the default run bit for bit (explain.py:657-660,673-676; same test): accepted, no extra state.
   if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_nodes: num_epochs < 1"); return GX_ERR_INVALID; }
+  if (h->m.variant && (mode != 0 || hp->init == GX_INIT_STATE || (io && (io->trace || io->trace_pred || io->adam_m_out || io->adam_v_out || io->mask_param_out || io->feat_state_out)))) {
+    gx_set_error("gx_explain_nodes: model variants (num_layers != 3 / --bn) build the mask optimisation only (no trace, optimiser state or gradient baseline)");
+    return GX_ERR_UNSUPPORTED;
+  }
   if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX && hp->init != GX_INIT_STATE) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   const int count = h->count;
@@ -733,7 +772,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     int maxnp = 0;
     for (int32_t t : h->class_order[kStreamClass]) maxnp = std::max(maxnp, h->tasks[t].npairs_in);
     const int gang_env = h->gang_override;
-    if (gang_env >= 0 && h->m.d <= 128 && gx_gang_smem_bytes(h->m.d, h->m.hid, h->m.C) <= gx_explain_max_smem()) {
+    if (!h->m.variant && gang_env >= 0 && h->m.d <= 128 && gx_gang_smem_bytes(h->m.d, h->m.hid, h->m.C) <= gx_explain_max_smem()) {
       // explain_gang.cu: G co-resident CTAs per task.  As many tasks in flight as keep their randomly accessed state
       // (a, gE: 8 B per directed edge; P, dP, dY1: 240 B per node) inside the L2, the SMs divided evenly among them.
       int64_t ws = 1;
@@ -803,7 +842,9 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
       cfg.smem_bytes = c == kOneClass ? kClasses[c].cap_bytes : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
-    if (c == kStreamClass && gang > 0) {
+    if (c == kStreamClass && h->m.variant) {
+      GX_CUDA_CHECK(gx_launch_explain_var(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
+    } else if (c == kStreamClass && gang > 0) {
       cfg.gang = gang;
       cfg.grid = stream_grid * gang;
       GX_CUDA_CHECK(h->d_gang.reserve((size_t)stream_grid * 16));
@@ -929,6 +970,7 @@ int gx_set_graph_batch_csr(gx_handle* h, int32_t G, int32_t max_nodes, const int
 int gx_plan_graphs(gx_handle* h, const int32_t* graph_ids, int32_t count, int64_t* edge_off, int64_t* total_edges) {
   if (!h || !graph_ids) { gx_set_error("gx_plan_graphs: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_batch || !h->has_model) { gx_set_error("gx_plan_graphs: call gx_set_model and gx_set_graph_batch_csr first"); return GX_ERR_INVALID; }
+  if (h->m.variant) { gx_set_error("gx_plan_graphs: graph mode builds the default model only (3 layers, no --bn)"); return GX_ERR_UNSUPPORTED; }
   if (h->gb.d != h->m.d) { gx_set_error("gx_plan_graphs: feat_dim %d != model input_dim %d", h->gb.d, h->m.d); return GX_ERR_INVALID; }
   if (count <= 0) { gx_set_error("gx_plan_graphs: count <= 0"); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));

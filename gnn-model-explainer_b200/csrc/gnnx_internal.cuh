@@ -8,6 +8,7 @@
 
 #define GX_MAX_LEVELS 8  // n_hops <= 7
 #define GX_NONE16 0xFFFFu
+#define GX_MAX_LAYERS 4  // num_gc_layers of a model variant (explain_var.cu); the tuned kernels build the reference default 3
 #define GX_MAX_GANG 160   // CTAs that may share one task in explain_gang.cu (<= number of SMs)
 #define GX_WP_SMEM_MAX 2048  // floats: pred_model (C x (2h+e) + C) is kept in shared memory up to this size
 
@@ -66,9 +67,11 @@ struct GxGraphDev {
 
 struct GxModelDev {
   int32_t d, hid, emb, C, L;
-  const float* W[3];   // row-major (in,out)
-  const float* Wt[3];  // row-major (out,in)
-  const float* b[3];   // never NULL on device (zeros when --nobias)
+  int32_t bn;          // --bn: per-node standardisation after every hidden ReLU (models.py:222-228)
+  int32_t variant;     // 1: num_layers != 3 or bn -> every task runs in explain_var.cu with the UNPADDED widths hid / emb
+  const float* W[GX_MAX_LAYERS];   // row-major (in,out)
+  const float* Wt[GX_MAX_LAYERS];  // row-major (out,in) (default model only)
+  const float* b[GX_MAX_LAYERS];   // never NULL on device (zeros when --nobias)
   const float* Wp;     // (C, 2*hid+emb)
   const float* bp;
 };
@@ -194,6 +197,30 @@ __host__ __device__ inline GxStreamLayout gx_make_stream_layout(int n, int n1, i
   return L;
 }
 
+// Global-memory slab of one task in the model-variant kernel (explain_var.cu); every hidden-width array has row stride 32.
+struct GxVarLayout {
+  int64_t a, U, dZ1, lapg, Yh, H, dZ, q, istd;
+  int64_t total_words;
+};
+__host__ __device__ inline GxVarLayout gx_make_var_layout(int n, int n2, int e1, int np_in, int d, int L) {
+  GxVarLayout Lo;
+  const int dp = gx_round_up(d, 4);
+  int64_t o = 0;
+  auto take = [&](int64_t words) { int64_t r = o; o += (words + 3) / 4 * 4; return r; };
+  (void)n;
+  Lo.a = take(e1);                            // masked adjacency of the rows the forward visits (level-order rows < n2)
+  Lo.U = take((int64_t)n2 * dp);              // A_m X
+  Lo.dZ1 = take((int64_t)n2 * dp);            // dL/d(A_m X') (.) sigmoid(feat_mask)
+  Lo.lapg = take(np_in);
+  Lo.Yh = take((int64_t)L * n2 * 32);         // per layer: normalised pre-activations
+  Lo.H = take((int64_t)L * n2 * 32);          // per layer: relu (+ standardisation) output = input of the next layer / the readout
+  Lo.dZ = take((int64_t)(L - 1) * n2 * 32);   // layers 2..L: dL/d(A_m H_{l-1})
+  Lo.q = take((int64_t)L * n2);
+  Lo.istd = take((int64_t)L * n2);
+  Lo.total_words = o;
+  return Lo;
+}
+
 // Shared-memory footprint of one graph-mode task (all `na` rows with at least one edge are computed at every layer).
 struct GxLayoutG {
   int X, U, Yh1, Yh2, Yh3, q, dZ2, dZ3, a, W1s, W1t, W2s, W2t, W3s, W3t, bs, cst, emb, dE, sF, F, mF, vF, gFp, zs, logit, Wp;
@@ -292,6 +319,10 @@ cudaError_t gx_launch_explain_gang(const GxExplainLaunch& cfg, const GxGraphDev&
                                    const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                                    float* out_mask, float* out_feat, cudaStream_t s);
 int gx_gang_smem_bytes(int d, int hid, int C);
+cudaError_t gx_launch_explain_var(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
+                                  const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
+                                  float* out_mask, float* out_feat, cudaStream_t s);
+int gx_var_smem_bytes(int d, int L, int hid, int emb, int C);
 constexpr int GX_STREAM_THREADS = 768;  // 24 warps: 80 registers per thread, 5 KB of cp.async staging per warp
 int gx_explain_max_smem();
 struct GxGraphBatchDev {

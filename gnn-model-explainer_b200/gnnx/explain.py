@@ -92,13 +92,14 @@ class Explainer:
         # masks equal the default run bit for bit (explain.py:657-660,673-676; pinned by tests/test_oracle.py) -- no extra state needed.
         if getattr(args, "opt", "adam") != "adam" or getattr(args, "opt_scheduler", "none") != "none":
             raise NotImplementedError("only Adam without scheduler (explainer_main.py defaults) is built")
-        if getattr(model, "bn", False):
-            raise NotImplementedError("--bn models are not built")
+        bn = bool(getattr(model, "bn", False))
+        if bn and graph_mode:
+            raise NotImplementedError("--bn is built for node tasks only")
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() else 0
         self.engine = Engine(device)
         weights, num_layers = model_weights(model)
-        self.engine.set_model(weights, num_layers=num_layers)
+        self.engine.set_model(weights, num_layers=num_layers, bn=bn)
         adj_np = np.asarray(adj)
         if graph_mode:
             # graph classification: the whole padded batch goes to the device once (explain.py:80-85)

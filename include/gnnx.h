@@ -47,10 +47,11 @@ typedef struct gx_model_dims {
   int32_t hidden_dim;  /* output width of conv_first / conv_block[*]    */
   int32_t embed_dim;   /* output width of conv_last                     */
   int32_t num_classes; /* label_dim                                     */
-  int32_t num_layers;  /* num_gc_layers; this build: 3                  */
+  int32_t num_layers;  /* num_gc_layers: 2, 3 (reference default) or 4    */
   int32_t flags;       /* GX_MODEL_* bits                               */
 } gx_model_dims;
-#define GX_MODEL_BN 1u /* args.bn (models.py:222-228): GX_ERR_UNSUPPORTED in this build */
+#define GX_MODEL_BN 1u /* args.bn (models.py:222-228): per-node standardisation after every hidden ReLU.  num_layers != 3 or bn
+                        * select the model-variant kernel (node mode, mask optimisation only: no trace / optimiser state / grad) */
 
 /* Optimisation hyper-parameters: explainer_main.py:143-167 defaults + ExplainModule.coeffs
  * (explainer/explain.py:624-631) + torch.optim.Adam defaults (utils/train_utils.py:10). */
