@@ -193,7 +193,11 @@ void gx_default_hparams(gx_hparams* hp) {
   hp->init = GX_INIT_M0;
   hp->seed = 0;
   hp->start_step = 0;
-  hp->reserved = 0;
+  hp->opt = GX_OPT_ADAM;
+  hp->opt_scheduler = GX_SCHED_NONE;
+  hp->opt_decay_step = 0;
+  hp->opt_decay_rate = 1.0f;
+  hp->opt_restart = 0;
 }
 
 int gx_create(int device, gx_handle** out) {
@@ -702,15 +706,33 @@ int io_finish(gx_handle* h, const gx_hparams* hp, gx_memspace space, const gx_ex
   return GX_OK;
 }
 
-// Adam bias-correction table in double, exactly as torch's python scalars (torch/optim/adam.py), for steps start+1 .. start+iters
+// Per-step table for steps start+1 .. start+iters, in double like torch's python scalars: the epoch's learning rate under the
+// scheduler (StepLR / CosineAnnealingLR are stepped once per epoch AFTER the optimiser, explain.py:144-146, so step t runs with the
+// rate after t-1 scheduler steps) and, for Adam, the bias corrections (torch/optim/adam.py): (lr_t / (1-b1^t), sqrt(1-b2^t)).
+int check_optimiser(const char* who, const gx_hparams* hp) {
+  if (hp->opt < GX_OPT_ADAM || hp->opt > GX_OPT_ADAGRAD) { gx_set_error("%s: unknown optimiser %d", who, hp->opt); return GX_ERR_INVALID; }
+  if (hp->opt_scheduler < GX_SCHED_NONE || hp->opt_scheduler > GX_SCHED_COS) { gx_set_error("%s: unknown scheduler %d", who, hp->opt_scheduler); return GX_ERR_INVALID; }
+  if (hp->opt_scheduler == GX_SCHED_STEP && hp->opt_decay_step < 1) { gx_set_error("%s: step scheduler needs opt_decay_step >= 1", who); return GX_ERR_INVALID; }
+  if (hp->opt_scheduler == GX_SCHED_COS && hp->opt_restart < 1) { gx_set_error("%s: cos scheduler needs opt_restart >= 1", who); return GX_ERR_INVALID; }
+  return GX_OK;
+}
 int upload_adam_table(gx_handle* h, const gx_hparams* hp, int iters, int start) {
   std::vector<float2> tab(std::max(iters, 1));
   for (int k = 1; k <= iters; ++k) {
     const double t = (double)(start + k);
-    const double bc1 = 1.0 - std::pow((double)hp->beta1, t);
-    const double bc2 = 1.0 - std::pow((double)hp->beta2, t);
-    tab[k - 1].x = (float)((double)hp->lr / bc1);
-    tab[k - 1].y = (float)std::sqrt(bc2);
+    const double e = t - 1.0;   // scheduler steps taken so far
+    double lr = (double)hp->lr;
+    if (hp->opt_scheduler == GX_SCHED_STEP) lr *= std::pow((double)hp->opt_decay_rate, std::floor(e / (double)hp->opt_decay_step));
+    else if (hp->opt_scheduler == GX_SCHED_COS) lr *= 0.5 * (1.0 + std::cos(3.14159265358979323846 * e / (double)hp->opt_restart));
+    if (hp->opt == GX_OPT_ADAM) {
+      const double bc1 = 1.0 - std::pow((double)hp->beta1, t);
+      const double bc2 = 1.0 - std::pow((double)hp->beta2, t);
+      tab[k - 1].x = (float)(lr / bc1);
+      tab[k - 1].y = (float)std::sqrt(bc2);
+    } else {
+      tab[k - 1].x = (float)lr;
+      tab[k - 1].y = 1.0f;
+    }
   }
   GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
   // pageable source: the copy is staged before the call returns, the vector may go out of scope
@@ -730,6 +752,7 @@ void fill_hparams(const gx_handle* h, const gx_hparams* hp, int mode, bool trace
   hd->init = hp->init;
   hd->flags = h->ieee_edge ? GX_HP_IEEE_EDGE : 0;
   hd->mode = mode;
+  hd->opt = hp->opt;
   hd->seed = hp->seed;
 }
 
@@ -744,8 +767,10 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   // moves it and the result equals the default run bit for bit (explain.py:657-660,673-676; same test): accepted, no extra state.
   if (hp->mask_act != 0) { gx_set_error("gx_explain_nodes: mask_act != sigmoid is not built (the reference's ReLU variant returns NaN masks)"); return GX_ERR_UNSUPPORTED; }
   if (hp->num_epochs < 1) { gx_set_error("gx_explain_nodes: num_epochs < 1"); return GX_ERR_INVALID; }
-  if (h->m.variant && (mode != 0 || hp->init == GX_INIT_STATE || (io && (io->trace || io->trace_pred || io->adam_m_out || io->adam_v_out || io->mask_param_out || io->feat_state_out)))) {
-    gx_set_error("gx_explain_nodes: model variants (num_layers != 3 / --bn) build the mask optimisation only (no trace, optimiser state or gradient baseline)");
+  { const int orc = check_optimiser("gx_explain_nodes", hp); if (orc != GX_OK) return orc; }
+  const bool all_var = h->m.variant || hp->opt != GX_OPT_ADAM;   // every task through explain_var.cu
+  if (all_var && (mode != 0 || hp->init == GX_INIT_STATE || (io && (io->trace || io->trace_pred || io->adam_m_out || io->adam_v_out || io->mask_param_out || io->feat_state_out)))) {
+    gx_set_error("gx_explain_nodes: model variants (num_layers != 3 / --bn) and optimisers other than Adam build the mask optimisation only (no trace, optimiser state or gradient baseline)");
     return GX_ERR_UNSUPPORTED;
   }
   if (hp->init != GX_INIT_M0 && hp->init != GX_INIT_PHILOX && hp->init != GX_INIT_STATE) { gx_set_error("gx_explain_nodes: unknown init %d", hp->init); return GX_ERR_INVALID; }
@@ -764,6 +789,32 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   float* out_dev = D.out;
   float* feat_dev = D.feat;
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
+  if (all_var && !h->m.variant) {
+    // default model, optimiser other than Adam: the whole batch in one launch of the variant kernel (+ the outer-pair recurrences)
+    if (gx_var_smem_bytes(h->m.d, h->m.L, h->m.hid, h->m.emb, h->m.C) > gx_explain_max_smem()) { gx_set_error("gx_explain_nodes: model does not fit the variant kernel"); return GX_ERR_UNSUPPORTED; }
+    int64_t words = 4; int maxnp = 0;
+    for (const GxTask& T : h->tasks) {
+      words = std::max<int64_t>(words, gx_make_var_layout(T.n, T.n2, T.e1, T.npairs_in, h->m.d, h->m.L).total_words);
+      maxnp = std::max(maxnp, T.npairs_in);
+    }
+    const int grid = std::min(count, h->num_sms * 4);
+    const int64_t pstride = ((int64_t)maxnp * 8 + 3) / 4 * 4 + 4;
+    GX_CUDA_CHECK(h->d_gws.reserve((size_t)grid * words * 4));
+    GX_CUDA_CHECK(h->d_pws.reserve((size_t)grid * pstride * 4));
+    GX_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->stream));
+    GxExplainLaunch cfg;
+    cfg.order = h->d_order.as<int32_t>(); cfg.ntasks = count; cfg.counter = h->d_counters.as<int32_t>();
+    cfg.smem_bytes = 0; cfg.threads = 0; cfg.grid = grid;
+    cfg.gws = h->d_gws.as<float>(); cfg.gws_stride_words = words;
+    cfg.pws = h->d_pws.as<float>(); cfg.pws_stride_words = pstride;
+    cfg.dbg = nullptr; cfg.x = D.x;
+    GX_CUDA_CHECK(gx_launch_explain_var(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->stream));
+    GX_CUDA_CHECK(gx_launch_outer_pairs(hd, h->g, h->plan, count, m0_dev, out_dev, D.x, h->stream));
+    h->launches += 2;
+    GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
+    h->timed = true;
+    return io_finish(h, hp, space, io, count, te, h->m.d, h->m.C, D);
+  }
   int stream_grid = 0;   // slabs of the streaming class = tasks in flight (CTAs of explain_stream.cu / gangs of explain_gang.cu)
   int gang = 0;          // > 0: explain_gang.cu with this many CTAs per task
   if (!h->class_order[kStreamClass].empty()) {
@@ -908,7 +959,10 @@ int gx_offedge_regularisers(gx_handle* h, const gx_hparams* hp, gx_memspace spac
   GX_CUDA_CHECK(cudaMemcpyAsync(h->d_dense_off.p, doff.data(), (size_t)(count + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   GxHparamsDev hd;
   fill_hparams(h, hp, 0, false, &hd);
-  int rc = upload_adam_table(h, hp, E, 0);
+  if (hp->opt != GX_OPT_ADAM) { gx_set_error("gx_offedge_regularisers: the off-edge trajectories are built for Adam only"); return GX_ERR_UNSUPPORTED; }
+  int rc = check_optimiser("gx_offedge_regularisers", hp);
+  if (rc != GX_OK) return rc;
+  rc = upload_adam_table(h, hp, E, 0);
   if (rc != GX_OK) return rc;
   hd.adam_tab = h->d_adam.as<float2>();
   const float* m0d = m0_dense;
@@ -1043,6 +1097,9 @@ static int explain_graphs_impl(gx_handle* h, const gx_hparams* hp, gx_memspace s
   int rc = io_prepare(h, "gx_explain_graphs", hp, 0, space, io, count, te, h->m.d, h->m.C, &D);
   if (rc != GX_OK) return rc;
   D.x.tr_outer = nullptr;   // graph mode has no outer pairs
+  rc = check_optimiser("gx_explain_graphs", hp);
+  if (rc != GX_OK) return rc;
+  if (hp->opt != GX_OPT_ADAM) { gx_set_error("gx_explain_graphs: graph mode builds Adam only (the schedulers work)"); return GX_ERR_UNSUPPORTED; }
   GxHparamsDev hd;
   fill_hparams(h, hp, 0, D.x.trace != nullptr, &hd);
   hd.c_lap = 0.f;           // lap_loss = 0 in graph mode (explain.py:787-788)

@@ -34,6 +34,15 @@ __device__ __forceinline__ float adam_delta_fast(float m, float v, float step, f
   return ieee ? step * (m / (sqrtf(v) / bc2s + eps)) : step * __fdividef(m, fmaf(__fsqrt_rn(v), bc2s_inv, eps));
 }
 
+// One optimiser step on a scalar parameter for the optimisers other than Adam (utils/train_utils.py:11-16 with torch's defaults):
+// SGD(momentum 0.95): buf = 0.95 buf + g (= g at the first step, buf starts at 0); RMSprop(alpha 0.99, eps 1e-8); Adagrad(eps 1e-10).
+// m = momentum buffer, v = squared-gradient accumulator, lr = this epoch's learning rate (scheduler applied on the host).
+__device__ __forceinline__ void opt_step_other(int opt, float& P, float g, float& m, float& v, float lr) {
+  if (opt == GX_OPT_SGD) { m = fmaf(0.95f, m, g); P -= lr * m; }
+  else if (opt == GX_OPT_RMSPROP) { v = fmaf(0.99f, v, 0.01f * g * g); P -= lr * (g / (sqrtf(v) + 1e-8f)); }
+  else { v = fmaf(g, g, v); P -= lr * (g / (sqrtf(v) + 1e-10f)); }
+}
+
 // Philox4x32-10 (Salmon et al. 2011), used only for GX_INIT_PHILOX.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t* out) {

@@ -24,7 +24,7 @@ namespace {
 
 constexpr int kGangThreads = 512;    // 16 warps, 128 registers per thread (the tensor-core passes hold 24 A fragments + 32 accumulators)
 constexpr int kDenseWarps = 6;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
-constexpr int kLongEdges = 1024;     // rows with more edges are sliced over all warps of one CTA
+constexpr int kLongEdges = 512;      // rows with more edges are sliced over all warps of one CTA
 constexpr int kBlockTiles = 8;       // dL/dsF is reduced over fixed blocks of 8 tiles (128 nodes): independent of the gang size
 
 struct GangSmem {
@@ -128,21 +128,33 @@ __device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const in
   const bool act = es < EPL;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* const src_q = src + 4 * q;
+  // software pipeline: the indices / values of step k+1 are loaded while the gathers of step k are in flight, so a step costs one
+  // memory latency instead of two (the loop is latency bound: 16 warps x 24 edges in flight per SM)
+  int cn[UN];
+  float an[UN];
+#pragma unroll
+  for (int k = 0; k < UN; ++k) {
+    const int ek = r0 + es + k * EPL;
+    const bool ok = act && ek < r1;
+    cn[k] = ok ? __ldg(icol + ek) : -1;
+    an[k] = ok ? __ldcg(a + ek) : 0.f;
+  }
 #pragma unroll 1
   for (int e = r0 + es; e - es < r1; e += UN * EPL) {
     int c[UN];
     float av[UN];
     float4 v[UN];
-    bool ok[UN];
+#pragma unroll
+    for (int k = 0; k < UN; ++k) { c[k] = cn[k]; av[k] = an[k]; }
+#pragma unroll
+    for (int k = 0; k < UN; ++k) v[k] = c[k] >= 0 ? ldcg4(src_q + (size_t)c[k] * HID) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < UN; ++k) {
-      const int ek = e + k * EPL;
-      ok[k] = act && ek < r1;
-      c[k] = ok[k] ? __ldg(icol + ek) : 0;
-      av[k] = ok[k] ? __ldcg(a + ek) : 0.f;
+      const int ek = e + (UN + k) * EPL;
+      const bool ok = act && ek < r1;
+      cn[k] = ok ? __ldg(icol + ek) : -1;
+      an[k] = ok ? __ldcg(a + ek) : 0.f;
     }
-#pragma unroll
-    for (int k = 0; k < UN; ++k) v[k] = ok[k] ? ldcg4(src_q + (size_t)c[k] * HID) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < UN; ++k) {
       if (kRelu) v[k] = relu4(v[k]);
@@ -156,7 +168,7 @@ __device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const in
           const float t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
           pd = t2 + __shfl_down_sync(0xffffffffu, pd, 4);
         }
-        if (ok[k] && q == 0) gout[e + k * EPL] = pd;
+        if (c[k] >= 0 && q == 0) gout[e + k * EPL] = pd;
       }
     }
   }
@@ -190,7 +202,7 @@ __device__ __forceinline__ float4 slot_reduce(float4 z) {
 template <int HID, bool kRelu, bool kDot, typename Bounds, typename Epi>
 __device__ __forceinline__ void row_pass(int R, int G, int grank, int warp, int nwarps, int lane, const int32_t* __restrict__ irp,
                                          const int32_t* __restrict__ icol, const float* a, const float* src, const float* dotsrc, float* gout,
-                                         const int32_t* longlist, int nlong, float* part, Bounds bounds, Epi epi) {
+                                         const int32_t* longlist, int nlong, float* part, int* row_ctr, Bounds bounds, Epi epi) {
   constexpr int H4 = HID / 4, EPL = 32 / H4;
   const int q = lane % H4;
   // long rows of this CTA
@@ -215,9 +227,16 @@ __device__ __forceinline__ void row_pass(int R, int G, int grank, int warp, int 
     }
     __syncthreads();
   }
-  // everything else: one warp per row, consecutive rows on different CTAs
-  const int gnw = nwarps * G;
-  for (int i = warp * G + grank; i < R; i += gnw) {
+  // everything else: one warp per row.  Row i belongs to CTA i mod G; inside the CTA the warps draw the next row from a shared
+  // counter (rows are sorted by degree inside a level, so this is longest-first scheduling; a row's result does not depend on
+  // which warp takes it).
+  (void)nwarps;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(row_ctr, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    const int i = k * G + grank;
+    if (i >= R) break;
     if (nlong > 0 && irp[i + 1] - irp[i] > kLongEdges) continue;
     int r0, r1;
     bounds(i, r0, r1);
@@ -414,6 +433,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_tr[kTrace ? 8 : 1];
   __shared__ long long s_ph[11];   // debug: per-phase cycle sums of the first task + last stamp
+  __shared__ int s_rowctr[4];      // next row of this CTA in each of the four sparse passes of an epoch
   static_assert((HID == 20 || HID == 32) && EMB == HID, "hidden width 20 or 32 (others are zero-padded to 32 by gx_set_model)");
   constexpr int HS = HID, H4 = HID / 4, PD = 2 * HID + EMB, NT = kGangThreads;
   constexpr int nwarps = NT / 32;
@@ -580,6 +600,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     if (timed && warp == 0) { const long long c_ = clock64(); if (lane == 0) { for (int k = 0; k < 10; ++k) s_ph[k] = 0; s_ph[10] = c_; } __syncwarp(); }
     for (int it = 1; it <= hp.iters; ++it) {
       // ---- F0: all nodes: P = (X . sigmoid(feat_mask)) W1 on the tensor cores               (explain.py:707, models.py:70-71)
+      if (tid < 4) s_rowctr[tid] = 0;
       for (int idx = tid; idx < dp * HID; idx += NT) {   // fold the feature mask into W1, split into tf32 hi / lo
         const int f = idx / HID, c = idx - f * HID;
         uint32_t hi, lo;
@@ -591,7 +612,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(0)
       // ---- F1: rows [0,n2): Y1 = A_m P + b1 ; row normalise                                   (models.py:70-78)
-      row_pass<HID, false, false>(n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part,
+      row_pass<HID, false, false>(n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part, s_rowctr + 0,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -604,7 +625,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
-      row_pass<HID, true, false>(n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part,
+      row_pass<HID, true, false>(n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part, s_rowctr + 1,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           if (lane < H4) st4(zw + 4 * lane, z);
@@ -733,7 +754,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(4)
       // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise' -> dY1
-      row_pass<HID, false, false>(n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part,
+      row_pass<HID, false, false>(n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part, s_rowctr + 2,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt1[i]; },
         [&](int i, float4 dh) {
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
@@ -753,7 +774,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(5)
       // ---- B0 (sparse half): all nodes: dP = A_m^T dY1 (columns < n2 of row j); layer-1 edge dots <dY1[col], P[row]> on the way
-      row_pass<HID, false, true>(n, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part,
+      row_pass<HID, false, true>(n, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part, s_rowctr + 3,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; },
         [&](int i, float4 z) { if (lane < H4) st4(dP + (size_t)i * HS + 4 * lane, z); });
       bar.sync();   // the tiles below read dP rows written by other warps / CTAs

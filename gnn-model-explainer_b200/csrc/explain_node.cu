@@ -744,13 +744,18 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
         }
         const float gi = Si * (1.f - Si) * (Gd + hp.c_size - ent_over_nn * Mi);
         const float gj = Sj * (1.f - Sj) * (Gd + hp.c_size - ent_over_nn * Mj);
-        mi = mi + (gi - mi) * hp.one_minus_b1;
-        mj = mj + (gj - mj) * hp.one_minus_b1;
-        vi = vi * hp.b2 + hp.one_minus_b2 * gi * gi;
-        vj = vj * hp.b2 + hp.one_minus_b2 * gj * gj;
-        const float bc2s_inv = 1.0f / tab.y;
-        Mi = Mi - adam_delta_fast(mi, vi, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
-        Mj = Mj - adam_delta_fast(mj, vj, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
+        if (hp.opt == GX_OPT_ADAM) {
+          mi = mi + (gi - mi) * hp.one_minus_b1;
+          mj = mj + (gj - mj) * hp.one_minus_b1;
+          vi = vi * hp.b2 + hp.one_minus_b2 * gi * gi;
+          vj = vj * hp.b2 + hp.one_minus_b2 * gj * gj;
+          const float bc2s_inv = 1.0f / tab.y;
+          Mi = Mi - adam_delta_fast(mi, vi, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
+          Mj = Mj - adam_delta_fast(mj, vj, tab.x, tab.y, bc2s_inv, hp.eps, ieee);
+        } else {
+          opt_step_other(hp.opt, Mi, gi, mi, vi, tab.x);
+          opt_step_other(hp.opt, Mj, gj, mj, vj, tab.x);
+        }
         Si = sigmoid_fast(Mi, ieee);
         Sj = sigmoid_fast(Mj, ieee);
         if (kTrace) atomicAdd(&s_acc[(it - 1) * 4 + 3], (double)(Si + Sj));   // 2 a' = S_i + S_j after the step (mask_density, explain.py:148)

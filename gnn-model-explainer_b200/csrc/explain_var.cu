@@ -280,9 +280,13 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
           const float s = sF[f];
           const float g = s * (1.f - s) * (gsum + hp.c_feat_size / (float)d);
           float mf = mF[f], vf = vF[f], Fv = Fm[f];
-          mf = mf + (g - mf) * hp.one_minus_b1;
-          vf = vf * hp.b2 + hp.one_minus_b2 * g * g;
-          Fv = Fv - step * (mf / (sqrtf(vf) / bc2s + hp.eps));
+          if (hp.opt == GX_OPT_ADAM) {
+            mf = mf + (g - mf) * hp.one_minus_b1;
+            vf = vf * hp.b2 + hp.one_minus_b2 * g * g;
+            Fv = Fv - step * (mf / (sqrtf(vf) / bc2s + hp.eps));
+          } else {
+            opt_step_other(hp.opt, Fv, g, mf, vf, step);
+          }
           mF[f] = mf; vF[f] = vf; Fm[f] = Fv;
           const float sn = sigmoid_f(Fv);
           sF[f] = sn;   // (the edge dots below use dZ1 (.) sF stored in the backward, not this value)
@@ -314,12 +318,17 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
           float2 m2 = mm[p], v2 = vv[p];
           const float gi = Sv.x * (1.f - Sv.x) * (Gd + hp.c_size - ent_over_nn * Mv.x);
           const float gj = Sv.y * (1.f - Sv.y) * (Gd + hp.c_size - ent_over_nn * Mv.y);
-          m2.x = m2.x + (gi - m2.x) * hp.one_minus_b1;
-          m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
-          v2.x = v2.x * hp.b2 + hp.one_minus_b2 * gi * gi;
-          v2.y = v2.y * hp.b2 + hp.one_minus_b2 * gj * gj;
-          Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s, bc2s_inv, hp.eps, ieee);
-          Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s, bc2s_inv, hp.eps, ieee);
+          if (hp.opt == GX_OPT_ADAM) {
+            m2.x = m2.x + (gi - m2.x) * hp.one_minus_b1;
+            m2.y = m2.y + (gj - m2.y) * hp.one_minus_b1;
+            v2.x = v2.x * hp.b2 + hp.one_minus_b2 * gi * gi;
+            v2.y = v2.y * hp.b2 + hp.one_minus_b2 * gj * gj;
+            Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s, bc2s_inv, hp.eps, ieee);
+            Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s, bc2s_inv, hp.eps, ieee);
+          } else {
+            opt_step_other(hp.opt, Mv.x, gi, m2.x, v2.x, step);
+            opt_step_other(hp.opt, Mv.y, gj, m2.y, v2.y, step);
+          }
           const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
           MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
           const float an = 0.5f * (Sn.x + Sn.y);

@@ -81,9 +81,10 @@ struct GxHparamsDev {
   int32_t out_iter;  // the mask (and the optimiser state) is emitted after this many updates: num_epochs - 1
   float one_minus_b1, b2, one_minus_b2, eps;
   float c_size, c_feat_size, c_ent, c_lap;
-  const float2* adam_tab;  // [iters] (step_size_t = lr/(1-b1^t), sqrt(1-b2^t)) for t = start_step + 1 .., computed in double on the host
+  const float2* adam_tab;  // [iters] Adam: (step_size_t = lr_t/(1-b1^t), sqrt(1-b2^t)) for t = start_step + 1 .., computed in double on the host; other optimisers: (lr_t, 0).  lr_t follows the scheduler
   int32_t init;
   int32_t flags;  // GX_HP_* bits
+  int32_t opt;    // GX_OPT_*; the tuned kernels build Adam only (others: explain_var.cu + outer_pairs_kernel)
   int32_t mode;   // 0: mask optimisation; 1: gradient baseline (explain(model="grad")): one forward/backward on the unmasked subgraph
   uint64_t seed;
 };

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgnnx.so")
 GX_OK = 0
 GX_HOST, GX_DEVICE = 0, 1
 GX_INIT_M0, GX_INIT_PHILOX, GX_INIT_STATE = 0, 1, 2
-GX_VERSION = 200
+GX_VERSION = 210
 GX_TRACE_COLS = 8
 TR_LOSS_EDGES, TR_PRED, TR_SIZE, TR_ENT, TR_LAP, TR_FEAT, TR_DENSITY, TR_PGT = range(8)
 GX_MODEL_BN = 1
@@ -35,7 +35,12 @@ class GxHparams(C.Structure):
                 ("eps", C.c_float), ("coef_size", C.c_float), ("coef_feat_size", C.c_float),
                 ("coef_ent", C.c_float), ("coef_lap", C.c_float), ("mask_act", C.c_int32),
                 ("mask_bias", C.c_int32), ("init", C.c_int32), ("seed", C.c_uint64),
-                ("start_step", C.c_int32), ("reserved", C.c_int32)]
+                ("start_step", C.c_int32), ("opt", C.c_int32), ("opt_scheduler", C.c_int32), ("opt_decay_step", C.c_int32),
+                ("opt_decay_rate", C.c_float), ("opt_restart", C.c_int32)]
+
+
+GX_OPT = {"adam": 0, "sgd": 1, "rmsprop": 2, "adagrad": 3}
+GX_SCHED = {"none": 0, "step": 1, "cos": 2}
 
 
 class GxExplainIo(C.Structure):

@@ -90,8 +90,11 @@ class Explainer:
                                       "tests/test_oracle.py)" % args.mask_act)
         # args.mask_bias: accepted.  The reference's bias matrix starts at 0 where ReLU6 has zero gradient, Adam never moves it and the
         # masks equal the default run bit for bit (explain.py:657-660,673-676; pinned by tests/test_oracle.py) -- no extra state needed.
-        if getattr(args, "opt", "adam") != "adam" or getattr(args, "opt_scheduler", "none") != "none":
-            raise NotImplementedError("only Adam without scheduler (explainer_main.py defaults) is built")
+        # utils/train_utils.py:7-23: adam / sgd / rmsprop / adagrad, schedulers none / step / cos
+        if getattr(args, "opt", "adam") not in _abi.GX_OPT or getattr(args, "opt_scheduler", "none") not in _abi.GX_SCHED:
+            raise ValueError("unknown optimiser / scheduler: %r / %r" % (getattr(args, "opt", None), getattr(args, "opt_scheduler", None)))
+        if graph_mode and getattr(args, "opt", "adam") != "adam":
+            raise NotImplementedError("graph mode builds Adam only (the schedulers work)")
         bn = bool(getattr(model, "bn", False))
         if bn and graph_mode:
             raise NotImplementedError("--bn is built for node tasks only")
@@ -100,6 +103,8 @@ class Explainer:
         self.engine = Engine(device)
         weights, num_layers = model_weights(model)
         self.engine.set_model(weights, num_layers=num_layers, bn=bn)
+        # model / optimiser variants run in the variant kernel, which does not log the per-epoch trace print_training replays
+        self._no_trace = bn or num_layers != 3 or getattr(args, "opt", "adam") != "adam"
         adj_np = np.asarray(adj)
         if graph_mode:
             # graph classification: the whole padded batch goes to the device once (explain.py:80-85)
@@ -146,6 +151,12 @@ class Explainer:
             num_epochs=a.num_epochs, lr=a.lr,
             init=_abi.GX_INIT_M0 if init == "torch" else _abi.GX_INIT_PHILOX,
             seed=int(getattr(a, "gnnx_seed", 0)))
+        hp.opt = _abi.GX_OPT[getattr(a, "opt", "adam")]
+        hp.opt_scheduler = _abi.GX_SCHED[getattr(a, "opt_scheduler", "none")]
+        if hp.opt_scheduler == _abi.GX_SCHED["step"]:
+            hp.opt_decay_step = int(a.opt_decay_step); hp.opt_decay_rate = float(a.opt_decay_rate)
+        elif hp.opt_scheduler == _abi.GX_SCHED["cos"]:
+            hp.opt_restart = int(a.opt_restart)
         return hp, init
 
     def _draw_m0(self, plan, keep_dense=False):
@@ -198,7 +209,9 @@ class Explainer:
             self.engine.grad_nodes_host(edge_mask)
             return plan, edge_mask
         hp, init = self._hparams()
-        if not self.print_training:
+        if not self.print_training or self._no_trace:
+            if self.print_training:
+                print("(per-epoch trace is not built for --bn / num_gc_layers != 3 / optimisers other than Adam)")
             m0 = self._draw_m0(plan) if init == "torch" else None
             self.engine.explain_nodes_host(hp, m0, edge_mask)
             return plan, edge_mask

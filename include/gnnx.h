@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GX_VERSION 200
+#define GX_VERSION 210
 
 typedef struct gx_handle gx_handle;
 
@@ -69,8 +69,19 @@ typedef struct gx_hparams {
   int32_t init;          /* GX_INIT_*                                                     */
   uint64_t seed;         /* GX_INIT_PHILOX: stream seed                                   */
   int32_t start_step;    /* GX_INIT_STATE: Adam steps already taken (torch's state["step"]); else 0 */
-  int32_t reserved;
+  int32_t opt;           /* GX_OPT_*: args.opt (utils/train_utils.py:9-16); default adam                       */
+  int32_t opt_scheduler; /* GX_SCHED_*: args.opt_scheduler (train_utils.py:17-23); stepped once per epoch (explain.py:145-146) */
+  int32_t opt_decay_step;/* StepLR step_size                                                          */
+  float opt_decay_rate;  /* StepLR gamma                                                              */
+  int32_t opt_restart;   /* CosineAnnealingLR T_max                                                   */
 } gx_hparams;
+#define GX_OPT_ADAM 0
+#define GX_OPT_SGD 1      /* torch.optim.SGD(momentum=0.95)                                    */
+#define GX_OPT_RMSPROP 2  /* torch.optim.RMSprop defaults (alpha 0.99, eps 1e-8)              */
+#define GX_OPT_ADAGRAD 3  /* torch.optim.Adagrad defaults (eps 1e-10)                          */
+#define GX_SCHED_NONE 0
+#define GX_SCHED_STEP 1
+#define GX_SCHED_COS 2    /* schedulers work with every kernel; optimisers other than Adam run node tasks in the variant kernel */
 #define GX_INIT_M0 0     /* caller supplies M0 at the directed-edge entries (parity with torch's RNG draw) */
 #define GX_INIT_PHILOX 1 /* N(1, 2/n) drawn on device, counter = (seed, node, edge slot)                  */
 #define GX_INIT_STATE 2  /* resume / teacher forcing: mask, Adam moments and feature-mask state supplied (gx_explain_io) */

@@ -392,6 +392,42 @@ def gen_variants(R, epochs=30):
     print("  variants golden written")
 
 
+OPT_VARIANTS = (("sgd", dict(opt="sgd")), ("rmsprop", dict(opt="rmsprop")), ("adagrad", dict(opt="adagrad")),
+                ("adamstep", dict(opt="adam", opt_scheduler="step", opt_decay_step=8, opt_decay_rate=0.5)),
+                ("adamcos", dict(opt="adam", opt_scheduler="cos", opt_restart=12)),
+                ("sgdstep", dict(opt="sgd", opt_scheduler="step", opt_decay_step=10, opt_decay_rate=0.3)))
+
+
+def gen_opts(R, epochs=30):
+    """Optimiser / scheduler variants (utils/train_utils.py:7-23, explain.py:145-146,622): the unmodified reference
+    on the rand fixture (its graph, trained weights, nodes and seeds) with --opt sgd / rmsprop / adagrad and the step / cos
+    schedulers -> tests/golden/opts_golden.npz (per variant and node: the returned mask at the edges; M0 = rand_golden's)."""
+    import gnnx_oracle as O
+    out = dict(num_epochs=np.int64(epochs))
+    for tag, over in OPT_VARIANTS:
+        make, g, gold = _load_fixture_model(R, "rand", num_epochs=epochs, **over)
+        ex = make()
+        nodes = [int(x) for x in gold["nodes"]]
+        for node in nodes:
+            torch.manual_seed(int(gold["n%d_seed" % node]))
+            with ref_harness.quiet():
+                node_idx_new, sub_adj, sub_feat, sub_label, nbrs = ex.extract_neighborhood(node, 0)
+                masked = np.asarray(ex.explain(node, graph_idx=0))
+            ei, ej = np.nonzero(sub_adj)
+            out["%s_n%d_mask" % (tag, node)] = masked[ei, ej].astype(np.float32)
+            # the oracle restatement must agree with the reference bit for bit
+            M0 = np.ones(sub_adj.shape, np.float32); M0[ei, ej] = gold["n%d_m0" % node]
+            W = {k: g[k] for k in ["W1", "b1", "W2", "b2", "W3", "b3", "Wp", "bp"]}
+            pl = np.argmax(g["pred"][nbrs], 1)
+            mine = O.explain_dense_torch(sub_adj, sub_feat, int(g["label"][node]), pl, node_idx_new, W, M0, hp=O.default_hparams(num_epochs=epochs, **over))
+            err = O.rel_l2(mine[ei, ej], masked[ei, ej])
+            assert err < 1e-6, (tag, node, err)
+        out[tag + "_nodes"] = np.asarray(nodes, np.int64)
+        print("  %s: %d nodes" % (tag, len(nodes)))
+    np.savez_compressed(os.path.join(OUT, "opts_golden.npz"), **out)
+    print("  optimiser-variant golden written")
+
+
 def _load_fixture_model(R, which, **eargs_over):
     """(explainer, graph npz, golden npz) of a committed fixture: the reference Explainer on the fixture's graph and weights."""
     g = np.load(os.path.join(OUT, which + "_graph.npz"))
@@ -538,6 +574,10 @@ def main():
     if a.only == "trace":
         torch.set_num_threads(8)
         gen_trace(ref_harness.load())
+        return
+    if a.only == "opts":
+        torch.set_num_threads(8)
+        gen_opts(ref_harness.load())
         return
     if a.only == "variants":
         torch.set_num_threads(8)

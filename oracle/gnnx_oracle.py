@@ -30,7 +30,8 @@ import numpy as np
 
 def default_hparams(**over):
     d = dict(num_epochs=100, lr=0.1, beta1=0.9, beta2=0.999, eps=1e-8,
-             size=0.005, feat_size=1.0, ent=1.0, lap=1.0)
+             size=0.005, feat_size=1.0, ent=1.0, lap=1.0,
+             opt="adam", opt_scheduler="none", opt_decay_step=0, opt_decay_rate=1.0, opt_restart=0)   # utils/parser_utils.py:10-19
     d.update(over)
     return types.SimpleNamespace(**d)
 
@@ -207,7 +208,22 @@ def explain_dense_torch(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
     mask = torch.nn.Parameter(torch.tensor(np.asarray(M0), dtype=torch.float))  # explain.py:646-652
     feat_mask = torch.nn.Parameter(torch.zeros(x.size(-1)))                     # explain.py:633-643
     diag_mask = torch.ones(n, n) - torch.eye(n)                                 # explain.py:617
-    opt = torch.optim.Adam([mask, feat_mask], lr=hp.lr, betas=(hp.beta1, hp.beta2), eps=hp.eps)
+    # utils/train_utils.py:7-23 (build_optimizer; explain.py:622)
+    if hp.opt == "adam":
+        opt = torch.optim.Adam([mask, feat_mask], lr=hp.lr, betas=(hp.beta1, hp.beta2), eps=hp.eps)
+    elif hp.opt == "sgd":
+        opt = torch.optim.SGD([mask, feat_mask], lr=hp.lr, momentum=0.95)
+    elif hp.opt == "rmsprop":
+        opt = torch.optim.RMSprop([mask, feat_mask], lr=hp.lr)
+    elif hp.opt == "adagrad":
+        opt = torch.optim.Adagrad([mask, feat_mask], lr=hp.lr)
+    else:
+        raise ValueError(hp.opt)
+    sched = None
+    if hp.opt_scheduler == "step":
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=hp.opt_decay_step, gamma=hp.opt_decay_rate)
+    elif hp.opt_scheduler == "cos":
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=hp.opt_restart)
     params = [mask, feat_mask] + W["conv_w"] + [b for b in W["conv_b"] if b is not None] + [W["pred_w"], W["pred_b"]]
     pred_label_t = None if graph_mode else torch.tensor(np.asarray(pred_label), dtype=torch.float)
 
@@ -246,6 +262,8 @@ def explain_dense_torch(sub_adj, sub_feat, gt_label, pred_label, node_idx_new, w
         m_used, ent_used = m.detach(), mask_ent.detach()
         loss.backward()                                                         # explain.py:142
         opt.step()                                                              # explain.py:144
+        if sched is not None:
+            sched.step()                                                        # explain.py:145-146
         with torch.no_grad():
             density = torch.sum(masked_adj_fn()) / torch.sum(adj)               # explain.py:148,680-683
         if trace is not None:

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libgnnx.so does not export %s" % s
     assert set(_abi.EXPORTS) == set(syms), "python binding and header disagree"
-    assert _abi.lib().gx_version() == _abi.GX_VERSION == 200
+    assert _abi.lib().gx_version() == _abi.GX_VERSION == 210
 
 
 def test_struct_layout_matches_defaults():
@@ -34,7 +34,7 @@ def test_struct_layout_matches_defaults():
     _abi.lib().gx_default_hparams(ctypes.byref(hp))
     assert hp.num_epochs == 100 and abs(hp.lr - 0.1) < 1e-8 and abs(hp.beta2 - 0.999) < 1e-7
     assert abs(hp.coef_size - 0.005) < 1e-9 and hp.coef_lap == 1.0 and hp.init == _abi.GX_INIT_M0
-    assert hp.seed == 0 and hp.start_step == 0
+    assert hp.seed == 0 and hp.start_step == 0 and hp.opt == 0 and hp.opt_scheduler == 0 and hp.opt_decay_rate == 1.0 and ctypes.sizeof(hp) == 80
     # gx_explain_io: twelve pointers, in the header's order
     src = open(os.path.join(ROOT, "include", "gnnx.h")).read()
     body = src[src.index("typedef struct gx_explain_io {"):src.index("} gx_explain_io;")]

@@ -111,3 +111,31 @@ def test_variant_refuses_what_it_does_not_build():
     with pytest.raises(Exception):
         eng.explain_nodes_ex(eng.make_hparams(num_epochs=3), g["bn_n0_m0"].astype(np.float32), out, trace=np.zeros((1, 3, _abi.GX_TRACE_COLS), np.float32))
     eng.close()
+
+
+OPT_CASES = [("sgd", dict(opt=1)), ("rmsprop", dict(opt=2)), ("adagrad", dict(opt=3)),
+             ("adamstep", dict(opt=0, opt_scheduler=1, opt_decay_step=8, opt_decay_rate=0.5)),
+             ("adamcos", dict(opt=0, opt_scheduler=2, opt_restart=12)),
+             ("sgdstep", dict(opt=1, opt_scheduler=1, opt_decay_step=10, opt_decay_rate=0.3))]
+
+
+@pytest.mark.parametrize("tag,over", OPT_CASES, ids=[c[0] for c in OPT_CASES])
+@pytest.mark.parametrize("stream", [False, True], ids=["smem", "stream"])
+def test_optimiser_variants_match_reference_golden(tag, over, stream):
+    """utils/train_utils.py:7-23 variants (--opt sgd / rmsprop / adagrad, --opt-scheduler step / cos) against the masks the
+    UNMODIFIED reference returned on the rand fixture (tests/golden/opts_golden.npz, oracle/gen_golden.py --only opts; 30 epochs).
+    Adam + scheduler runs in the tuned kernels (shared-memory and streaming), the other optimisers in explain_var.cu."""
+    if stream and over["opt"] != 0:
+        pytest.skip("optimisers other than Adam always run in the variant kernel")
+    g = np.load(util.GOLDEN + "/opts_golden.npz")
+    fx = util.load_fixture("rand")
+    eng = util.make_engine(fx)
+    if stream:
+        eng.debug_force_stream(True)
+    plan = eng.plan_nodes(fx.nodes, 3)
+    out = np.zeros(plan.total_edges, np.float32)
+    eng.explain_nodes_host(eng.make_hparams(num_epochs=int(g["num_epochs"]), **over), util.golden_m0(fx, plan), out)
+    eng.close()
+    for t, node in enumerate(fx.nodes):
+        err = util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], g["%s_n%d_mask" % (tag, node)])
+        assert err <= 1e-4, (tag, node, err)

@@ -270,3 +270,21 @@ def test_sparse_large_scale_spec_equals_the_edge_list_spec():
         a1, _ = KS.explain_pruned_edges(srp, scol, sfeat, slabel[idx], pred_label[nbrs], idx, w, m0, num_epochs=8)
         a2 = KS.explain_pruned_edges_sparse(srp, scol, sfeat, slabel[idx], pred_label[nbrs], idx, w, m0, num_epochs=8, chunk=64)
         assert O.rel_l2(a2, a1) < 1e-12, O.rel_l2(a2, a1)
+
+
+@pytest.mark.parametrize("tag,over", [("sgd", dict(opt="sgd")), ("rmsprop", dict(opt="rmsprop")), ("adagrad", dict(opt="adagrad")),
+                                      ("adamstep", dict(opt="adam", opt_scheduler="step", opt_decay_step=8, opt_decay_rate=0.5)),
+                                      ("adamcos", dict(opt="adam", opt_scheduler="cos", opt_restart=12)),
+                                      ("sgdstep", dict(opt="sgd", opt_scheduler="step", opt_decay_step=10, opt_decay_rate=0.3))])
+def test_oracle_optimiser_variants_match_reference(tag, over):
+    """The torch port with the reference's other optimisers / schedulers (utils/train_utils.py:7-23) against masks produced by the
+    UNMODIFIED reference (tests/golden/opts_golden.npz, oracle/gen_golden.py --only opts)."""
+    g = np.load(util.GOLDEN + "/opts_golden.npz")
+    fx = util.load_fixture("rand")
+    for node in fx.nodes[:3]:
+        idx, srp, scol, sfeat, slabel, nbrs = O.extract_neighborhood(fx.rowptr, fx.col, fx.feat, fx.label, node, 3)
+        A = O.dense_from_csr(srp, scol)
+        ei, ej = np.nonzero(A)
+        M0 = np.ones_like(A, dtype=np.float32); M0[ei, ej] = fx.gold["n%d_m0" % node]
+        port = O.explain_dense_torch(A, sfeat, slabel[idx], fx.pred_label[nbrs], idx, fx.weights, M0, hp=O.default_hparams(num_epochs=int(g["num_epochs"]), **over))
+        assert O.rel_l2(port[ei, ej], g["%s_n%d_mask" % (tag, node)]) < 1e-6, (tag, node)
