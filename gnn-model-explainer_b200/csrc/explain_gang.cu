@@ -22,6 +22,9 @@
 
 namespace {
 
+#ifndef GXG_UNROLL
+#define GXG_UNROLL 8   // steps of six edges a warp keeps in flight in the sparse passes (the passes are latency bound: profiles/r02_gang.md)
+#endif
 constexpr int kGangThreads = 512;    // 16 warps, 128 registers per thread (the tensor-core passes hold 24 A fragments + 32 accumulators)
 constexpr int kDenseWarps = 6;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
 constexpr int kLongEdges = 512;      // rows with more edges are sliced over all warps of one CTA
@@ -92,8 +95,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 // global -> shared bulk copy by the TMA engine (UBLKCP in SASS); bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t l2_policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(l2_policy) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ tensor cores (3xTF32)
@@ -116,14 +119,44 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+// ------------------------------------------------------------------------------------------------ L2 residency control
+// One task streams ~0.4 GB per epoch through the 126 MB L2 (CSR indices, pair indices and optimiser state, feature rows) while its
+// randomly accessed arrays (a, gE: 8 B per directed edge; P, dP, dY1: 240 B per node) are touched 4-byte-wise from all SMs: without
+// a hint the streams evict them and every scattered access becomes a DRAM read-modify-write (the edge phase was DRAM-latency
+// bound).  Streams are therefore loaded / stored with an evict_first policy, the scattered arrays with evict_last.
+struct L2Pol { uint64_t first, last; };
+__device__ __forceinline__ L2Pol make_l2pol() {
+  L2Pol p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.last));
+  return p;
+}
+__device__ __forceinline__ int ld_i32_stream(const int32_t* a, uint64_t pol) { int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol)); return v; }
+__device__ __forceinline__ float ld_f32_pol(const float* a, uint64_t pol) { float v; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol) : "memory"); return v; }
+__device__ __forceinline__ float4 ld_v4_pol(const float* a, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_v2_pol(const float2* a, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_f32_pol(float* a, float v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory"); }
+__device__ __forceinline__ void st_v2_pol(float2* a, float2 v, uint64_t pol) { asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(a), "f"(v.x), "f"(v.y), "l"(pol) : "memory"); }
+__device__ __forceinline__ void st_v4_pol(float* a, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ sparse passes
 // One row segment [r0,r1) by one warp: lane = (edge slot es, float4 index q); returns this lane's partial aggregate
 //   sum_{e = r0 + es, step EPL} a[e] f(src[icol[e]])[4q..4q+3]
 // kDot: gout[e] = <src[icol[e]], dv> for every edge (dv = this lane's float4 of the row's dot vector).
 template <int HID, bool kRelu, bool kDot>
 __device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const int32_t* __restrict__ icol, const float* a, const float* src,
-                                              float4 dv, float* gout) {
-  constexpr int H4 = HID / 4, EPL = 32 / H4, UN = 4;
+                                              float4 dv, float* gout, const L2Pol pol) {
+  constexpr int H4 = HID / 4, EPL = 32 / H4, UN = GXG_UNROLL;
   const int es = lane / H4, q = lane - es * H4;
   const bool act = es < EPL;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -136,8 +169,8 @@ __device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const in
   for (int k = 0; k < UN; ++k) {
     const int ek = r0 + es + k * EPL;
     const bool ok = act && ek < r1;
-    cn[k] = ok ? __ldg(icol + ek) : -1;
-    an[k] = ok ? __ldcg(a + ek) : 0.f;
+    cn[k] = ok ? ld_i32_stream(icol + ek, pol.first) : -1;
+    an[k] = ok ? ld_f32_pol(a + ek, pol.last) : 0.f;
   }
 #pragma unroll 1
   for (int e = r0 + es; e - es < r1; e += UN * EPL) {
@@ -147,13 +180,13 @@ __device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const in
 #pragma unroll
     for (int k = 0; k < UN; ++k) { c[k] = cn[k]; av[k] = an[k]; }
 #pragma unroll
-    for (int k = 0; k < UN; ++k) v[k] = c[k] >= 0 ? ldcg4(src_q + (size_t)c[k] * HID) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < UN; ++k) v[k] = c[k] >= 0 ? ld_v4_pol(src_q + (size_t)c[k] * HID, pol.last) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < UN; ++k) {
       const int ek = e + (UN + k) * EPL;
       const bool ok = act && ek < r1;
-      cn[k] = ok ? __ldg(icol + ek) : -1;
-      an[k] = ok ? __ldcg(a + ek) : 0.f;
+      cn[k] = ok ? ld_i32_stream(icol + ek, pol.first) : -1;
+      an[k] = ok ? ld_f32_pol(a + ek, pol.last) : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < UN; ++k) {
@@ -168,7 +201,7 @@ __device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const in
           const float t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
           pd = t2 + __shfl_down_sync(0xffffffffu, pd, 4);
         }
-        if (c[k] >= 0 && q == 0) gout[e + k * EPL] = pd;
+        if (c[k] >= 0 && q == 0) st_f32_pol(gout + e + k * EPL, pd, pol.last);
       }
     }
   }
@@ -196,13 +229,13 @@ __device__ __forceinline__ float4 slot_reduce(float4 z) {
   return z;
 }
 
-// z_i = sum_{e in bounds(i)} a[e] f(src[icol[e]]) for the rows i < R of this gang, then epi(i, z) with the warp converged
+// z_i = sum_{e in bounds(i)} a[e] f(src[icol[e]]) for the rows i < Rn of this gang (and the long rows among Rn .. R-1), then epi(i, z) with the warp converged
 // (z valid on lanes < H4).  Long rows (full degree > kLongEdges, listed in longlist) are sliced over the warps of the CTA
 // that owns them; every other row is taken by one warp.  bounds(i, r0, r1) gives the edge range of row i in this pass.
 template <int HID, bool kRelu, bool kDot, typename Bounds, typename Epi>
-__device__ __forceinline__ void row_pass(int R, int G, int grank, int warp, int nwarps, int lane, const int32_t* __restrict__ irp,
+__device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int warp, int nwarps, int lane, const int32_t* __restrict__ irp,
                                          const int32_t* __restrict__ icol, const float* a, const float* src, const float* dotsrc, float* gout,
-                                         const int32_t* longlist, int nlong, float* part, int* row_ctr, Bounds bounds, Epi epi) {
+                                         const int32_t* longlist, int nlong, float* part, int* row_ctr, const L2Pol pol, Bounds bounds, Epi epi) {
   constexpr int H4 = HID / 4, EPL = 32 / H4;
   const int q = lane % H4;
   // long rows of this CTA
@@ -212,11 +245,11 @@ __device__ __forceinline__ void row_pass(int R, int G, int grank, int warp, int 
     int r0, r1;
     bounds(i, r0, r1);
     const int len = r1 - r0;
-    const int per = gx_round_up((len + nwarps - 1) / nwarps, 4 * EPL);
+    const int per = gx_round_up((len + nwarps - 1) / nwarps, 4 * EPL);   // (a multiple of the slot count; independent of the unroll depth)
     const int s0 = min(r1, r0 + warp * per), s1 = min(r1, s0 + per);
     float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kDot && lane < EPL * H4) dv = ldcg4(dotsrc + (size_t)i * HID + 4 * q);
-    float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(s0, s1, lane, icol, a, src, dv, gout));
+    float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(s0, s1, lane, icol, a, src, dv, gout, pol));
     if (lane < H4) st4(part + warp * HID + 4 * lane, z);
     __syncthreads();
     if (warp == 0) {
@@ -236,14 +269,72 @@ __device__ __forceinline__ void row_pass(int R, int G, int grank, int warp, int 
     if (lane == 0) k = atomicAdd(row_ctr, 1);
     k = __shfl_sync(0xffffffffu, k, 0);
     const int i = k * G + grank;
-    if (i >= R) break;
+    if (i >= Rn) break;   // (rows Rn .. R-1: only the long ones, above)
     if (nlong > 0 && irp[i + 1] - irp[i] > kLongEdges) continue;
     int r0, r1;
     bounds(i, r0, r1);
     float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kDot && lane < EPL * H4) dv = ldcg4(dotsrc + (size_t)i * HID + 4 * q);
-    const float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(r0, r1, lane, icol, a, src, dv, gout));
+    const float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(r0, r1, lane, icol, a, src, dv, gout, pol));
     epi(i, z);
+  }
+}
+
+// Row-parallel variant for SHORT rows (B0 on the outermost nodes: a handful of gradient-carrying neighbours per row): every
+// edge slot of the warp (H4 lanes) owns one row and walks its edges with four gathers in flight, so a warp keeps EPL rows in
+// flight instead of one; no cross-slot reduction.  out[i] = sum_e a[e] src[icol[e]], gout[e] = <src[icol[e]], dotsrc[i]>.
+// Rows R0 .. R-1 of this gang; rows whose full degree exceeds kLongEdges are left to the whole-CTA path of row_pass.
+template <int HID, typename Bounds>
+__device__ __forceinline__ void short_rows_pass(int R0, int R, int G, int grank, int lane, const int32_t* __restrict__ irp,
+                                                const int32_t* __restrict__ icol, const float* a, const float* src, const float* dotsrc,
+                                                float* gout, float* out, int nlong, int* row_ctr, const L2Pol pol, Bounds bounds) {
+  constexpr int H4 = HID / 4, EPL = 32 / H4, UN = 4;
+  const int es = lane / H4, q = lane - es * H4;
+  const bool act = es < EPL;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(row_ctr, EPL);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (R0 + k * G + grank >= R) break;   // (rows of this CTA: R0 + grank, R0 + grank + G, ...)
+    const int i = R0 + (k + es) * G + grank;
+    int r0 = 0, r1 = 0;
+    bool mine = act && i < R;
+    if (mine && nlong > 0 && irp[i + 1] - irp[i] > kLongEdges) mine = false;
+    if (mine) bounds(i, r0, r1);
+    const float4 dv = mine ? ldcg4(dotsrc + (size_t)i * HID + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int wl = r1 - r0;   // warp-wide longest row: uniform trip count (the dot reduction shuffles need every lane)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+    const float* const src_q = src + 4 * q;
+    for (int e0 = 0; e0 < wl; e0 += UN) {
+      int c[UN];
+      float av[UN];
+      float4 v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int e = r0 + e0 + u;
+        const bool ok = e < r1;
+        c[u] = ok ? ld_i32_stream(icol + e, pol.first) : -1;
+        av[u] = ok ? ld_f32_pol(a + e, pol.last) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) v[u] = c[u] >= 0 ? ld_v4_pol(src_q + (size_t)c[u] * HID, pol.last) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        fma4(acc, av[u], v[u]);
+        float pd = fmaf(v[u].x, dv.x, fmaf(v[u].y, dv.y, fmaf(v[u].z, dv.z, v[u].w * dv.w)));
+        if (H4 == 8) {
+          pd += __shfl_xor_sync(0xffffffffu, pd, 1); pd += __shfl_xor_sync(0xffffffffu, pd, 2); pd += __shfl_xor_sync(0xffffffffu, pd, 4);
+        } else {
+          const float t1 = pd + __shfl_down_sync(0xffffffffu, pd, 1);
+          const float t2 = t1 + __shfl_down_sync(0xffffffffu, t1, 2);
+          pd = t2 + __shfl_down_sync(0xffffffffu, pd, 4);
+        }
+        if (c[u] >= 0 && q == 0) st_f32_pol(gout + r0 + e0 + u, pd, pol.last);
+      }
+    }
+    if (mine) st_v4_pol(out + (size_t)i * HID + 4 * q, acc, pol.last);
   }
 }
 
@@ -264,16 +355,16 @@ struct TileIter {
 // the lanes copy the rows themselves (synchronous).  with_dp: also the tile's 16 x HID block of dP (contiguous).
 template <int HID>
 __device__ __forceinline__ void tile_issue(int t, int n, int d, int dp8, int xs, bool tma, bool with_dp, int lane, const float* __restrict__ feat,
-                                           const int32_t* __restrict__ lo2gid, const float* dP, float* xt, float* pt, uint32_t bar) {
+                                           const int32_t* __restrict__ lo2gid, const float* dP, float* xt, float* pt, uint32_t bar, const L2Pol pol) {
   const int rows = min(16, n - t * 16);
   if (tma) {
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)(rows * d * 4 + (with_dp ? rows * HID * 4 : 0)));
     __syncwarp();
     if (lane < rows) {
       const int gid = __ldg(lo2gid + t * 16 + lane);
-      tma_load_1d((uint32_t)__cvta_generic_to_shared(xt + lane * xs), feat + (size_t)gid * d, (uint32_t)(d * 4), bar);
+      tma_load_1d((uint32_t)__cvta_generic_to_shared(xt + lane * xs), feat + (size_t)gid * d, (uint32_t)(d * 4), bar, pol.first);   // the feature matrix streams
     }
-    if (with_dp && lane == 31) tma_load_1d((uint32_t)__cvta_generic_to_shared(pt), dP + (size_t)t * 16 * HID, (uint32_t)(rows * HID * 4), bar);
+    if (with_dp && lane == 31) tma_load_1d((uint32_t)__cvta_generic_to_shared(pt), dP + (size_t)t * 16 * HID, (uint32_t)(rows * HID * 4), bar, pol.last);
   } else {
     for (int r = 0; r < rows; ++r) {
       const float* row = feat + (size_t)__ldg(lo2gid + t * 16 + r) * d;
@@ -289,7 +380,7 @@ __device__ __forceinline__ void tile_issue(int t, int n, int d, int dp8, int xs,
 template <int HID>
 __device__ __forceinline__ void dense_forward(int n, int d, const GangSmem& S, bool tma, int dwarp, int G, int grank, int lane,
                                               const float* __restrict__ feat, const int32_t* __restrict__ lo2gid, const float* Whi, const float* Wlo,
-                                              float* xt0, uint32_t bar0, uint32_t& phase, float* P) {
+                                              float* xt0, uint32_t bar0, uint32_t& phase, float* P, const L2Pol pol) {
   constexpr int NTL = (HID + 7) / 8;
   const int xs = S.xs, ldb = S.ldb, dp8 = S.dp8;
   const int ntile = (n + 15) / 16, nb = (ntile + kBlockTiles - 1) / kBlockTiles;
@@ -297,9 +388,9 @@ __device__ __forceinline__ void dense_forward(int n, int d, const GangSmem& S, b
   TileIter it{dwarp * G + grank, 0, nb, ntile, kDenseWarps * G};
   TileIter nx = it;
   int buf = 0;
-  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, false, lane, feat, lo2gid, nullptr, xt0, nullptr, bar0); nx.next(); }
+  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, false, lane, feat, lo2gid, nullptr, xt0, nullptr, bar0, pol); nx.next(); }
   while (it.valid()) {
-    if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, false, lane, feat, lo2gid, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8); nx.next(); }
+    if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, false, lane, feat, lo2gid, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8, pol); nx.next(); }
     if (tma) { mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf; }
     const float* xr = xt0 + buf * 16 * xs;
     float c[NTL][4];
@@ -337,7 +428,7 @@ __device__ __forceinline__ void dense_forward(int n, int d, const GangSmem& S, b
 template <int HID, int NF8>
 __device__ __forceinline__ void dense_backward(int n, int d, int dp, const GangSmem& S, bool tma, int dwarp, int G, int grank, int lane,
                                                const float* __restrict__ feat, const int32_t* __restrict__ lo2gid, const float* Thi, const float* Tlo,
-                                               const float* dP, float* xt0, float* pt0, uint32_t bar0, uint32_t& phase, float* gFb) {
+                                               const float* dP, float* xt0, float* pt0, uint32_t bar0, uint32_t& phase, float* gFb, const L2Pol pol) {
   constexpr int NTL = (HID + 7) / 8;
   const int xs = S.xs, ldt = S.ldt, dp8 = S.dp8;
   const int nf8 = dp8 / 8;
@@ -349,10 +440,10 @@ __device__ __forceinline__ void dense_backward(int n, int d, int dp, const GangS
   float ga[NF8][2];
 #pragma unroll
   for (int nt = 0; nt < NF8; ++nt) { ga[nt][0] = 0.f; ga[nt][1] = 0.f; }
-  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, true, lane, feat, lo2gid, dP, xt0, pt0, bar0); nx.next(); }
+  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, true, lane, feat, lo2gid, dP, xt0, pt0, bar0, pol); nx.next(); }
   while (it.valid()) {
     if (nx.valid()) {
-      tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, true, lane, feat, lo2gid, dP, xt0 + (buf ^ 1) * 16 * xs, pt0 + (buf ^ 1) * 16 * HID, bar0 + (buf ^ 1) * 8);
+      tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, true, lane, feat, lo2gid, dP, xt0 + (buf ^ 1) * 16 * xs, pt0 + (buf ^ 1) * 16 * HID, bar0 + (buf ^ 1) * 8, pol);
       nx.next();
     }
     if (tma) { mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf; }
@@ -433,7 +524,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_tr[kTrace ? 8 : 1];
   __shared__ long long s_ph[11];   // debug: per-phase cycle sums of the first task + last stamp
-  __shared__ int s_rowctr[4];      // next row of this CTA in each of the four sparse passes of an epoch
+  __shared__ int s_rowctr[5];      // next row of this CTA in each of the sparse passes of an epoch
   static_assert((HID == 20 || HID == 32) && EMB == HID, "hidden width 20 or 32 (others are zero-padded to 32 by gx_set_model)");
   constexpr int HS = HID, H4 = HID / 4, PD = 2 * HID + EMB, NT = kGangThreads;
   constexpr int nwarps = NT / 32;
@@ -493,6 +584,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   float* const slab = A.gws + (int64_t)gang * A.gws_stride_words;
   float2* const MM0 = reinterpret_cast<float2*>(A.pws + (int64_t)gang * A.pws_stride_words);
   GangBar bar{GA.bars + gang, 0ull, G};
+  const L2Pol pol = make_l2pol();
   int32_t* const mail = GA.mail + gang * 2;
   const int gtid = grank * NT + tid, gthreads = G * NT;
   const int gnw = nwarps * G;
@@ -600,7 +692,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     if (timed && warp == 0) { const long long c_ = clock64(); if (lane == 0) { for (int k = 0; k < 10; ++k) s_ph[k] = 0; s_ph[10] = c_; } __syncwarp(); }
     for (int it = 1; it <= hp.iters; ++it) {
       // ---- F0: all nodes: P = (X . sigmoid(feat_mask)) W1 on the tensor cores               (explain.py:707, models.py:70-71)
-      if (tid < 4) s_rowctr[tid] = 0;
+      if (tid < 5) s_rowctr[tid] = 0;
       for (int idx = tid; idx < dp * HID; idx += NT) {   // fold the feature mask into W1, split into tf32 hi / lo
         const int f = idx / HID, c = idx - f * HID;
         uint32_t hi, lo;
@@ -608,11 +700,11 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
         Whi[f * S.ldb + c] = __uint_as_float(hi); Wlo[f * S.ldb + c] = __uint_as_float(lo);
       }
       __syncthreads();
-      if (warp < kDenseWarps) dense_forward<HID>(n, d, S, tma, warp, G, grank, lane, A.g.feat, lo2gid, Whi, Wlo, xt0, bar0, tile_phase, P);
+      if (warp < kDenseWarps) dense_forward<HID>(n, d, S, tma, warp, G, grank, lane, A.g.feat, lo2gid, Whi, Wlo, xt0, bar0, tile_phase, P, pol);
       bar.sync();
       GXG_MARK(0)
       // ---- F1: rows [0,n2): Y1 = A_m P + b1 ; row normalise                                   (models.py:70-78)
-      row_pass<HID, false, false>(n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part, s_rowctr + 0,
+      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part, s_rowctr + 0, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -625,7 +717,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
-      row_pass<HID, true, false>(n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part, s_rowctr + 1,
+      row_pass<HID, true, false>(n1, n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part, s_rowctr + 1, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           if (lane < H4) st4(zw + 4 * lane, z);
@@ -718,7 +810,8 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
         const int r0 = irp[0];
         const int items = 1 + irp[1] - r0;
         const int ntask = (items + epi - 1) / epi;
-        for (int t = warp * G + grank; t < ntask; t += gnw) {
+        // a handful of rows: every CTA computes all of them for itself (identical values, benign duplicate stores) -- saves a gang barrier
+        for (int t = warp; t < ntask; t += nwarps) {
           const int item = t * epi + G8.grp;
           const bool act = item < items;
           int j = 0;
@@ -751,10 +844,11 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
           __syncwarp();
         }
       }
-      bar.sync();
+      __threadfence();
+      __syncthreads();
       GXG_MARK(4)
       // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise' -> dY1
-      row_pass<HID, false, false>(n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part, s_rowctr + 2,
+      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part, s_rowctr + 2, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt1[i]; },
         [&](int i, float4 dh) {
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
@@ -774,15 +868,18 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(5)
       // ---- B0 (sparse half): all nodes: dP = A_m^T dY1 (columns < n2 of row j); layer-1 edge dots <dY1[col], P[row]> on the way
-      row_pass<HID, false, true>(n, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part, s_rowctr + 3,
+      //      rows < n2 (hub-heavy, long gradient-carrying prefixes): a warp per row; the outermost rows (a few edges each): a row per edge slot
+      row_pass<HID, false, true>(n, n2, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part, s_rowctr + 3, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; },
         [&](int i, float4 z) { if (lane < H4) st4(dP + (size_t)i * HS + 4 * lane, z); });
+      short_rows_pass<HID>(n2, n, G, grank, lane, irp, icol, a, dY1, P, gE, dP, nlong, s_rowctr + 4, pol,
+        [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; });
       bar.sync();   // the tiles below read dP rows written by other warps / CTAs
       GXG_MARK(6)
       // ---- B0 (dense half): per 128-node block: sum_j X_j (.) (dP_j W1^T) on the tensor cores
       if (!hp.mode && warp < kDenseWarps) {
         asm volatile("fence.proxy.async.global;" ::: "memory");   // dP was written with ordinary stores, the TMA engine reads it
-        dense_backward<HID, 16>(n, d, dp, S, tma, warp, G, grank, lane, A.g.feat, lo2gid, Thi, Tlo, dP, xt0, pt0, bar0, tile_phase, gFb);
+        dense_backward<HID, 16>(n, d, dp, S, tma, warp, G, grank, lane, A.g.feat, lo2gid, Thi, Tlo, dP, xt0, pt0, bar0, tile_phase, gFb, pol);
       }
       bar.sync();
       GXG_MARK(7)
@@ -841,11 +938,12 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
           }
         } else
         for (int p = (warp * G + grank) * 32 + lane; p < np; p += gthreads) {
-          const int sij = ppij[p], sji = ppji[p];
-          float2 Mv = MM[p];
-          const float2 Sv = SS[p];
-          float2 m2 = mm[p], v2 = vv[p];
-          float Gd = lapg[p] + __ldcg(gE + sji) + __ldcg(gE + sij);
+          // streams (pair indices, optimiser state) pass through the L2 with evict_first, the scattered a / gE accesses keep their lines
+          const int sij = ld_i32_stream(ppij + p, pol.first), sji = ld_i32_stream(ppji + p, pol.first);
+          float2 Mv = ld_v2_pol(MM + p, pol.first);
+          const float2 Sv = ld_v2_pol(SS + p, pol.first);
+          float2 m2 = ld_v2_pol(mm + p, pol.first), v2 = ld_v2_pol(vv + p, pol.first);
+          float Gd = ld_f32_pol(lapg + p, pol.first) + ld_f32_pol(gE + sji, pol.last) + ld_f32_pol(gE + sij, pol.last);
           if (p < np1) {
             const int i = pi[p], j = pj[p];   // i < j, i < n1
             Gd += dot_relu_v4(dZ2 + (size_t)i * HS, Yh1 + (size_t)j * HS, H4);
@@ -867,11 +965,11 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
           Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s, bc2s_inv, hp.eps, ieee);
           Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s, bc2s_inv, hp.eps, ieee);
           const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
-          MM[p] = Mv; mm[p] = m2; vv[p] = v2; SS[p] = Sn;
+          st_v2_pol(MM + p, Mv, pol.first); st_v2_pol(mm + p, m2, pol.first); st_v2_pol(vv + p, v2, pol.first); st_v2_pol(SS + p, Sn, pol.first);
           const float an = 0.5f * (Sn.x + Sn.y);
           if (kTrace) trD += 2.0f * an;
-          a[sij] = an;
-          a[sji] = an;
+          st_f32_pol(a + sij, an, pol.last);
+          st_f32_pol(a + sji, an, pol.last);
           if (last) {
             const int64_t oij = edge_off + poij[p], oji = edge_off + poji[p];
             A.out_mask[oij] = an;

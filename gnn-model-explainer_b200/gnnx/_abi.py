@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgnnx.so")
+LIB_PATH = os.environ.get("GNNX_LIB_PATH") or os.path.join(_HERE, "lib", "libgnnx.so")   # GNNX_LIB_PATH: tools/ A-B builds of the same ABI
 
 GX_OK = 0
 GX_HOST, GX_DEVICE = 0, 1

@@ -260,7 +260,9 @@ int gx_last_explain_ms(gx_handle* h, float* ms);
  * gx_debug_set_gang:     CTAs per task of the streaming kernel explain_gang.cu (0 = automatic: the tasks in flight keep their
  *                        scattered state L2 resident; -1 = the first-generation kernel explain_stream.cu);
  * gx_debug_set_cluster:  thread-block cluster size (1, 2, 4; 0 = automatic) and cost threshold of the shared-memory kernel's
- *                        cluster class.  Neither knob changes a single bit of the result (tests/test_gpu_stream.py, test_gpu_cluster.py). */
+ *                        cluster class (off by default: a latency tool for small batches).  The gang size never changes a bit of the
+ *                        result (tests/test_gpu_stream.py); a cluster sums the per-warp dL/dsF partials in another order, so it
+ *                        agrees with the single-CTA run to round-off (tests/test_gpu_cluster.py). */
 int gx_debug_set_gang(gx_handle* h, int ctas_per_task);
 int gx_debug_set_cluster(gx_handle* h, int cluster_size, int64_t min_cost);
 int gx_debug_force_stream(gx_handle* h, int on);

@@ -19,7 +19,7 @@ EPOCHS = int(os.environ.get("SAN_EPOCHS", "4"))
 
 
 def main():
-    which = sys.argv[1:] or ["node", "stream", "graph", "misc"]
+    which = sys.argv[1:] or ["node", "stream", "graph", "misc", "var", "cluster"]
     fx = util.load_fixture("syn1")
     if "node" in which:
         eng = util.make_engine(fx)
@@ -33,13 +33,44 @@ def main():
         eng.close()
     if "stream" in which:
         fr = util.load_fixture("rand")
-        eng = util.make_engine(fr)
-        eng.debug_force_stream(True)
-        plan = eng.plan_nodes(fr.nodes[:4], 3)
+        for gang in (0, 3, -1):          # explain_gang.cu (automatic gang size, 3 CTAs per task) and explain_stream.cu
+            eng = util.make_engine(fr)
+            eng.debug_force_stream(True)
+            eng.debug_gang(gang)
+            plan = eng.plan_nodes(fr.nodes[:4], 3)
+            out = np.zeros(plan.total_edges, np.float32)
+            eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS), util.golden_m0(fr, plan), out)
+            eng.grad_nodes_host(out)
+            print("stream ok (gang %d)" % gang, float(out.sum()))
+            eng.close()
+    if "var" in which:
+        g = np.load(util.GOLDEN + "/variants_golden.npz")
+        import gnnx_oracle as O
+        N = int(g["N"])
+        rowptr, col = O.csr_from_edges(N, g["edges"])
+        for tag, L, bn in (("bn", 3, True), ("L4", 4, False)):
+            w = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_W") or k.startswith(tag + "_b")}
+            eng = gnnx.Engine(0)
+            eng.set_model(w, num_layers=L, bn=bn)
+            eng.set_graph_csr(rowptr, col, g["feat"].astype(np.float32), g["label"].astype(np.int32), np.argmax(g[tag + "_pred"], 1).astype(np.int32))
+            plan = eng.plan_nodes([0, 17], L)
+            out = np.zeros(plan.total_edges, np.float32)
+            eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS, init=_abi.GX_INIT_PHILOX, seed=2), None, out)
+            print("var ok", tag, float(out.sum()))
+            eng.close()
+        eng = util.make_engine(fx)     # default model, optimiser other than Adam -> the variant kernel
+        plan = eng.plan_nodes([300, 5], 3)
         out = np.zeros(plan.total_edges, np.float32)
-        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS), util.golden_m0(fr, plan), out)
-        eng.grad_nodes_host(out)
-        print("stream ok", float(out.sum()))
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS, opt=1), util.golden_m0(fx, plan), out)
+        print("var ok sgd", float(out.sum()))
+        eng.close()
+    if "cluster" in which:
+        eng = util.make_engine(fx)
+        eng.debug_cluster(4, 1)
+        plan = eng.plan_nodes([0, 300, 13], 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS), util.golden_m0(fx, plan), out)
+        print("cluster ok", float(out.sum()))
         eng.close()
     if "graph" in which:
         g = np.load(util.GOLDEN + "/graphs_golden.npz")
