@@ -23,7 +23,7 @@
 namespace {
 
 #ifndef GXG_UNROLL
-#define GXG_UNROLL 8   // steps of six edges a warp keeps in flight in the sparse passes (the passes are latency bound: profiles/r02_gang.md)
+#define GXG_UNROLL 4   // steps of six edges a warp keeps in flight in the sparse passes (8 measured no faster: profiles/r02_gang.md)
 #endif
 constexpr int kGangThreads = 512;    // 16 warps, 128 registers per thread (the tensor-core passes hold 24 A fragments + 32 accumulators)
 constexpr int kDenseWarps = 6;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
@@ -351,35 +351,25 @@ struct TileIter {
   }
 };
 
-// issue the loads of tile t into buffer `buf` (whole warp).  tma: d % 4 == 0 and 16-byte aligned features -> bulk copies; otherwise
-// the lanes copy the rows themselves (synchronous).  with_dp: also the tile's 16 x HID block of dP (contiguous).
+// issue the loads of tile t into buffer `buf` (whole warp; one lane talks to the TMA engine).  The task's feature rows were copied
+// once into level order with the shared-memory tile pitch (xlo), so a tile is ONE contiguous bulk copy that lands in the padded,
+// bank-conflict-free layout; with_dp: also the tile's 16 x HID block of dP (contiguous as well).
 template <int HID>
-__device__ __forceinline__ void tile_issue(int t, int n, int d, int dp8, int xs, bool tma, bool with_dp, int lane, const float* __restrict__ feat,
-                                           const int32_t* __restrict__ lo2gid, const float* dP, float* xt, float* pt, uint32_t bar, const L2Pol pol) {
+__device__ __forceinline__ void tile_issue(int t, int n, int xs, bool with_dp, int lane, const float* xlo, const float* dP,
+                                           float* xt, float* pt, uint32_t bar, const L2Pol pol) {
   const int rows = min(16, n - t * 16);
-  if (tma) {
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(rows * d * 4 + (with_dp ? rows * HID * 4 : 0)));
-    __syncwarp();
-    if (lane < rows) {
-      const int gid = __ldg(lo2gid + t * 16 + lane);
-      tma_load_1d((uint32_t)__cvta_generic_to_shared(xt + lane * xs), feat + (size_t)gid * d, (uint32_t)(d * 4), bar, pol.first);   // the feature matrix streams
-    }
-    if (with_dp && lane == 31) tma_load_1d((uint32_t)__cvta_generic_to_shared(pt), dP + (size_t)t * 16 * HID, (uint32_t)(rows * HID * 4), bar, pol.last);
-  } else {
-    for (int r = 0; r < rows; ++r) {
-      const float* row = feat + (size_t)__ldg(lo2gid + t * 16 + r) * d;
-      for (int f = lane; f < dp8; f += 32) xt[r * xs + f] = f < d ? __ldg(row + f) : 0.f;
-    }
-    if (with_dp)
-      for (int idx = lane; idx < rows * HID; idx += 32) pt[idx] = __ldcg(dP + (size_t)t * 16 * HID + idx);
-    __syncwarp();
+  if (lane == 0) {
+    mbar_expect_tx(bar, (uint32_t)(16 * xs * 4 + (with_dp ? rows * HID * 4 : 0)));
+    tma_load_1d((uint32_t)__cvta_generic_to_shared(xt), xlo + (size_t)t * 16 * xs, (uint32_t)(16 * xs * 4), bar, pol.first);   // the feature rows stream
+    if (with_dp) tma_load_1d((uint32_t)__cvta_generic_to_shared(pt), dP + (size_t)t * 16 * HID, (uint32_t)(rows * HID * 4), bar, pol.last);
   }
+  __syncwarp();
 }
 
 // F0: P[j] = X[j] (sF (.) W1) for the tiles of this dense warp                                        (explain.py:707, models.py:70-71)
 template <int HID>
-__device__ __forceinline__ void dense_forward(int n, int d, const GangSmem& S, bool tma, int dwarp, int G, int grank, int lane,
-                                              const float* __restrict__ feat, const int32_t* __restrict__ lo2gid, const float* Whi, const float* Wlo,
+__device__ __forceinline__ void dense_forward(int n, const GangSmem& S, int dwarp, int G, int grank, int lane,
+                                              const float* xlo, const float* Whi, const float* Wlo,
                                               float* xt0, uint32_t bar0, uint32_t& phase, float* P, const L2Pol pol) {
   constexpr int NTL = (HID + 7) / 8;
   const int xs = S.xs, ldb = S.ldb, dp8 = S.dp8;
@@ -388,10 +378,10 @@ __device__ __forceinline__ void dense_forward(int n, int d, const GangSmem& S, b
   TileIter it{dwarp * G + grank, 0, nb, ntile, kDenseWarps * G};
   TileIter nx = it;
   int buf = 0;
-  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, false, lane, feat, lo2gid, nullptr, xt0, nullptr, bar0, pol); nx.next(); }
+  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0, nullptr, bar0, pol); nx.next(); }
   while (it.valid()) {
-    if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, false, lane, feat, lo2gid, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8, pol); nx.next(); }
-    if (tma) { mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf; }
+    if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8, pol); nx.next(); }
+    mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf;
     const float* xr = xt0 + buf * 16 * xs;
     float c[NTL][4];
 #pragma unroll
@@ -426,8 +416,8 @@ __device__ __forceinline__ void dense_forward(int n, int d, const GangSmem& S, b
 // B0 (dense half): per 128-node block b the partial  gFb[b][f] = sum_{j in block} X[j][f] (dP_j W1^T)[f]        (dL/dsF, explain.py:707)
 // NF8 = feature n-tiles kept in registers (dp8 / 8 <= 16).
 template <int HID, int NF8>
-__device__ __forceinline__ void dense_backward(int n, int d, int dp, const GangSmem& S, bool tma, int dwarp, int G, int grank, int lane,
-                                               const float* __restrict__ feat, const int32_t* __restrict__ lo2gid, const float* Thi, const float* Tlo,
+__device__ __forceinline__ void dense_backward(int n, int dp, const GangSmem& S, int dwarp, int G, int grank, int lane,
+                                               const float* xlo, const float* Thi, const float* Tlo,
                                                const float* dP, float* xt0, float* pt0, uint32_t bar0, uint32_t& phase, float* gFb, const L2Pol pol) {
   constexpr int NTL = (HID + 7) / 8;
   const int xs = S.xs, ldt = S.ldt, dp8 = S.dp8;
@@ -440,13 +430,13 @@ __device__ __forceinline__ void dense_backward(int n, int d, int dp, const GangS
   float ga[NF8][2];
 #pragma unroll
   for (int nt = 0; nt < NF8; ++nt) { ga[nt][0] = 0.f; ga[nt][1] = 0.f; }
-  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, true, lane, feat, lo2gid, dP, xt0, pt0, bar0, pol); nx.next(); }
+  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, true, lane, xlo, dP, xt0, pt0, bar0, pol); nx.next(); }
   while (it.valid()) {
     if (nx.valid()) {
-      tile_issue<HID>(nx.tile(), n, d, dp8, xs, tma, true, lane, feat, lo2gid, dP, xt0 + (buf ^ 1) * 16 * xs, pt0 + (buf ^ 1) * 16 * HID, bar0 + (buf ^ 1) * 8, pol);
+      tile_issue<HID>(nx.tile(), n, xs, true, lane, xlo, dP, xt0 + (buf ^ 1) * 16 * xs, pt0 + (buf ^ 1) * 16 * HID, bar0 + (buf ^ 1) * 8, pol);
       nx.next();
     }
-    if (tma) { mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf; }
+    mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf;
     const float* xr = xt0 + buf * 16 * xs;
     const float* pr = pt0 + buf * 16 * HID;
     const int rows = min(16, n - it.tile() * 16);
@@ -537,7 +527,6 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   const int d = m.d, C = m.C;
   const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
   const int dp = gx_round_up(d, 4);
-  const bool tma = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.g.feat) & 15) == 0);
   const GangSmem S = gang_smem(d, HID, EMB, C, nwarps);
   float* const W1s = sm + S.W1s; float* const Whi = sm + S.Whi; float* const Wlo = sm + S.Wlo; float* const Thi = sm + S.Thi; float* const Tlo = sm + S.Tlo;
   float* const W2s = sm + S.W2s; float* const W2t = sm + S.W2t; float* const W3s = sm + S.W3s; float* const bs = sm + S.bs;
@@ -612,6 +601,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     int32_t* const cnt1 = reinterpret_cast<int32_t*>(slab + L.cnt1); int32_t* const cnt2 = reinterpret_cast<int32_t*>(slab + L.cnt2);
     int32_t* const longlist = reinterpret_cast<int32_t*>(slab + L.longlist);
     float* const dP = slab + L.dP; float* const gE = slab + L.gE;
+    float* const xlo = slab + L.xlo;
     float2* const MM = MM0; float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
     const float nn = (float)n * (float)n;
     const float ent_over_nn = hp.c_ent / nn;
@@ -675,6 +665,11 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
         }
       }
     }
+    // the task's feature rows in level order at the tile pitch (pad columns zero; the 16 rows past the end belong to the last tile)
+    for (int64_t idx = gtid; idx < (int64_t)(n + 16) * S.xs; idx += gthreads) {
+      const int j = (int)(idx / S.xs), f = (int)(idx - (int64_t)j * S.xs);
+      xlo[idx] = (j < n && f < d) ? __ldg(A.g.feat + (size_t)__ldg(lo2gid + j) * d + f) : 0.f;
+    }
     for (int e = gtid; e < e_d; e += gthreads) gE[e] = 0.f;   // slots outside the < n2 prefixes are never written and must read as 0
     for (int i = gtid; i < n; i += gthreads) {
       const int r0 = irp[i], r1 = irp[i + 1];
@@ -700,7 +695,10 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
         Whi[f * S.ldb + c] = __uint_as_float(hi); Wlo[f * S.ldb + c] = __uint_as_float(lo);
       }
       __syncthreads();
-      if (warp < kDenseWarps) dense_forward<HID>(n, d, S, tma, warp, G, grank, lane, A.g.feat, lo2gid, Whi, Wlo, xt0, bar0, tile_phase, P, pol);
+      if (warp < kDenseWarps) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // xlo was written with ordinary stores, the TMA engine reads it
+        dense_forward<HID>(n, S, warp, G, grank, lane, xlo, Whi, Wlo, xt0, bar0, tile_phase, P, pol);
+      }
       bar.sync();
       GXG_MARK(0)
       // ---- F1: rows [0,n2): Y1 = A_m P + b1 ; row normalise                                   (models.py:70-78)
@@ -878,8 +876,8 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       GXG_MARK(6)
       // ---- B0 (dense half): per 128-node block: sum_j X_j (.) (dP_j W1^T) on the tensor cores
       if (!hp.mode && warp < kDenseWarps) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");   // dP was written with ordinary stores, the TMA engine reads it
-        dense_backward<HID, 16>(n, d, dp, S, tma, warp, G, grank, lane, A.g.feat, lo2gid, Thi, Tlo, dP, xt0, pt0, bar0, tile_phase, gFb, pol);
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // dP (and, first epoch, xlo) were written with ordinary stores, the TMA engine reads them
+        dense_backward<HID, 16>(n, dp, S, warp, G, grank, lane, xlo, Thi, Tlo, dP, xt0, pt0, bar0, tile_phase, gFb, pol);
       }
       bar.sync();
       GXG_MARK(7)
@@ -893,8 +891,17 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
           const int slices = NT / dp > 0 ? NT / dp : 1;
           for (int idx = tid; idx < slices * dp; idx += NT) {
             const int s = idx / dp, f = idx - s * dp;
+            // (sixteen independent loads in flight, added in block order: the loop was a chain of ~200 dependent L2 round trips)
             float t = 0.f;
-            for (int b = s; b < nblk; b += slices) t += __ldcg(gFb + (size_t)b * dp + f);
+            int b = s;
+            for (; b + 15 * slices < nblk; b += 16 * slices) {
+              float v[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) v[u] = __ldcg(gFb + (size_t)(b + u * slices) * dp + f);
+#pragma unroll
+              for (int u = 0; u < 16; ++u) t += v[u];
+            }
+            for (; b < nblk; b += slices) t += __ldcg(gFb + (size_t)b * dp + f);
             red[idx] = t;
           }
           __syncthreads();
