@@ -666,9 +666,9 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       }
     }
     // the task's feature rows in level order at the tile pitch (pad columns zero; the 16 rows past the end belong to the last tile)
-    for (int64_t idx = gtid; idx < (int64_t)(n + 16) * S.xs; idx += gthreads) {
-      const int j = (int)(idx / S.xs), f = (int)(idx - (int64_t)j * S.xs);
-      xlo[idx] = (j < n && f < d) ? __ldg(A.g.feat + (size_t)__ldg(lo2gid + j) * d + f) : 0.f;
+    for (int j = warp * G + grank; j < n + 16; j += gnw) {   // a warp per row: coalesced read of the node's d floats, coalesced write
+      const float* const row = j < n ? A.g.feat + (size_t)__ldg(lo2gid + j) * d : nullptr;
+      for (int f = lane; f < S.xs; f += 32) xlo[(size_t)j * S.xs + f] = (row != nullptr && f < d) ? __ldg(row + f) : 0.f;
     }
     for (int e = gtid; e < e_d; e += gthreads) gE[e] = 0.f;   // slots outside the < n2 prefixes are never written and must read as 0
     for (int i = gtid; i < n; i += gthreads) {

@@ -135,8 +135,9 @@ class Explainer:
         """explain.py:492-501: (node_idx_new, sub_adj, sub_feat, sub_label, neighbors)."""
         plan = self.engine.plan_nodes([int(node_idx)], self.n_hops)
         nbrs = plan.neighbors_of(0).astype(np.int64)
-        sub_adj = plan.dense_of(0, np.ones(plan.total_edges, dtype=np.float64),
-                                dtype=np.asarray(self.adj).dtype)
+        # the caller's own adjacency rows / columns, exactly like the reference (adj[g][nbrs][:, nbrs]): self loops, if any, stay in
+        # sub_adj (the plan's edge list drops them, as the explainer's diag_mask does for the optimisation)
+        sub_adj = np.asarray(self.adj)[graph_idx][nbrs][:, nbrs]
         sub_feat = np.asarray(self.feat)[graph_idx, nbrs]
         sub_label = np.asarray(self.label)[graph_idx][nbrs]
         return int(plan.node_idx_new[0]), sub_adj, sub_feat, sub_label, nbrs
