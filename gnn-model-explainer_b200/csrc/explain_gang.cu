@@ -110,12 +110,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// c += (ahi + alo) (bhi + blo) without the lo*lo term; small terms first
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-  mma_tf32(c, alo, bh0, bh1);
-  mma_tf32(c, ahi, bl0, bl1);
-  mma_tf32(c, ahi, bh0, bh1);
-}
+// 3xTF32: (ahi + alo)(bhi + blo) without the lo*lo term = alo*bhi + ahi*blo (small) + ahi*bhi (big), each an mma_tf32 (see the callers)
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
@@ -383,21 +378,33 @@ __device__ __forceinline__ void dense_forward(int n, const GangSmem& S, int dwar
     if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8, pol); nx.next(); }
     mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf;
     const float* xr = xt0 + buf * 16 * xs;
-    float c[NTL][4];
+    // 3xTF32 with two accumulators per n-tile (small terms lo*hi + hi*lo, big term hi*hi) and the MMAs of the n-tiles interleaved:
+    // back-to-back MMAs into ONE accumulator serialise on the ~35-cycle MMA latency (the first version spent 3/4 of F0 there)
+    float cs[NTL][4], cb[NTL][4];
 #pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) { c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f; }
+    for (int nt = 0; nt < NTL; ++nt) { cs[nt][0] = cs[nt][1] = cs[nt][2] = cs[nt][3] = 0.f; cb[nt][0] = cb[nt][1] = cb[nt][2] = cb[nt][3] = 0.f; }
     for (int k0 = 0; k0 < dp8; k0 += 8) {
       uint32_t ahi[4], alo[4];
       tf32_split(xr[g * xs + k0 + t4], ahi[0], alo[0]);
       tf32_split(xr[(g + 8) * xs + k0 + t4], ahi[1], alo[1]);
       tf32_split(xr[g * xs + k0 + t4 + 4], ahi[2], alo[2]);
       tf32_split(xr[(g + 8) * xs + k0 + t4 + 4], ahi[3], alo[3]);
+      uint32_t bh0[NTL], bh1[NTL], bl0[NTL], bl1[NTL];
 #pragma unroll
       for (int nt = 0; nt < NTL; ++nt) {
         const int o0 = (k0 + t4) * ldb + nt * 8 + g, o1 = o0 + 4 * ldb;
-        mma_3xtf32(c[nt], ahi, alo, __float_as_uint(Whi[o0]), __float_as_uint(Whi[o1]), __float_as_uint(Wlo[o0]), __float_as_uint(Wlo[o1]));
+        bh0[nt] = __float_as_uint(Whi[o0]); bh1[nt] = __float_as_uint(Whi[o1]); bl0[nt] = __float_as_uint(Wlo[o0]); bl1[nt] = __float_as_uint(Wlo[o1]);
       }
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) mma_tf32(cs[nt], alo, bh0[nt], bh1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) mma_tf32(cb[nt], ahi, bh0[nt], bh1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) mma_tf32(cs[nt], ahi, bl0[nt], bl1[nt]);
     }
+    float c[NTL][4];
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) { c[nt][0] = cs[nt][0] + cb[nt][0]; c[nt][1] = cs[nt][1] + cb[nt][1]; c[nt][2] = cs[nt][2] + cb[nt][2]; c[nt][3] = cs[nt][3] + cb[nt][3]; }
     const int row0 = it.tile() * 16 + g;
 #pragma unroll
     for (int nt = 0; nt < NTL; ++nt) {
@@ -451,20 +458,38 @@ __device__ __forceinline__ void dense_backward(int n, int dp, const GangSmem& S,
       tf32_split((v0 && k1 < HID) ? pr[g * HID + k1] : 0.f, ahi[ks][2], alo[ks][2]);
       tf32_split((v1 && k1 < HID) ? pr[(g + 8) * HID + k1] : 0.f, ahi[ks][3], alo[ks][3]);
     }
+    // feature n-tiles two at a time, two accumulators each (small / big 3xTF32 terms): four independent MMA chains in flight
 #pragma unroll
-    for (int nt = 0; nt < NF8; ++nt) {
-      if (nt < nf8) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int np2 = 0; np2 < NF8; np2 += 2) {
+      if (np2 < nf8) {
+        float cs[2][4], cb[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { cs[j][0] = cs[j][1] = cs[j][2] = cs[j][3] = 0.f; cb[j][0] = cb[j][1] = cb[j][2] = cb[j][3] = 0.f; }
 #pragma unroll
         for (int ks = 0; ks < NTL; ++ks) {
-          const int o0 = (ks * 8 + t4) * ldt + nt * 8 + g, o1 = o0 + 4 * ldt;
-          mma_3xtf32(c, ahi[ks], alo[ks], __float_as_uint(Thi[o0]), __float_as_uint(Thi[o1]), __float_as_uint(Tlo[o0]), __float_as_uint(Tlo[o1]));
+          uint32_t bh0[2], bh1[2], bl0[2], bl1[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int nt = np2 + j < nf8 ? np2 + j : np2;   // (odd tile count: the second lane of the pair repeats the first, its result is dropped)
+            const int o0 = (ks * 8 + t4) * ldt + nt * 8 + g, o1 = o0 + 4 * ldt;
+            bh0[j] = __float_as_uint(Thi[o0]); bh1[j] = __float_as_uint(Thi[o1]); bl0[j] = __float_as_uint(Tlo[o0]); bl1[j] = __float_as_uint(Tlo[o1]);
+          }
+          mma_tf32(cs[0], alo[ks], bh0[0], bh1[0]); mma_tf32(cs[1], alo[ks], bh0[1], bh1[1]);
+          mma_tf32(cb[0], ahi[ks], bh0[0], bh1[0]); mma_tf32(cb[1], ahi[ks], bh0[1], bh1[1]);
+          mma_tf32(cs[0], ahi[ks], bl0[0], bl1[0]); mma_tf32(cs[1], ahi[ks], bl0[1], bl1[1]);
         }
-        const int col = nt * 8 + 2 * t4;
-        const float2 x0 = v0 ? *reinterpret_cast<const float2*>(xr + g * xs + col) : make_float2(0.f, 0.f);
-        const float2 x1 = v1 ? *reinterpret_cast<const float2*>(xr + (g + 8) * xs + col) : make_float2(0.f, 0.f);
-        ga[nt][0] = fmaf(c[0], x0.x, ga[nt][0]); ga[nt][1] = fmaf(c[1], x0.y, ga[nt][1]);
-        ga[nt][0] = fmaf(c[2], x1.x, ga[nt][0]); ga[nt][1] = fmaf(c[3], x1.y, ga[nt][1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int nt = np2 + j;
+          if (nt < nf8) {
+            const float c0 = cs[j][0] + cb[j][0], c1 = cs[j][1] + cb[j][1], c2 = cs[j][2] + cb[j][2], c3 = cs[j][3] + cb[j][3];
+            const int col = nt * 8 + 2 * t4;
+            const float2 x0 = v0 ? *reinterpret_cast<const float2*>(xr + g * xs + col) : make_float2(0.f, 0.f);
+            const float2 x1 = v1 ? *reinterpret_cast<const float2*>(xr + (g + 8) * xs + col) : make_float2(0.f, 0.f);
+            ga[nt][0] = fmaf(c0, x0.x, ga[nt][0]); ga[nt][1] = fmaf(c1, x0.y, ga[nt][1]);
+            ga[nt][0] = fmaf(c2, x1.x, ga[nt][0]); ga[nt][1] = fmaf(c3, x1.y, ga[nt][1]);
+          }
+        }
       }
     }
     __syncwarp();
@@ -602,7 +627,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     int32_t* const longlist = reinterpret_cast<int32_t*>(slab + L.longlist);
     float* const dP = slab + L.dP; float* const gE = slab + L.gE;
     float* const xlo = slab + L.xlo;
-    float2* const MM = MM0; float2* const mm = MM + np; float2* const vv = mm + np; float2* const SS = vv + np;
+    float2* const MM = MM0; float2* const mm = MM + np; float2* const vv = mm + np;   // (sigmoid(M) is recomputed, not stored)
     const float nn = (float)n * (float)n;
     const float ent_over_nn = hp.c_ent / nn;
     const float lap_over_nn = hp.c_lap / nn;
@@ -648,7 +673,6 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
         mm[p] = m2;
         vv[p] = v2;
         const float Si = resume ? sigmoid_fast(Mi, ieee) : sigmoid_f(Mi), Sj = resume ? sigmoid_fast(Mj, ieee) : sigmoid_f(Mj);   // a resumed state came out of the edge phase: same sigmoid as there, so that a split run equals the straight one bit for bit
-        SS[p] = make_float2(Si, Sj);
         const float a0 = hp.mode ? 1.0f : 0.5f * (Si + Sj);  // explain.py:665-678 ; gradient baseline: the adjacency itself
         a[ppij[p]] = a0;
         a[ppji[p]] = a0;
@@ -948,7 +972,10 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
           // streams (pair indices, optimiser state) pass through the L2 with evict_first, the scattered a / gE accesses keep their lines
           const int sij = ld_i32_stream(ppij + p, pol.first), sji = ld_i32_stream(ppji + p, pol.first);
           float2 Mv = ld_v2_pol(MM + p, pol.first);
-          const float2 Sv = ld_v2_pol(SS + p, pol.first);
+          // sigmoid(M) is recomputed instead of streamed (16 B less per pair and epoch): bit-identical to the value the previous
+          // epoch's update produced (same function of the same M); the first epoch of a fresh run uses the IEEE form like the init
+          const bool s_ieee = ieee || (it == 1 && !resume);
+          const float2 Sv = make_float2(s_ieee ? sigmoid_f(Mv.x) : sigmoid_fast(Mv.x, false), s_ieee ? sigmoid_f(Mv.y) : sigmoid_fast(Mv.y, false));
           float2 m2 = ld_v2_pol(mm + p, pol.first), v2 = ld_v2_pol(vv + p, pol.first);
           float Gd = ld_f32_pol(lapg + p, pol.first) + ld_f32_pol(gE + sji, pol.last) + ld_f32_pol(gE + sij, pol.last);
           if (p < np1) {
@@ -972,7 +999,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
           Mv.x = Mv.x - adam_delta_fast(m2.x, v2.x, step, bc2s, bc2s_inv, hp.eps, ieee);
           Mv.y = Mv.y - adam_delta_fast(m2.y, v2.y, step, bc2s, bc2s_inv, hp.eps, ieee);
           const float2 Sn = make_float2(sigmoid_fast(Mv.x, ieee), sigmoid_fast(Mv.y, ieee));
-          st_v2_pol(MM + p, Mv, pol.first); st_v2_pol(mm + p, m2, pol.first); st_v2_pol(vv + p, v2, pol.first); st_v2_pol(SS + p, Sn, pol.first);
+          st_v2_pol(MM + p, Mv, pol.first); st_v2_pol(mm + p, m2, pol.first); st_v2_pol(vv + p, v2, pol.first);
           const float an = 0.5f * (Sn.x + Sn.y);
           if (kTrace) trD += 2.0f * an;
           st_f32_pol(a + sij, an, pol.last);
