@@ -306,8 +306,8 @@ class Explainer:
     def explain_nodes(self, node_indices, args=None, graph_idx=0, save=True, copy=True):
         """explain.py:225-292 -> list of (n,n) float64 masked adjacencies in input order.  One batched launch; the dense arrays are
         built ON DEVICE (gx_densify) and come back in one transfer -- the list entries are views of that one buffer:
-          copy=True  (default) a fresh host array per call (independent results, like the reference's);
-          copy=False a pinned buffer owned by the Explainer, overwritten by the next call (zero host copies).
+          copy=True  (default) independent results like the reference's: views of a pinned buffer that is not reused while any of them is alive;
+          copy=False ONE pinned buffer owned by the Explainer, overwritten by the next call.
         save=True writes the reference's per-node .npy files (explain.py:216-220), which at ~0.4 MB per node dominates the call;
         args.gnnx_init="device" removes the n^2 host normals per node of the torch-compatible init."""
         if self.print_training or graph_idx not in (0, -1):
@@ -325,7 +325,8 @@ class Explainer:
             mask_dev = eng.explain_nodes_device(hp, m0_dev)
             dense_dev = eng.densify_device(mask_dev)
             if copy:
-                host = dense_dev.cpu().numpy()
+                host = self._result_buffer(dense_dev.numel())       # pinned, never handed out twice while a result still refers to it
+                torch.from_numpy(host)[:dense_dev.numel()].copy_(dense_dev)
             else:
                 if getattr(self, "_pinned", None) is None or self._pinned.numel() < dense_dev.numel():
                     self._pinned = torch.empty(max(dense_dev.numel(), 1), dtype=torch.float64).pin_memory()
@@ -338,6 +339,21 @@ class Explainer:
             for t, node in enumerate(node_indices):
                 self._save(out[t], int(node))
         return out
+
+    def _result_buffer(self, numel):
+        """Host memory for one call's dense results: a pinned buffer from a small pool.  The returned arrays are views of it
+        (numpy keeps the buffer alive through .base), and a buffer is reused only when no earlier result refers to it any more
+        (sys.getrefcount), so results stay independent like the reference's -- without a 0.3 GB pageable allocation + copy per call."""
+        import sys
+        pool = self.__dict__.setdefault("_pool", [])
+        for i, (t, a) in enumerate(pool):
+            if t.numel() >= numel and sys.getrefcount(a) <= 3:      # pool tuple + loop variable + getrefcount's argument
+                return a
+        pool[:] = [(t, a) for (t, a) in pool if sys.getrefcount(a) > 3][-2:]     # drop idle buffers that are too small
+        t = torch.empty(max(int(numel), 1), dtype=torch.float64).pin_memory()
+        a = t.numpy()
+        pool.append((t, a))
+        return a
 
     # ---------------------------------------------------------------- evaluation step right after the masks
     # planted-motif edges relative to the first motif node, in the sorted local numbering (explain.py:537-577)
