@@ -1,8 +1,8 @@
 """Multi-GPU plumbing: nodes-to-explain are independent units, so they are dealt across ranks (one process per GPU) with
 NO data-path collective; the only exchange is ONE all-gather of the packed edge masks at the end.
 
-How one collective suffices: every rank counts the k-hop subgraph of EVERY node of the list first (gx_count_nodes: the
-integer frontier expansion without building a plan, ~0.2 ms for 700 nodes), so the shard assignment (cost balanced), every
+How one collective suffices: every rank knows the k-hop subgraph size of EVERY node of the list (gx_count_nodes: the
+integer frontier expansion without building a plan, ~0.2 ms for 700 nodes, remembered per graph), so the shard assignment (cost balanced), every
 rank's payload size and every item's offset are known everywhere without a metadata exchange.  Each rank pads its packed masks to
 the largest per-rank payload, ONE all-gather moves the slots (NCCL over NVLink through the library's own communicator,
 gx_allgather_masks; torch.distributed -- gloo in the CPU tests -- when no engine communicator exists), and a device kernel
@@ -77,20 +77,39 @@ def ensure_comm(engine, group=None):
     engine.comm_init(world, rank, box[0])
 
 
+def count_nodes_cached(explainer, nodes):
+    """(n, E_d) of every node of the list.  The k-hop sizes are a property of (graph, node, n_hops), so they are counted once per
+    Explainer graph (gx_count_nodes on the nodes not seen yet) and remembered: a steady stream of explain calls pays nothing here."""
+    eng = explainer.engine
+    key = (getattr(explainer, "_current_graph", 0), int(explainer.n_hops))
+    cache = explainer.__dict__.setdefault("_count_cache", {})
+    if key not in cache:
+        N = eng.num_nodes
+        cache[key] = (np.full(N, -1, np.int64), np.zeros(N, np.int64))
+    n_c, e_c = cache[key]
+    nodes = np.asarray(nodes, np.int64)
+    todo = np.unique(nodes[n_c[nodes] < 0])
+    if len(todo):
+        n_new, e_new = eng.count_nodes(todo.astype(np.int32), explainer.n_hops)
+        n_c[todo] = n_new; e_c[todo] = e_new
+    return n_c[nodes], e_c[nodes]
+
+
 def explain_nodes_sharded(explainer, node_indices, costs=None, group=None, use_engine_comm=True):
     """Explainer.explain_nodes across all ranks of the default process group.
-    Every rank returns the packed masks of ALL nodes: (values float32 tensor, offsets int64 array, (local plan, local positions));
+    Every rank returns the packed masks of ALL nodes: (values float32 tensor, offsets int64 array, (local plan or None, local positions));
     values[offsets[t]:offsets[t+1]] are the masked_adj entries of node_indices[t] at the row-major sub-adjacency slots."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     eng = explainer.engine
     nodes = np.asarray(node_indices)
     dev = torch.device("cuda", eng.device)
-    n_all, e_all = eng.count_nodes(nodes, explainer.n_hops)
+    n_all, e_all = count_nodes_cached(explainer, nodes)
     shards = shard_layout(e_all, world, costs)[0]
     pos = shards[rank]
     hp, init = explainer._hparams()
     if len(pos):
-        plan = eng.plan_nodes(nodes[pos], explainer.n_hops)
+        # the canonical sub-graph description comes back to the host only when the torch-compatible init needs it (M0 gather)
+        plan = eng.plan_nodes(nodes[pos], explainer.n_hops, fetch=(init == "torch"))
         m0_dev = None
         if init == "torch":   # every rank walks the whole list so that torch's RNG is consumed exactly as one process would
             m0_dev = torch.from_numpy(explainer._draw_m0_subset(plan, n_all, pos)).to(dev)

@@ -112,27 +112,49 @@ class Explainer:
                 raise ValueError("graph mode expects adj of shape (G,n,n)")
             self.engine.set_graph_batch(adj_np, np.asarray(feat), np.asarray(label))
             return
-        if adj_np.ndim != 3 or adj_np.shape[0] != 1:
-            raise NotImplementedError("node mode expects adj of shape (1,N,N) (single graph)")
-        self._rowptr, self._col = _gu.csr_from_dense(adj_np[0])
-        feat_np = np.asarray(feat, dtype=np.float32)[0]
-        label_np = np.asarray(label)[0].astype(np.int32)
-        pred_np = np.asarray(pred)[0]
-        self._pred_label = np.argmax(pred_np, axis=1).astype(np.int32)          # explain.py:105
+        if adj_np.ndim != 3:
+            raise ValueError("node mode expects adj of shape (B,N,N)")
+        # node tasks on a batch of graphs (explain.py:80-95 index adj / feat / label / pred with graph_idx): the engine holds one graph
+        # at a time, graph 0 is uploaded now, another one when a call names it
+        self._csr_cache = {}
+        self._current_graph = None
+        self._select_graph(0)
+
+    def _select_graph(self, graph_idx):
+        g = 0 if graph_idx in (-1, None, False) else int(graph_idx)
+        if g == self._current_graph:
+            return g
+        adj_np = np.asarray(self.adj)
+        if not 0 <= g < adj_np.shape[0]:
+            raise IndexError("graph_idx %d out of range for adj of shape %s" % (g, adj_np.shape))
+        if g not in self._csr_cache:
+            self._csr_cache[g] = _gu.csr_from_dense(adj_np[g])
+        self._rowptr, self._col = self._csr_cache[g]
+        feat_np = np.asarray(self.feat, dtype=np.float32)[g]
+        label_np = np.asarray(self.label)[g].astype(np.int32)
+        self._pred_label = np.argmax(np.asarray(self.pred)[g], axis=1).astype(np.int32)          # explain.py:105
         self.engine.set_graph_csr(self._rowptr, self._col, feat_np, label_np, self._pred_label)
+        self._current_graph = g
+        return g
 
     # the reference computes this dense (B,N,N) matrix eagerly in __init__ (explain.py:67); here
     # it is materialised on demand only (the engine never needs it).
     @property
     def neighborhoods(self):
         if self._neighborhoods is None:
-            N = self.engine.num_nodes
-            rows = self.engine.neighborhood_rows(np.arange(N, dtype=np.int32), self.n_hops)
-            self._neighborhoods = rows.astype(int)[None]
+            keep = self._current_graph
+            mats = []
+            for g in range(np.asarray(self.adj).shape[0]):
+                self._select_graph(g)
+                N = self.engine.num_nodes
+                mats.append(self.engine.neighborhood_rows(np.arange(N, dtype=np.int32), self.n_hops).astype(int))
+            self._select_graph(keep)
+            self._neighborhoods = np.stack(mats)
         return self._neighborhoods
 
     def extract_neighborhood(self, node_idx, graph_idx=0):
         """explain.py:492-501: (node_idx_new, sub_adj, sub_feat, sub_label, neighbors)."""
+        graph_idx = self._select_graph(graph_idx)
         plan = self.engine.plan_nodes([int(node_idx)], self.n_hops)
         nbrs = plan.neighbors_of(0).astype(np.int64)
         # the caller's own adjacency rows / columns, exactly like the reference (adj[g][nbrs][:, nbrs]): self loops, if any, stay in
@@ -199,8 +221,7 @@ class Explainer:
             raise NotImplementedError("model=%r (att) is not built" % model)
         if unconstrained:
             raise NotImplementedError("unconstrained=True is not built")
-        if graph_idx not in (0, -1):
-            raise NotImplementedError("multi-graph node tasks (graph_idx != 0) are not built")
+        self._select_graph(graph_idx)
         nodes = [int(i) for i in node_indices]
         plan = self.engine.plan_nodes(nodes, self.n_hops)
         edge_mask = np.empty(plan.total_edges, dtype=np.float32)
@@ -310,7 +331,8 @@ class Explainer:
           copy=False ONE pinned buffer owned by the Explainer, overwritten by the next call.
         save=True writes the reference's per-node .npy files (explain.py:216-220), which at ~0.4 MB per node dominates the call;
         args.gnnx_init="device" removes the n^2 host normals per node of the torch-compatible init."""
-        if self.print_training or graph_idx not in (0, -1):
+        self._select_graph(graph_idx)
+        if self.print_training:
             plan, edge_mask = self._explain_batch(node_indices, graph_idx)
             out = [plan.dense_of(t, edge_mask, dtype=np.float64) for t in range(plan.count)]
         else:

@@ -316,6 +316,37 @@ def test_explainer_dropin_reproduces_reference_under_torch_seed(syn1, tmp_path):
     assert hop.shape == (1, syn1.N, syn1.N) and hop[0, 300].sum() == len(syn1.gold["n300_nbrs"])
 
 
+def test_node_tasks_on_a_batch_of_graphs(syn1, tmp_path):
+    """explain.py:80-95 index adj / feat / label / pred with graph_idx: an Explainer built on a batch (B, N, N) of graphs must
+    explain node i of graph g exactly like an Explainer built on graph g alone (here: graph 1 = syn1 relabelled by a permutation,
+    so graph 0 and graph 1 give different sub-graph orderings for the same node id)."""
+    fx = syn1
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(fx.N)
+    A0 = O.dense_from_csr(fx.rowptr, fx.col)
+    A1 = A0[perm][:, perm]
+    adj = np.stack([A0, A1]); feat = np.stack([fx.feat, fx.feat[perm]]).astype(np.float64)
+    label = np.stack([fx.label, fx.label[perm]]); pred = np.stack([fx.pred, fx.pred[perm]])
+    ex, args = _explainer(fx, tmp_path, num_epochs=10)
+    both = gnnx.Explainer(model=ex.model, adj=adj, feat=feat, label=label, pred=pred, train_idx=list(range(fx.N)), args=args, writer=None,
+                          print_training=False, graph_idx=-1)
+    only1 = gnnx.Explainer(model=ex.model, adj=adj[1:], feat=feat[1:], label=label[1:], pred=pred[1:], train_idx=list(range(fx.N)), args=args,
+                           writer=None, print_training=False, graph_idx=-1)
+    for node in (5, 300, 620):
+        torch.manual_seed(11 + node); a = both.explain(node, graph_idx=1)
+        torch.manual_seed(11 + node); b = only1.explain(node, graph_idx=0)
+        assert np.array_equal(a, b)
+        torch.manual_seed(11 + node); c = both.explain(node, graph_idx=0)
+        torch.manual_seed(11 + node); d = ex.explain(node, graph_idx=0)
+        assert np.array_equal(c, d)
+        _, sa, sf, sl, nb = both.extract_neighborhood(node, graph_idx=1)
+        assert np.array_equal(sa, A1[nb][:, nb]) and np.array_equal(sl, label[1][nb])
+    torch.manual_seed(5); batch1 = both.explain_nodes([5, 300], args, graph_idx=1, save=False)
+    torch.manual_seed(5); solo1 = only1.explain_nodes([5, 300], args, graph_idx=0, save=False)
+    assert all(np.array_equal(x, y) for x, y in zip(batch1, solo1))
+    assert both.neighborhoods.shape == (2, fx.N, fx.N)
+
+
 def test_error_behaviour(tmp_path):
     fx = util.load_fixture("rand")
     eng = util.make_engine(fx)
