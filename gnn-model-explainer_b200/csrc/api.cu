@@ -101,7 +101,7 @@ struct gx_handle {
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
   DevBuf d_pws, d_gws, d_adam, d_m0, d_out, d_feat, d_dense_off, d_dense, d_rows;
   DevBuf d_trace, d_trpred, d_trouter, d_min, d_vin, d_fsin, d_Mout, d_mout, d_vout, d_fsout, d_m0dense, d_offedge;   // gx_explain_io staging (GX_HOST)
-  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals, d_send, d_us, d_gang;
+  DevBuf d_dn_thr, d_dn_cnt, d_dn_slots, d_dn_vals, d_send, d_us, d_gang, d_fwd;
   GxComm* comm = nullptr;
   int32_t label_min = 0, label_max = 0, pred_min = 0, pred_max = 0;   // ranges of the uploaded labels (checked against num_classes at plan time)
   bool has_label = false;
@@ -252,7 +252,7 @@ int gx_destroy(gx_handle* h) {
                     &h->d_pairs, &h->d_order, &h->d_counters, &h->gb_rowptr, &h->gb_col, &h->gb_feat, &h->gb_label, &h->d_pws, &h->d_gws, &h->d_adam, &h->d_m0, &h->d_out,
                     &h->d_feat, &h->d_dense_off, &h->d_dense, &h->d_rows, &h->ws_buf, &h->d_trace, &h->d_trpred, &h->d_trouter, &h->d_min, &h->d_vin,
                     &h->d_fsin, &h->d_Mout, &h->d_mout, &h->d_vout, &h->d_fsout, &h->d_m0dense, &h->d_offedge,
-                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals, &h->d_send, &h->d_us, &h->d_gang};
+                    &h->d_dn_thr, &h->d_dn_cnt, &h->d_dn_slots, &h->d_dn_vals, &h->d_send, &h->d_us, &h->d_gang, &h->d_fwd};
   gx_comm_impl_destroy(h->comm);
   h->comm = nullptr;
   for (DevBuf* b : bufs) b->release();
@@ -289,6 +289,23 @@ int gx_debug_set_dump(gx_handle* h, float* dev_buf) { if (!h) return GX_ERR_INVA
 int gx_debug_ieee_edge(gx_handle* h, int on) { if (!h) return GX_ERR_INVALID; h->ieee_edge = on != 0; return GX_OK; }
 
 /* debug only (not in gnnx.h): plan every task into the streaming class (explain_stream.cu) regardless of its size */
+int gx_model_forward(gx_handle* h, gx_memspace space, float* pred) {
+  if (!h || !pred) { gx_set_error("gx_model_forward: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->has_graph || !h->has_model) { gx_set_error("gx_model_forward: call gx_set_model and gx_set_graph_csr first"); return GX_ERR_INVALID; }
+  if (h->g.d != h->m.d) { gx_set_error("gx_model_forward: graph feat_dim %d != model input_dim %d", h->g.d, h->m.d); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const size_t np_ = (size_t)h->g.N * h->m.C;
+  GX_CUDA_CHECK(h->d_fwd.reserve(((size_t)h->m.L * h->g.N * 32 + np_) * 4));
+  float* H = h->d_fwd.as<float>();
+  float* pd = space == GX_DEVICE ? pred : H + (size_t)h->m.L * h->g.N * 32;
+  GX_CUDA_CHECK(gx_launch_model_forward(h->g, h->m, H, pd, nullptr, h->stream));
+  h->launches += h->m.L + 1;
+  if (space != GX_DEVICE) {
+    GX_CUDA_CHECK(cudaMemcpyAsync(pred, pd, np_ * 4, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return GX_OK;
+}
 int gx_debug_set_gang(gx_handle* h, int ctas_per_task) { if (!h) return GX_ERR_INVALID; h->gang_override = ctas_per_task; return GX_OK; }
 int gx_debug_set_cluster(gx_handle* h, int cluster_size, int64_t min_cost) {
   if (!h || !(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4)) return GX_ERR_INVALID;
@@ -898,8 +915,8 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     } else if (c == kStreamClass && gang > 0) {
       cfg.gang = gang;
       cfg.grid = stream_grid * gang;
-      GX_CUDA_CHECK(h->d_gang.reserve((size_t)stream_grid * 16));
-      GX_CUDA_CHECK(cudaMemsetAsync(h->d_gang.p, 0, (size_t)stream_grid * 16, h->side[c]));
+      GX_CUDA_CHECK(h->d_gang.reserve((size_t)stream_grid * 24));
+      GX_CUDA_CHECK(cudaMemsetAsync(h->d_gang.p, 0, (size_t)stream_grid * 24, h->side[c]));
       cfg.gang_bars = h->d_gang.as<unsigned long long>();
       cfg.gang_mail = reinterpret_cast<int32_t*>(h->d_gang.as<char>() + (size_t)stream_grid * 8);
       GX_CUDA_CHECK(gx_launch_explain_gang(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));

@@ -21,7 +21,7 @@ EXPORTS = [
     "gx_set_graph_batch_csr", "gx_plan_graphs", "gx_explain_graphs", "gx_grad_nodes",
     "gx_explain_nodes_ex", "gx_explain_graphs_ex", "gx_offedge_regularisers",
     "gx_debug_force_stream", "gx_debug_ieee_edge", "gx_debug_set_dump", "gx_debug_set_gang", "gx_debug_set_cluster", "gx_denoise_topk",
-    "gx_comm_unique_id", "gx_comm_init", "gx_comm_destroy", "gx_count_nodes", "gx_allgather_masks", "gx_unshard_masks",
+    "gx_model_forward", "gx_comm_unique_id", "gx_comm_init", "gx_comm_destroy", "gx_count_nodes", "gx_allgather_masks", "gx_unshard_masks",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.gx_debug_force_stream.argtypes = [vp, C.c_int]
     L.gx_debug_ieee_edge.argtypes = [vp, C.c_int]
     L.gx_debug_set_dump.argtypes = [vp, vp]
+    L.gx_model_forward.argtypes = [vp, C.c_int, f32p]
     L.gx_debug_set_gang.argtypes = [vp, C.c_int]
     L.gx_debug_set_cluster.argtypes = [vp, C.c_int, C.c_int64]
     L.gx_launch_count.argtypes = [vp]

@@ -352,6 +352,12 @@ class Engine:
         """Test knob: plan every task into the streaming kernel (explain_stream.cu) regardless of its size."""
         _abi.check(self._lib.gx_debug_force_stream(self._h, int(bool(on))))
 
+    def model_forward(self):
+        """Logits (N, C) of the uploaded model on the uploaded graph: GcnEncoderNode.forward(x, adj)[0][0] (gx_model_forward)."""
+        out = np.zeros((self.num_nodes, self.num_classes), np.float32)
+        _abi.check(self._lib.gx_model_forward(self._h, _abi.GX_HOST, _np_ptr(out)))
+        return out
+
     def debug_gang(self, ctas_per_task=0):
         """Test knob: CTAs per task of the streaming kernel (0 automatic, -1 first-generation kernel)."""
         _abi.check(self._lib.gx_debug_set_gang(self._h, int(ctas_per_task)))

@@ -117,6 +117,7 @@ class Explainer:
         # node tasks on a batch of graphs (explain.py:80-95 index adj / feat / label / pred with graph_idx): the engine holds one graph
         # at a time, graph 0 is uploaded now, another one when a call names it
         self._csr_cache = {}
+        self._own_pred = {}
         self._current_graph = None
         self._select_graph(0)
 
@@ -132,7 +133,16 @@ class Explainer:
         self._rowptr, self._col = self._csr_cache[g]
         feat_np = np.asarray(self.feat, dtype=np.float32)[g]
         label_np = np.asarray(self.label)[g].astype(np.int32)
-        self._pred_label = np.argmax(np.asarray(self.pred)[g], axis=1).astype(np.int32)          # explain.py:105
+        if self.pred is None or g in self._own_pred:
+            # no stored predictions (the reference reads cg["pred"] from the checkpoint, explainer_main.py:186-193): run the model's
+            # forward on the device (gx_model_forward = GcnEncoderNode.forward on the whole graph) and keep the logits
+            if g not in self._own_pred:
+                self.engine.set_graph_csr(self._rowptr, self._col, feat_np, label_np, np.zeros(len(label_np), np.int32))
+                self._own_pred[g] = self.engine.model_forward()
+            pred_g = self._own_pred[g]
+        else:
+            pred_g = np.asarray(self.pred)[g]
+        self._pred_label = np.argmax(pred_g, axis=1).astype(np.int32)          # explain.py:105
         self.engine.set_graph_csr(self._rowptr, self._col, feat_np, label_np, self._pred_label)
         self._current_graph = g
         return g

@@ -248,6 +248,11 @@ int gx_allgather_masks(gx_handle* h, const float* local_dev, int64_t local_float
 int gx_unshard_masks(gx_handle* h, const float* gathered_dev, int32_t items, const int64_t* src_off, const int64_t* dst_off,
                      const int32_t* sizes, float* out_dev);
 
+/* GcnEncoderNode.forward on the uploaded graph (models.py:58-80,230-267,363-376): pred[num_nodes * num_classes] = the logits the
+ * reference reads from its checkpoint (`cg["pred"]`, explainer_main.py:186-193) and hands to Explainer(pred=...).  Raw adjacency
+ * (self loops included), no masks; every model gx_set_model accepts (2 / 3 / 4 layers, --bn). */
+int gx_model_forward(gx_handle* h, gx_memspace space, float* pred);
+
 /* Counters for bench.py: number of kernels this handle has launched so far, and the device time
  * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);

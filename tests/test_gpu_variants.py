@@ -139,3 +139,38 @@ def test_optimiser_variants_match_reference_golden(tag, over, stream):
     for t, node in enumerate(fx.nodes):
         err = util.rel_l2(out[plan.edge_off[t]:plan.edge_off[t + 1]], g["%s_n%d_mask" % (tag, node)])
         assert err <= 1e-4, (tag, node, err)
+
+
+def test_model_forward_matches_reference_predictions(tmp_path):
+    """gx_model_forward (GcnEncoderNode.forward on the whole graph, models.py:58-80,230-267,363-376) against the logits the
+    UNMODIFIED reference produced: syn1 / syn4 (trained checkpoints, golden/*_graph.npz `pred`) and the 2-layer, 4-layer and --bn
+    models of variants_golden.npz; and Explainer(pred=None) uses it to obtain the predicted labels."""
+    for name in ("syn1", "syn4", "rand"):
+        fx = util.load_fixture(name)
+        eng = util.make_engine(fx)
+        got = eng.model_forward()
+        eng.close()
+        assert got.shape == fx.pred.shape
+        assert np.abs(got - fx.pred).max() <= 2e-5 * max(1.0, np.abs(fx.pred).max()), name
+        assert np.array_equal(np.argmax(got, 1), fx.pred_label)
+    g = np.load(util.GOLDEN + "/variants_golden.npz")
+    N = int(g["N"])
+    rowptr, col = O.csr_from_edges(N, g["edges"])
+    for tag, L, bn in (("L2", 2, False), ("L4", 4, False), ("bn", 3, True)):
+        w = {k[len(tag) + 1:]: g[k] for k in g.files if k.startswith(tag + "_W") or k.startswith(tag + "_b")}
+        ref = g[tag + "_pred"]
+        eng = _engine(rowptr, col, g["feat"].astype(np.float32), g["label"].astype(np.int32), np.argmax(ref, 1).astype(np.int32), w, L, bn)
+        got = eng.model_forward()
+        eng.close()
+        assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), tag
+    # the drop-in without stored predictions
+    import torch
+    import test_gpu_parity as P
+    fx = util.load_fixture("syn1")
+    ex, args = P._explainer(fx, tmp_path, num_epochs=10)
+    A = O.dense_from_csr(fx.rowptr, fx.col)
+    nopred = gnnx.Explainer(model=ex.model, adj=A[None], feat=fx.feat[None].astype(np.float64), label=fx.label[None], pred=None,
+                            train_idx=list(range(fx.N)), args=args, writer=None, print_training=False, graph_idx=-1)
+    torch.manual_seed(3); a = nopred.explain(300)
+    torch.manual_seed(3); b = ex.explain(300)
+    assert np.array_equal(a, b)
