@@ -268,6 +268,16 @@ def _sm_metrics(tag):
     return None
 
 
+def _c5_traffic(K):
+    """DRAM bytes of one configs[4] launch, from the committed ncu capture (one 100 000-node task x 15 updates: dram__bytes_read + write
+    per task-epoch) x K tasks x 99 updates; None when the capture is not there."""
+    m = _sm_metrics("c5")
+    try:
+        return float(m["steady_state_one_task_16_epochs"]["dram_bytes_per_task_epoch"]) * K * (NUM_EPOCHS - 1)
+    except Exception:
+        return None
+
+
 def cpu_baseline_subprocess(workload, timeout=300):
     """The CPU arm on a bounded sample, in a separate process (the worker pool must fork before torch/CUDA exist)."""
     import subprocess
@@ -693,7 +703,7 @@ def bench_c5(a, c):
         "e2e": {"value": K / float(np.mean(wall)), "unit": "nodes/s", "ms_per_step": 1e3 * float(np.mean(wall)),
                 "h2d_bytes_per_step": int(K * 4), "d2h_bytes_per_step": int(total_e * 4)},
         "gpu_launches": int(4 * a.steps), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": algo / kern_s / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / kern_s / 1e9 / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": algo / kern_s / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / kern_s / 1e9 / peak, "traffic": _c5_traffic(K),
                      "peak_source": peak_src, "kernel": "explain_gang_kernel (gangs of co-resident CTAs per node, TMA-staged 3xTF32 mma.sync feature passes) + outer_pairs_kernel", "algorithmic_bytes_per_step": algo, "sm": _sm_metrics("c5"),
                      "note": "algorithmic bytes = SURVEY 8(d) fused lower bound of the UNPRUNED algorithm (84*E_d + 8*n*d per node-epoch); the kernel "
                              "prunes to the receptive field and runs outermost pairs as register recurrences, so it can move fewer bytes than that"},

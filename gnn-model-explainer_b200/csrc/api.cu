@@ -915,8 +915,8 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     } else if (c == kStreamClass && gang > 0) {
       cfg.gang = gang;
       cfg.grid = stream_grid * gang;
-      GX_CUDA_CHECK(h->d_gang.reserve((size_t)stream_grid * 24));
-      GX_CUDA_CHECK(cudaMemsetAsync(h->d_gang.p, 0, (size_t)stream_grid * 24, h->side[c]));
+      GX_CUDA_CHECK(h->d_gang.reserve((size_t)stream_grid * 16));
+      GX_CUDA_CHECK(cudaMemsetAsync(h->d_gang.p, 0, (size_t)stream_grid * 16, h->side[c]));
       cfg.gang_bars = h->d_gang.as<unsigned long long>();
       cfg.gang_mail = reinterpret_cast<int32_t*>(h->d_gang.as<char>() + (size_t)stream_grid * 8);
       GX_CUDA_CHECK(gx_launch_explain_gang(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));

@@ -27,8 +27,7 @@ namespace {
 #endif
 constexpr int kGangThreads = 512;    // 16 warps, 128 registers per thread (the tensor-core passes hold 24 A fragments + 32 accumulators)
 constexpr int kDenseWarps = 6;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
-constexpr int kLongEdges = 512;      // rows with more edges are sliced over all 16 warps of one CTA
-constexpr int kMidEdges = 128;       // rows with more edges (up to kLongEdges) are sliced over four warps, four such rows per round
+constexpr int kLongEdges = 512;      // rows with more edges are sliced over all warps of one CTA
 constexpr int kBlockTiles = 8;       // dL/dsF is reduced over fixed blocks of 8 tiles (128 nodes): independent of the gang size
 
 struct GangSmem {
@@ -231,8 +230,7 @@ __device__ __forceinline__ float4 slot_reduce(float4 z) {
 template <int HID, bool kRelu, bool kDot, typename Bounds, typename Epi>
 __device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int warp, int nwarps, int lane, const int32_t* __restrict__ irp,
                                          const int32_t* __restrict__ icol, const float* a, const float* src, const float* dotsrc, float* gout,
-                                         const int32_t* longlist, int nlong, const int32_t* midlist, int nmid, float* part, int* row_ctr, const L2Pol pol,
-                                         Bounds bounds, Epi epi) {
+                                         const int32_t* longlist, int nlong, float* part, int* row_ctr, const L2Pol pol, Bounds bounds, Epi epi) {
   constexpr int H4 = HID / 4, EPL = 32 / H4;
   const int q = lane % H4;
   // long rows of this CTA
@@ -257,32 +255,6 @@ __device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int wa
     }
     __syncthreads();
   }
-  // mid rows (kMidEdges < degree <= kLongEdges) of this CTA: four per round, four warps each.  A 500-edge row on ONE warp was the
-  // critical path of every sparse phase (20 dependent gather steps while the other warps wait at the phase barrier).
-  for (int kb = grank * 4; kb < nmid; kb += 4 * G) {
-    const int sub = warp >> 2, seg = warp & 3;
-    const int k = kb + sub;
-    const int i = k < nmid ? midlist[k] : R;
-    const bool valid = i < R;
-    if (valid) {
-      int r0, r1;
-      bounds(i, r0, r1);
-      const int per = gx_round_up((r1 - r0 + 3) / 4, 4 * EPL);
-      const int s0 = min(r1, r0 + seg * per), s1 = min(r1, s0 + per);
-      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kDot && lane < EPL * H4) dv = ldcg4(dotsrc + (size_t)i * HID + 4 * q);
-      const float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(s0, s1, lane, icol, a, src, dv, gout, pol));
-      if (lane < H4) st4(part + warp * HID + 4 * lane, z);
-    }
-    __syncthreads();
-    if (valid && seg == 0) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < H4)
-        for (int w = 0; w < 4; ++w) { const float4 o = ld4(part + (sub * 4 + w) * HID + 4 * lane); t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-      epi(i, t);
-    }
-    __syncthreads();
-  }
   // everything else: one warp per row.  Row i belongs to CTA i mod G; inside the CTA the warps draw the next row from a shared
   // counter (rows are sorted by degree inside a level, so this is longest-first scheduling; a row's result does not depend on
   // which warp takes it).
@@ -292,8 +264,8 @@ __device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int wa
     if (lane == 0) k = atomicAdd(row_ctr, 1);
     k = __shfl_sync(0xffffffffu, k, 0);
     const int i = k * G + grank;
-    if (i >= Rn) break;   // (rows Rn .. R-1: only the long / mid ones, above)
-    if (nlong + nmid > 0 && irp[i + 1] - irp[i] > kMidEdges) continue;
+    if (i >= Rn) break;   // (rows Rn .. R-1: only the long ones, above)
+    if (nlong > 0 && irp[i + 1] - irp[i] > kLongEdges) continue;
     int r0, r1;
     bounds(i, r0, r1);
     float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -310,7 +282,7 @@ __device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int wa
 template <int HID, typename Bounds>
 __device__ __forceinline__ void short_rows_pass(int R0, int R, int G, int grank, int lane, const int32_t* __restrict__ irp,
                                                 const int32_t* __restrict__ icol, const float* a, const float* src, const float* dotsrc,
-                                                float* gout, float* out, int nlong_mid, int* row_ctr, const L2Pol pol, Bounds bounds) {
+                                                float* gout, float* out, int nlong, int* row_ctr, const L2Pol pol, Bounds bounds) {
   constexpr int H4 = HID / 4, EPL = 32 / H4, UN = 4;
   const int es = lane / H4, q = lane - es * H4;
   const bool act = es < EPL;
@@ -322,7 +294,7 @@ __device__ __forceinline__ void short_rows_pass(int R0, int R, int G, int grank,
     const int i = R0 + (k + es) * G + grank;
     int r0 = 0, r1 = 0;
     bool mine = act && i < R;
-    if (mine && nlong_mid > 0 && irp[i + 1] - irp[i] > kMidEdges) mine = false;
+    if (mine && nlong > 0 && irp[i + 1] - irp[i] > kLongEdges) mine = false;
     if (mine) bounds(i, r0, r1);
     const float4 dv = mine ? ldcg4(dotsrc + (size_t)i * HID + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -559,7 +531,7 @@ struct GangArgs {
   ExplainArgs A;
   int G;                          // CTAs per gang
   unsigned long long* bars;       // [ngangs] barrier counters (zeroed before the launch)
-  int32_t* mail;                  // [ngangs * 4] task mailbox + long-row / mid-row counters
+  int32_t* mail;                  // [ngangs * 2] task mailbox + long-row counter
 };
 
 template <int HID, int EMB, bool kTrace>
@@ -627,12 +599,12 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   float2* const MM0 = reinterpret_cast<float2*>(A.pws + (int64_t)gang * A.pws_stride_words);
   GangBar bar{GA.bars + gang, 0ull, G};
   const L2Pol pol = make_l2pol();
-  int32_t* const mail = GA.mail + gang * 4;
+  int32_t* const mail = GA.mail + gang * 2;
   const int gtid = grank * NT + tid, gthreads = G * NT;
   const int gnw = nwarps * G;
 
   for (;;) {
-    if (grank == 0 && tid == 0) { mail[0] = atomicAdd(A.counter, 1); mail[1] = 0; mail[2] = 0; }
+    if (grank == 0 && tid == 0) { mail[0] = atomicAdd(A.counter, 1); mail[1] = 0; }
     bar.sync();
     const int qi = __ldcg(mail);
     if (qi >= A.ntasks) break;
@@ -653,7 +625,6 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     float* const lapg = slab + L.lapg; float* const gFb = slab + L.gFb;
     int32_t* const cnt1 = reinterpret_cast<int32_t*>(slab + L.cnt1); int32_t* const cnt2 = reinterpret_cast<int32_t*>(slab + L.cnt2);
     int32_t* const longlist = reinterpret_cast<int32_t*>(slab + L.longlist);
-    int32_t* const midlist = reinterpret_cast<int32_t*>(slab + L.midlist);
     float* const dP = slab + L.dP; float* const gE = slab + L.gE;
     float* const xlo = slab + L.xlo;
     float2* const MM = MM0; float2* const mm = MM + np; float2* const vv = mm + np;   // (sigmoid(M) is recomputed, not stored)
@@ -729,10 +700,9 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       cnt2[i] = prefix_below_g(icol, r0, r1, n2);
       if (i < n2) cnt1[i] = prefix_below_g(icol, r0, r1, n1);
       if (r1 - r0 > kLongEdges) longlist[atomicAdd(mail + 1, 1)] = i;   // (any order: a row's result does not depend on its position)
-      else if (r1 - r0 > kMidEdges) midlist[atomicAdd(mail + 2, 1)] = i;
     }
     bar.sync();
-    const int nlong = __ldcg(mail + 1), nmid = __ldcg(mail + 2);
+    const int nlong = __ldcg(mail + 1);
     const int np1 = prefix_below_g(pi, 0, np, n1);   // pairs are sorted by i: the first np1 touch rows < n1 (layer-2/3 terms)
 
     // ------------------------------------------------------------------ epochs
@@ -756,7 +726,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(0)
       // ---- F1: rows [0,n2): Y1 = A_m P + b1 ; row normalise                                   (models.py:70-78)
-      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, midlist, nmid, part, s_rowctr + 0, pol,
+      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part, s_rowctr + 0, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -769,7 +739,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
-      row_pass<HID, true, false>(n1, n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, midlist, nmid, part, s_rowctr + 1, pol,
+      row_pass<HID, true, false>(n1, n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part, s_rowctr + 1, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           if (lane < H4) st4(zw + 4 * lane, z);
@@ -900,7 +870,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       __syncthreads();
       GXG_MARK(4)
       // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise' -> dY1
-      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, midlist, nmid, part, s_rowctr + 2, pol,
+      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part, s_rowctr + 2, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt1[i]; },
         [&](int i, float4 dh) {
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
@@ -921,10 +891,10 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       GXG_MARK(5)
       // ---- B0 (sparse half): all nodes: dP = A_m^T dY1 (columns < n2 of row j); layer-1 edge dots <dY1[col], P[row]> on the way
       //      rows < n2 (hub-heavy, long gradient-carrying prefixes): a warp per row; the outermost rows (a few edges each): a row per edge slot
-      row_pass<HID, false, true>(n, n2, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, midlist, nmid, part, s_rowctr + 3, pol,
+      row_pass<HID, false, true>(n, n2, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part, s_rowctr + 3, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; },
         [&](int i, float4 z) { if (lane < H4) st4(dP + (size_t)i * HS + 4 * lane, z); });
-      short_rows_pass<HID>(n2, n, G, grank, lane, irp, icol, a, dY1, P, gE, dP, nlong + nmid, s_rowctr + 4, pol,
+      short_rows_pass<HID>(n2, n, G, grank, lane, irp, icol, a, dY1, P, gE, dP, nlong, s_rowctr + 4, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; });
       bar.sync();   // the tiles below read dP rows written by other warps / CTAs
       GXG_MARK(6)

@@ -170,7 +170,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
 // Global-memory slab of one task in the streaming kernel (explain_stream.cu: tasks whose state does not fit
 // shared memory).  Offsets in 4-byte words; the CSR / pair index arrays are read straight from the plan.
 struct GxStreamLayout {
-  int64_t a, gE, P, dP, Yh1, q1, dY1, Yh2, q2, dZ2, lapg, cnt1, cnt2, gFp, gFb, longlist, midlist, trw, xlo;
+  int64_t a, gE, P, dP, Yh1, q1, dY1, Yh2, q2, dZ2, lapg, cnt1, cnt2, gFp, gFb, longlist, trw, xlo;
   int64_t total_words;
   int dp;
 };
@@ -193,7 +193,6 @@ __host__ __device__ inline GxStreamLayout gx_make_stream_layout(int n, int n1, i
   // explain_gang.cu: dL/dsF partials of the 128-node blocks, rows sliced over a whole CTA, per-warp trace partials of a gang
   L.gFb = take((int64_t)((n + 127) / 128) * dp);
   L.longlist = take(n);
-  L.midlist = take(n);
   L.trw = take(GX_MAX_GANG * 32 * 4);
   L.xlo = take((int64_t)(n + 16) * (gx_round_up(d, 8) + 4));   // the task's feature rows in level order, padded to the shared-memory tile pitch
   L.total_words = o;
