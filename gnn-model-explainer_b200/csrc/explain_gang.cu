@@ -28,29 +28,10 @@ namespace {
 constexpr int kGangThreads = 512;    // 16 warps, 128 registers per thread (the tensor-core passes hold 24 A fragments + 32 accumulators)
 constexpr int kDenseWarps = 6;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
 constexpr int kLongEdges = 512;      // rows with more edges are sliced over all warps of one CTA
-#ifndef GXG_SPLIT_EDGES
-#define GXG_SPLIT_EDGES 192
-#endif
-constexpr int kSplitEdges = GXG_SPLIT_EDGES;     // rows with more edges (up to kLongEdges) are split into segments that any idle warp of the CTA picks up (512 = off)
-constexpr int kSegEdges = 96;        // target segment length (four gather steps)
-constexpr int kSplitSlots = 8;       // split rows in flight per CTA
-constexpr int kMaxSegs = 8;
 constexpr int kBlockTiles = 8;       // dL/dsF is reduced over fixed blocks of 8 tiles (128 nodes): independent of the gang size
 
-// Split rows (kSplitEdges < edges <= kLongEdges) without a CTA barrier.  The warp that draws such a row from the row counter claims a slot,
-// publishes (row, edge range, segment count) and goes on; every warp looking for work first takes open segments (slot.next), computes the
-// segment's partial aggregate into the slot's shared-memory row, and the warp that completes the LAST segment sums the partials in segment order
-// and runs the row's epilogue.  Deterministic (fixed segment boundaries and summation order), wait-free (nobody waits for anybody: a warp that
-// finds no free slot simply takes the whole row).  A 500-edge row on one warp was 20 dependent gather steps -- the straggler of every sparse phase.
-struct SplitSlots {
-  int busy[kSplitSlots];      // 0 free, 1 claimed (being set up or in use)
-  unsigned state[kSplitSlots];  // generation << 16 | segments << 8 | next segment: one word, so a claim (CAS) can never hit a recycled slot
-  int row[kSplitSlots], r0[kSplitSlots], r1[kSplitSlots], per[kSplitSlots];
-  int done[kSplitSlots];
-};
-
 struct GangSmem {
-  int W1s, Whi, Wlo, Thi, Tlo, W2s, W2t, W3s, bs, sF, F, mF, vF, zs, dE, dZ3, logit, Wp, part, spart, sslots, red, xt, pt, bar, total;
+  int W1s, Whi, Wlo, Thi, Tlo, W2s, W2t, W3s, bs, sF, F, mF, vF, zs, dE, dZ3, logit, Wp, part, red, xt, pt, bar, total;
   int xs, ldb, ldt, dp8, ntl;
 };
 __host__ __device__ inline GangSmem gang_smem(int d, int hid, int emb, int C, int nwarps) {
@@ -72,8 +53,6 @@ __host__ __device__ inline GangSmem gang_smem(int d, int hid, int emb, int C, in
   S.dE = take(2 * hid); S.dZ3 = take(hid); S.logit = take(C < 32 ? 32 : C);
   S.Wp = take(C * (2 * hid + emb + 1) <= GX_WP_SMEM_MAX ? C * (2 * hid + emb + 1) : 0);
   S.part = take(nwarps * hid);             // long rows: per-warp partial aggregates
-  S.spart = take(kSplitSlots * kMaxSegs * hid);   // split rows: per-segment partial aggregates
-  S.sslots = take((int)((sizeof(SplitSlots) + 3) / 4));
   S.red = take(kGangThreads > dp ? kGangThreads : dp);   // dL/dsF: slice partials
   S.xt = take(kDenseWarps * 2 * 16 * S.xs);              // feature tiles (TMA destination), two per dense warp
   S.pt = take(kDenseWarps * 2 * 16 * hid);               // dP tiles
@@ -169,8 +148,13 @@ __device__ __forceinline__ void st_v4_pol(float* a, float4 v, uint64_t pol) {
 // One row segment [r0,r1) by one warp: lane = (edge slot es, float4 index q); returns this lane's partial aggregate
 //   sum_{e = r0 + es, step EPL} a[e] f(src[icol[e]])[4q..4q+3]
 // kDot: gout[e] = <src[icol[e]], dv> for every edge (dv = this lane's float4 of the row's dot vector).
+#ifdef GXG_OUTLINE_SEGMENT
+#define GXG_SEG_INLINE __noinline__
+#else
+#define GXG_SEG_INLINE __forceinline__
+#endif
 template <int HID, bool kRelu, bool kDot>
-__device__ __forceinline__ float4 row_segment(int r0, int r1, int lane, const int32_t* __restrict__ icol, const float* a, const float* src,
+__device__ GXG_SEG_INLINE float4 row_segment(int r0, int r1, int lane, const int32_t* __restrict__ icol, const float* a, const float* src,
                                               float4 dv, float* gout, const L2Pol pol) {
   constexpr int H4 = HID / 4, EPL = 32 / H4, UN = GXG_UNROLL;
   const int es = lane / H4, q = lane - es * H4;
@@ -251,8 +235,7 @@ __device__ __forceinline__ float4 slot_reduce(float4 z) {
 template <int HID, bool kRelu, bool kDot, typename Bounds, typename Epi>
 __device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int warp, int nwarps, int lane, const int32_t* __restrict__ irp,
                                          const int32_t* __restrict__ icol, const float* a, const float* src, const float* dotsrc, float* gout,
-                                         const int32_t* longlist, int nlong, float* part, int* row_ctr, SplitSlots* sp, float* spart, const L2Pol pol,
-                                         Bounds bounds, Epi epi) {
+                                         const int32_t* longlist, int nlong, float* part, int* row_ctr, const L2Pol pol, Bounds bounds, Epi epi) {
   constexpr int H4 = HID / 4, EPL = 32 / H4;
   const int q = lane % H4;
   // long rows of this CTA
@@ -281,88 +264,15 @@ __device__ __forceinline__ void row_pass(int R, int Rn, int G, int grank, int wa
   // counter (rows are sorted by degree inside a level, so this is longest-first scheduling; a row's result does not depend on
   // which warp takes it).
   (void)nwarps;
-  bool rows_left = true;
   for (;;) {
-    // 1. an open segment of a split row?
-    int slot = -1, seg = 0;
-    int nseg = 0;
-    if (lane == 0) {
-      for (int s2 = 0; s2 < kSplitSlots && slot < 0; ++s2) {
-        unsigned v = *(volatile unsigned*)&sp->state[s2];
-        while ((v & 0xffu) < ((v >> 8) & 0xffu)) {   // an unclaimed segment of this generation
-          const unsigned old = atomicCAS(&sp->state[s2], v, v + 1u);
-          if (old == v) { slot = s2; seg = (int)(v & 0xffu); nseg = (int)((v >> 8) & 0xffu); break; }
-          v = old;
-        }
-      }
-    }
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    seg = __shfl_sync(0xffffffffu, seg, 0);
-    nseg = __shfl_sync(0xffffffffu, nseg, 0);
-    if (slot >= 0) {
-      __threadfence_block();
-      const int i = *(volatile int*)&sp->row[slot];
-      const int per = *(volatile int*)&sp->per[slot], rr0 = *(volatile int*)&sp->r0[slot], rr1 = *(volatile int*)&sp->r1[slot];
-      const int s0 = min(rr1, rr0 + seg * per), s1 = min(rr1, s0 + per);
-      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kDot && lane < EPL * H4) dv = ldcg4(dotsrc + (size_t)i * HID + 4 * q);
-      const float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(s0, s1, lane, icol, a, src, dv, gout, pol));
-      float* const pr = spart + (slot * kMaxSegs) * HID;
-      if (lane < H4) st4(pr + seg * HID + 4 * lane, z);
-      __threadfence_block();
-      int last = 0;
-      if (lane == 0) last = atomicAdd(&sp->done[slot], 1) == nseg - 1;
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence_block();
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < H4)
-          for (int w = 0; w < nseg; ++w) { const volatile float* o = pr + w * HID + 4 * lane; t.x += o[0]; t.y += o[1]; t.z += o[2]; t.w += o[3]; }
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); *(volatile int*)&sp->busy[slot] = 0; }   // the partials are in registers: the slot is free again
-        epi(i, t);
-      }
-      continue;
-    }
-    if (!rows_left) {   // no rows left: stay while a split row is still open (its later segments may need hands), then leave
-      int open = 0;
-      if (lane == 0)
-        for (int s2 = 0; s2 < kSplitSlots; ++s2) open |= *(volatile int*)&sp->busy[s2];
-      open = __shfl_sync(0xffffffffu, open, 0);
-      if (!open) break;
-      __nanosleep(100);
-      continue;
-    }
-    // 2. the next row of this CTA
     int k = 0;
     if (lane == 0) k = atomicAdd(row_ctr, 1);
     k = __shfl_sync(0xffffffffu, k, 0);
     const int i = k * G + grank;
-    if (i >= Rn) { rows_left = false; continue; }   // (rows Rn .. R-1: only the long ones, above) -- one more look at the slots, then out
+    if (i >= Rn) break;   // (rows Rn .. R-1: only the long ones, above)
     if (nlong > 0 && irp[i + 1] - irp[i] > kLongEdges) continue;
     int r0, r1;
     bounds(i, r0, r1);
-    if (r1 - r0 > kSplitEdges) {
-      int got = -1;
-      if (lane == 0)
-        for (int s2 = 0; s2 < kSplitSlots && got < 0; ++s2)
-          if (atomicCAS(&sp->busy[s2], 0, 1) == 0) got = s2;
-      got = __shfl_sync(0xffffffffu, got, 0);
-      if (got >= 0) {
-        if (lane == 0) {
-          const int len = r1 - r0;
-          const int ns = min(kMaxSegs, (len + kSegEdges - 1) / kSegEdges);
-          sp->row[got] = i; sp->r0[got] = r0; sp->r1[got] = r1;
-          sp->per[got] = gx_round_up((len + ns - 1) / ns, 4 * EPL);
-          sp->done[got] = 0;
-          __threadfence_block();
-          const unsigned gen = (*(volatile unsigned*)&sp->state[got] >> 16) + 1u;
-          *(volatile unsigned*)&sp->state[got] = (gen << 16) | ((unsigned)ns << 8);   // publish: ns segments, none taken
-        }
-        __syncwarp();
-        continue;   // (this warp takes segments like everybody else, starting with its own row's)
-      }
-    }
     float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kDot && lane < EPL * H4) dv = ldcg4(dotsrc + (size_t)i * HID + 4 * q);
     const float4 z = slot_reduce<HID>(row_segment<HID, kRelu, kDot>(r0, r1, lane, icol, a, src, dv, gout, pol));
@@ -654,8 +564,6 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   float* const zw = sm + S.zs + warp * 128;
   float* const dE = sm + S.dE; float* const dZ3 = sm + S.dZ3; float* const logit = sm + S.logit;
   float* const part = sm + S.part; float* const red = sm + S.red;
-  float* const spart = sm + S.spart;
-  SplitSlots* const sp = reinterpret_cast<SplitSlots*>(sm + S.sslots);
   const bool wp_smem = C * (PD + 1) <= GX_WP_SMEM_MAX;
   const float* const Wpp = wp_smem ? sm + S.Wp : m.Wp;
   const float* const bpp = wp_smem ? sm + S.Wp + C * PD : m.bp;
@@ -684,7 +592,6 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     for (int idx = tid; idx < C; idx += NT) Wps[C * PD + idx] = __ldg(m.bp + idx);
   }
   for (int idx = tid; idx < kDenseWarps * 2 * 16 * S.xs; idx += NT) sm[S.xt + idx] = 0.f;   // the pad columns [d, dp8) stay zero
-  if (tid < (int)(sizeof(SplitSlots) / 4)) reinterpret_cast<int*>(sp)[tid] = 0;
   if (tid < kDenseWarps * 2) mbar_init((uint32_t)__cvta_generic_to_shared(sm + S.bar) + tid * 8, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -824,7 +731,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(0)
       // ---- F1: rows [0,n2): Y1 = A_m P + b1 ; row normalise                                   (models.py:70-78)
-      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part, s_rowctr + 0, sp, spart, pol,
+      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, P, nullptr, nullptr, longlist, nlong, part, s_rowctr + 0, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -837,7 +744,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(1)
       // ---- F2: rows [0,n1): Y2 = (A_m relu(Yh1)) W2 + b2 ; row normalise
-      row_pass<HID, true, false>(n1, n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part, s_rowctr + 1, sp, spart, pol,
+      row_pass<HID, true, false>(n1, n1, G, grank, warp, nwarps, lane, irp, icol, a, Yh1, nullptr, nullptr, longlist, nlong, part, s_rowctr + 1, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = irp[i + 1]; },
         [&](int i, float4 z) {
           if (lane < H4) st4(zw + 4 * lane, z);
@@ -968,7 +875,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       __syncthreads();
       GXG_MARK(4)
       // ---- B1: rows [0,n2): dH1 = A_m^T dZ2 (only columns < n1 carry gradient), relu', normalise' -> dY1
-      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part, s_rowctr + 2, sp, spart, pol,
+      row_pass<HID, false, false>(n2, n2, G, grank, warp, nwarps, lane, irp, icol, a, dZ2, nullptr, nullptr, longlist, nlong, part, s_rowctr + 2, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt1[i]; },
         [&](int i, float4 dh) {
           float4 yh = make_float4(0.f, 0.f, 0.f, 0.f), dy = yh;
@@ -989,7 +896,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       GXG_MARK(5)
       // ---- B0 (sparse half): all nodes: dP = A_m^T dY1 (columns < n2 of row j); layer-1 edge dots <dY1[col], P[row]> on the way
       //      rows < n2 (hub-heavy, long gradient-carrying prefixes): a warp per row; the outermost rows (a few edges each): a row per edge slot
-      row_pass<HID, false, true>(n, n2, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part, s_rowctr + 3, sp, spart, pol,
+      row_pass<HID, false, true>(n, n2, G, grank, warp, nwarps, lane, irp, icol, a, dY1, P, gE, longlist, nlong, part, s_rowctr + 3, pol,
         [&](int i, int& r0, int& r1) { r0 = irp[i]; r1 = r0 + cnt2[i]; },
         [&](int i, float4 z) { if (lane < H4) st4(dP + (size_t)i * HS + 4 * lane, z); });
       short_rows_pass<HID>(n2, n, G, grank, lane, irp, icol, a, dY1, P, gE, dP, nlong, s_rowctr + 4, pol,
