@@ -149,44 +149,66 @@ def main_reference(a):
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (NVML) -- runs during the timed region
 # ------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.sm_max = None
-        self._halt = threading.Event()
-        self.err = None
+class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe): `nvidia-smi --query-gpu=... -lms 10` in a child
+    PROCESS started when the sampler is created (nvidia-smi needs a few hundred ms before its first line); begin() / end() bracket the
+    timed region and only the samples stamped inside it count.  (A polling thread inside the benchmark process competes for the GIL
+    with the host side of the step: +1 ms per 5 600-node sharded step at 8 GPUs.)"""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_power_brake_slowdown")
 
-    def run(self):
+    def __init__(self, index):
+        import subprocess
+        self.index = index
+        self.err = None
+        self.t0 = self.t1 = None
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
-                     "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
-                     "applications_clocks": 0x2}
-            while not self._halt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.005)
-        except Exception as e:  # NVML missing: report, do not fail the bench
-            self.err = repr(e)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "10"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception as e:
+            self.proc, self.err = None, repr(e)
+
+    def start(self):      # (kept for callers that mark the beginning of the timed region this way)
+        self.begin()
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self._halt.set()
-        self.join(2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-                "samples": len(self.samples), **({"error": self.err} if self.err else {})}
+        import datetime
+        if self.t1 is None:
+            self.end()
+        rows, sm_max = [], None
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out = self.proc.communicate(timeout=5)[0]
+            except Exception as e:
+                out, self.err = "", repr(e)
+            for line in out.splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), [v.lower().startswith("active") for v in f[3:8]]))
+                    sm_max = float(f[2])
+                except ValueError:
+                    continue
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap", "hw_power_brake"]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for r in rows if t0 - 0.005 <= r[0] <= self.t1 + 0.005]
+        note = "samples stamped inside the timed region"
+        if not inside and rows:      # a region shorter than the sampling period: the three samples nearest to it
+            mid = 0.5 * (t0 + self.t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "timed region shorter than the 10 ms sampling period: the three samples nearest to it"
+        reasons = sorted({nm for r in inside for nm, on in zip(names, r[2]) if on})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": sm_max, "reasons": reasons, "samples": len(inside),
+                "how": "nvidia-smi -lms 10 in a child process; " + note, **({"error": self.err} if self.err else {})}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,7 +369,7 @@ def timed(c, fn, steps, warmup, sampler=None, after=None):
         fn()
     barrier(c)
     if sampler is not None:
-        sampler.start()
+        sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     extra = []
     t0 = time.perf_counter()
@@ -360,6 +382,8 @@ def timed(c, fn, steps, warmup, sampler=None, after=None):
             extra.append(after())
     barrier(c)
     wall = time.perf_counter() - t0
+    if sampler is not None:
+        sampler.end()
     clocks = sampler.stop() if sampler is not None else None
     ms = float(sum(s.elapsed_time(e) for s, e in ev))
     t = torch.tensor([ms], dtype=torch.float64, device=c.dev)
