@@ -32,7 +32,8 @@ def shard_layout(sizes_all, world, costs=None):
     the gathered [world*slot] buffer; offsets[p] = where it goes in input order."""
     sizes_all = np.asarray(sizes_all, np.int64)
     num = len(sizes_all)
-    shards = [shard_indices(num, world, r, sizes_all if costs is None else costs) for r in range(world)]
+    order = np.argsort(-np.asarray(sizes_all if costs is None else costs), kind="stable")     # one sort; shard r = every world-th item of it
+    shards = [np.sort(order[r::world]) for r in range(world)]
     slot = max(1, max(int(sizes_all[s].sum()) for s in shards))
     offsets = np.concatenate([[0], np.cumsum(sizes_all)]).astype(np.int64)
     src_off = np.zeros(num, np.int64)
@@ -42,12 +43,12 @@ def shard_layout(sizes_all, world, costs=None):
     return shards, slot, src_off, offsets
 
 
-def allgather_packed(local_vals, sizes_all, rank, world, costs=None, group=None, engine=None, out=None):
+def allgather_packed(local_vals, sizes_all, rank, world, costs=None, group=None, engine=None, out=None, layout=None):
     """ONE all-gather of ragged per-item float32 payloads.
     local_vals : 1-D float32 tensor = this rank's items (positions shard_layout(...)[0][rank], ascending) concatenated
     sizes_all  : payload length of EVERY item of the list (known on every rank: gx_count_nodes)
     Returns (values, offsets): all payloads concatenated in input order, int64 offsets[num_items+1]."""
-    shards, slot, src_off, offsets = shard_layout(sizes_all, world, costs)
+    shards, slot, src_off, offsets = layout if layout is not None else shard_layout(sizes_all, world, costs)
     sizes_all = np.asarray(sizes_all, np.int64)
     device = local_vals.device
     total = int(offsets[-1])
@@ -104,8 +105,14 @@ def explain_nodes_sharded(explainer, node_indices, costs=None, group=None, use_e
     nodes = np.asarray(node_indices)
     dev = torch.device("cuda", eng.device)
     n_all, e_all = count_nodes_cached(explainer, nodes)
-    shards = shard_layout(e_all, world, costs)[0]
-    pos = shards[rank]
+    # the layout of a node list is a pure function of (list, world, costs): remembered for the list that was explained last
+    key = (nodes.tobytes(), world, None if costs is None else np.asarray(costs).tobytes(), getattr(explainer, "_current_graph", 0))
+    memo = explainer.__dict__.get("_layout_memo")
+    if memo is None or memo[0] != key:
+        memo = (key, shard_layout(e_all, world, costs))
+        explainer._layout_memo = memo
+    layout = memo[1]
+    pos = layout[0][rank]
     hp, init = explainer._hparams()
     if len(pos):
         # the canonical sub-graph description comes back to the host only when the torch-compatible init needs it (M0 gather)
@@ -118,5 +125,5 @@ def explain_nodes_sharded(explainer, node_indices, costs=None, group=None, use_e
         plan, local = None, torch.zeros(0, dtype=torch.float32, device=dev)
     if use_engine_comm:
         ensure_comm(eng, group)
-    values, offsets = allgather_packed(local, e_all, rank, world, costs, group=group, engine=eng if use_engine_comm else None)
+    values, offsets = allgather_packed(local, e_all, rank, world, costs, group=group, engine=eng if use_engine_comm else None, layout=layout)
     return values, offsets, (plan, pos)
