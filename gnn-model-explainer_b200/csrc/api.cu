@@ -293,6 +293,7 @@ int gx_model_forward(gx_handle* h, gx_memspace space, float* pred) {
   if (!h || !pred) { gx_set_error("gx_model_forward: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_graph || !h->has_model) { gx_set_error("gx_model_forward: call gx_set_model and gx_set_graph_csr first"); return GX_ERR_INVALID; }
   if (h->g.d != h->m.d) { gx_set_error("gx_model_forward: graph feat_dim %d != model input_dim %d", h->g.d, h->m.d); return GX_ERR_INVALID; }
+  if (h->m.hid > 32 || h->m.emb > 32) { gx_set_error("gx_model_forward: widths > 32 are not built (pass pred to the Explainer)"); return GX_ERR_UNSUPPORTED; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   const size_t np_ = (size_t)h->g.N * h->m.C;
   GX_CUDA_CHECK(h->d_fwd.reserve(((size_t)h->m.L * h->g.N * 32 + np_) * 4));
@@ -330,8 +331,8 @@ int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* co
     gx_set_error("gx_set_model: num_layers=%d outside [2,%d]", dims->num_layers, GX_MAX_LAYERS);
     return GX_ERR_UNSUPPORTED;
   }
-  if (dims->hidden_dim < 1 || dims->embed_dim < 1 || dims->hidden_dim > 32 || dims->embed_dim > 32) {
-    gx_set_error("gx_set_model: hidden_dim=%d output_dim=%d; this build supports widths up to 32", dims->hidden_dim, dims->embed_dim);
+  if (dims->hidden_dim < 1 || dims->embed_dim < 1 || dims->hidden_dim > 128 || dims->embed_dim > 128) {
+    gx_set_error("gx_set_model: hidden_dim=%d output_dim=%d; this build supports widths up to 128 (tuned kernels up to 32, the variant kernel beyond)", dims->hidden_dim, dims->embed_dim);
     return GX_ERR_UNSUPPORTED;
   }
   if (dims->input_dim < 1 || dims->input_dim > 128) {
@@ -340,8 +341,8 @@ int gx_set_model(gx_handle* h, const gx_model_dims* dims, const float* const* co
   }
   if (dims->num_classes < 1) { gx_set_error("gx_set_model: num_classes < 1"); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
-  if (dims->num_layers != 3 || (dims->flags & GX_MODEL_BN)) {
-    // Model variant (num_gc_layers 2 / 4, --bn): explain_var.cu, true widths (a zero-padded column would enter the bn statistics).
+  if (dims->num_layers != 3 || (dims->flags & GX_MODEL_BN) || dims->hidden_dim > 32 || dims->embed_dim > 32) {
+    // Model variant (num_gc_layers 2 / 4, --bn, widths 33..128): explain_var.cu, true widths (a zero-padded column would enter the bn statistics).
     const int L = dims->num_layers, d = dims->input_dim, hid0 = dims->hidden_dim, emb0 = dims->embed_dim, C = dims->num_classes;
     if (gx_var_smem_bytes(d, L, hid0, emb0, C) > gx_explain_max_smem()) { gx_set_error("gx_set_model: model variant does not fit shared memory"); return GX_ERR_UNSUPPORTED; }
     std::vector<float> host;
@@ -545,7 +546,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     }
     T.smem_bytes = bytes;
     if (cls == kStreamClass && h->m.variant)
-      gws_words = std::max<int64_t>(gws_words, gx_make_var_layout(T.n, T.n2, T.e1, T.npairs_in, h->m.d, h->m.L).total_words);
+      gws_words = std::max<int64_t>(gws_words, gx_make_var_layout(T.n, T.n2, T.e1, T.npairs_in, h->m.d, h->m.L, gx_var_row_stride(h->m.hid, h->m.emb)).total_words);
     else if (cls == kStreamClass)
       gws_words = std::max<int64_t>(gws_words, gx_make_stream_layout(T.n, T.n1, T.n2, T.e_d, T.npairs_in, h->m.d, h->m.hid, GX_STREAM_THREADS / 32).total_words);
     h->class_order[cls].push_back(t);
@@ -811,7 +812,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     if (gx_var_smem_bytes(h->m.d, h->m.L, h->m.hid, h->m.emb, h->m.C) > gx_explain_max_smem()) { gx_set_error("gx_explain_nodes: model does not fit the variant kernel"); return GX_ERR_UNSUPPORTED; }
     int64_t words = 4; int maxnp = 0;
     for (const GxTask& T : h->tasks) {
-      words = std::max<int64_t>(words, gx_make_var_layout(T.n, T.n2, T.e1, T.npairs_in, h->m.d, h->m.L).total_words);
+      words = std::max<int64_t>(words, gx_make_var_layout(T.n, T.n2, T.e1, T.npairs_in, h->m.d, h->m.L, gx_var_row_stride(h->m.hid, h->m.emb)).total_words);
       maxnp = std::max(maxnp, T.npairs_in);
     }
     const int grid = std::min(count, h->num_sms * 4);

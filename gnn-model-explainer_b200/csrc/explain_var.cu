@@ -4,7 +4,7 @@
 //   the feature axis, eps 1e-5, biased variance, applied after the ReLU of every hidden layer; the readout concatenates the
 //   standardised activations, models.py:241-260).
 // It computes exactly what oracle/kernel_spec.py specifies (parameters on the directed edges, layer l only on the rows within
-// L - l hops of the explained node, inner / outer pair split), for any widths <= 32 and d <= 128.  These options are rare, so the
+// L - l hops of the explained node, inner / outer pair split), for hidden / output widths up to 128 (the tuned kernels stop at 32) and d <= 128.  These options are rare, so the
 // kernel is written for clarity, not speed: one persistent CTA per task, state in a per-CTA global slab (L2 resident for the
 // reference's graph sizes), one warp per row with lane = feature, one thread per undirected edge in the edge phase.
 // Phases per epoch (one __syncthreads each): F1 .. FL | S | BL .. B1 | P.  The default model (3 layers, no bn) never comes here.
@@ -13,34 +13,42 @@
 namespace {
 
 constexpr int kVarThreads = 256;
-constexpr int VW = 32;   // row stride of every hidden-width array (widths <= 32, lane = feature)
+constexpr int kVarWeightWords = 36 * 1024;   // conv weights are staged in shared memory up to this many floats (144 KB), read through L2 beyond
 
-struct VarSmem { int W[GX_MAX_LAYERS], b[GX_MAX_LAYERS], Wp, sF, F, mF, vF, zs, gFp, emb, dEmb, logit, total; };
+// KW = 32-lane chunks of a hidden-width row (lane = feature, chunk k holds features 32k + lane): 1 for widths <= 32, 2 <= 64, 4 <= 128
+__host__ __device__ inline int var_kw(int hid, int emb) { const int w = hid > emb ? hid : emb; return w <= 32 ? 1 : (w <= 64 ? 2 : 4); }
+
+struct VarSmem { int W[GX_MAX_LAYERS], b[GX_MAX_LAYERS], Wp, sF, F, mF, vF, zs, zlen, gFp, emb, dEmb, logit, w_in_smem, total; };
 __host__ __device__ inline VarSmem var_smem(int d, int L, int hid, int emb, int C, int nwarps) {
   VarSmem S;
   const int dp = gx_round_up(d, 4);
   int o = 0;
   auto take = [&](int words) { int r = o; o += gx_round_up(words, 4); return r; };
+  int wwords = 0;
+  for (int l = 0; l < L; ++l) wwords += (l == 0 ? d : hid) * (l == L - 1 ? emb : hid);
+  S.w_in_smem = wwords <= kVarWeightWords;
   for (int l = 0; l < L; ++l) {
     const int win = l == 0 ? d : hid, wout = l == L - 1 ? emb : hid;
-    S.W[l] = take(win * wout);
+    S.W[l] = take(S.w_in_smem ? win * wout : 0);
     S.b[l] = take(wout);
   }
   const int PD = hid * (L - 1) + emb;
   S.Wp = take(C * (PD + 1) <= GX_WP_SMEM_MAX ? C * (PD + 1) : 0);
   S.sF = take(dp); S.F = take(dp); S.mF = take(dp); S.vF = take(dp);
-  S.zs = take(nwarps * dp);
+  S.zlen = dp > 32 * var_kw(hid, emb) ? dp : 32 * var_kw(hid, emb);   // per-warp scratch row: a feature row or a hidden row
+  S.zs = take(nwarps * S.zlen);
   S.gFp = take(nwarps * dp);
   S.emb = take(PD); S.dEmb = take(PD); S.logit = take(C < 32 ? 32 : C);
   S.total = o;
   return S;
 }
 
-template <bool kBn>
+template <bool kBn, int KW>
 __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainArgs A) {
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_task;
   constexpr int NT = kVarThreads, nwarps = NT / 32;
+  constexpr int VW = 32 * KW;   // row stride of every hidden-width array
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const GxModelDev& m = A.m;
   const GxHparamsDev& hp = A.hp;
@@ -50,7 +58,7 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
   const bool ieee = (hp.flags & GX_HP_IEEE_EDGE) != 0;
   const VarSmem S = var_smem(d, L, hid, embw, C, nwarps);
   float* const sF = sm + S.sF; float* const Fm = sm + S.F; float* const mF = sm + S.mF; float* const vF = sm + S.vF;
-  float* const zs = sm + S.zs + warp * dp;
+  float* const zs = sm + S.zs + warp * S.zlen;
   float* const gFp = sm + S.gFp;
   float* const emb = sm + S.emb; float* const dEmb = sm + S.dEmb; float* const logit = sm + S.logit;
   const bool wp_smem = C * (PD + 1) <= GX_WP_SMEM_MAX;
@@ -59,9 +67,12 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
   auto win_of = [&](int l) { return l == 0 ? d : hid; };            // l = 0 .. L-1
   auto wout_of = [&](int l) { return l == L - 1 ? embw : hid; };
 
+  const float* Wl[GX_MAX_LAYERS];   // conv weights: shared memory when they fit, else global (L2 resident)
   for (int l = 0; l < L; ++l) {
     const int cnt = win_of(l) * wout_of(l);
-    for (int idx = tid; idx < cnt; idx += NT) sm[S.W[l] + idx] = __ldg(m.W[l] + idx);
+    if (S.w_in_smem)
+      for (int idx = tid; idx < cnt; idx += NT) sm[S.W[l] + idx] = __ldg(m.W[l] + idx);
+    Wl[l] = S.w_in_smem ? sm + S.W[l] : m.W[l];
     for (int idx = tid; idx < wout_of(l); idx += NT) sm[S.b[l] + idx] = __ldg(m.b[l] + idx);
   }
   if (wp_smem) {
@@ -85,7 +96,7 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
     int R[GX_MAX_LAYERS + 1];   // R[l] = rows of layer l (1-based): nodes within L - l hops; R[0] = n
     R[0] = n;
     for (int l = 1; l <= L; ++l) R[l] = Tp->cum[L - l] < n ? Tp->cum[L - l] : n;
-    const GxVarLayout Lo = gx_make_var_layout(n, n2, e1, np, d, L);
+    const GxVarLayout Lo = gx_make_var_layout(n, n2, e1, np, d, L, VW);
     const int32_t* __restrict__ lo2gid = A.plan.lo2gid + node_off;
     const int32_t* __restrict__ irp = A.plan.irowptr + rp_off;
     const int32_t* __restrict__ icol = A.plan.icol + edge_off;
@@ -139,10 +150,12 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
       // ---------------------------------------------------------------- forward, layer by layer        (models.py:58-80,230-267)
       for (int l = 1; l <= L; ++l) {
         const int win = win_of(l - 1), wout = wout_of(l - 1);
-        const float* const Ws = sm + S.W[l - 1]; const float* const bsm = sm + S.b[l - 1];
+        const float* const Ws = Wl[l - 1]; const float* const bsm = sm + S.b[l - 1];
         for (int i = warp; i < R[l]; i += nwarps) {
           const int r0 = irp[i], r1 = irp[i + 1];
-          float y = lane < wout ? bsm[lane] : 0.f;
+          float y[KW];
+#pragma unroll
+          for (int k = 0; k < KW; ++k) y[k] = lane + 32 * k < wout ? bsm[lane + 32 * k] : 0.f;
           if (l == 1) {
             for (int f0 = 0; f0 < d; f0 += 32) {
               const int f = f0 + lane;
@@ -151,37 +164,56 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
                 for (int e = r0; e < r1; ++e) z = fmaf(a[e], __ldg(A.g.feat + (int64_t)lo2gid[icol[e]] * d + f), z);
               if (f < d) { U[(int64_t)i * dp + f] = z; zs[f] = z * sF[f]; }   // x * sigmoid(feat_mask) (explain.py:707), linear in x
             }
-            __syncwarp();
-            if (lane < wout)
-              for (int f = 0; f < d; ++f) y = fmaf(zs[f], Ws[f * wout + lane], y);
-            __syncwarp();
           } else {
             const float* const Hp = Hh(l - 1);
-            float z = 0.f;
-            if (lane < win)
-              for (int e = r0; e < r1; ++e) z = fmaf(a[e], Hp[(int64_t)icol[e] * VW + lane], z);
-            for (int f = 0; f < win; ++f) {
-              const float zf = __shfl_sync(0xffffffffu, z, f);
-              if (lane < wout) y = fmaf(zf, Ws[f * wout + lane], y);
+#pragma unroll
+            for (int k = 0; k < KW; ++k) {
+              const int f = lane + 32 * k;
+              float z = 0.f;
+              if (f < win)
+                for (int e = r0; e < r1; ++e) z = fmaf(a[e], Hp[(int64_t)icol[e] * VW + f], z);
+              if (f < win) zs[f] = z;
             }
           }
-          const float ss = warp_sum(lane < wout ? y * y : 0.f);
+          __syncwarp();
+          for (int f = 0; f < win; ++f) {
+            const float zf = zs[f];
+#pragma unroll
+            for (int k = 0; k < KW; ++k)
+              if (lane + 32 * k < wout) y[k] = fmaf(zf, Ws[f * wout + lane + 32 * k], y[k]);
+          }
+          __syncwarp();
+          float ssl = 0.f;
+#pragma unroll
+          for (int k = 0; k < KW; ++k) ssl += lane + 32 * k < wout ? y[k] * y[k] : 0.f;
+          const float ss = warp_sum(ssl);
           const float q = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(p=2, dim=2), eps 1e-12
-          const float yh = lane < wout ? y / q : 0.f;
-          float h = yh;
+          float yh[KW], h[KW];
+#pragma unroll
+          for (int k = 0; k < KW; ++k) { yh[k] = lane + 32 * k < wout ? y[k] / q : 0.f; h[k] = yh[k]; }
           if (l < L) {
-            h = fmaxf(yh, 0.f);
+#pragma unroll
+            for (int k = 0; k < KW; ++k) h[k] = fmaxf(yh[k], 0.f);
             if (kBn) {   // fresh BatchNorm1d(n) in train mode: per node, over the feature axis (models.py:222-228)
-              const float mu = warp_sum(lane < wout ? h : 0.f) / (float)wout;
-              const float dv = lane < wout ? h - mu : 0.f;
-              const float var = warp_sum(dv * dv) / (float)wout;
+              float sl = 0.f;
+#pragma unroll
+              for (int k = 0; k < KW; ++k) sl += lane + 32 * k < wout ? h[k] : 0.f;
+              const float mu = warp_sum(sl) / (float)wout;
+              float vl = 0.f;
+#pragma unroll
+              for (int k = 0; k < KW; ++k) { h[k] = lane + 32 * k < wout ? h[k] - mu : 0.f; vl += h[k] * h[k]; }
+              const float var = warp_sum(vl) / (float)wout;
               const float is = 1.0f / sqrtf(var + 1e-5f);
-              h = dv * is;
+#pragma unroll
+              for (int k = 0; k < KW; ++k) h[k] *= is;
               if (lane == 0) istd(l)[i] = is;
             }
           }
-          Yh(l)[(int64_t)i * VW + lane] = yh;
-          Hh(l)[(int64_t)i * VW + lane] = lane < wout ? h : 0.f;
+#pragma unroll
+          for (int k = 0; k < KW; ++k) {
+            Yh(l)[(int64_t)i * VW + lane + 32 * k] = yh[k];
+            Hh(l)[(int64_t)i * VW + lane + 32 * k] = lane + 32 * k < wout ? h[k] : 0.f;
+          }
           if (lane == 0) qn(l)[i] = q;
         }
         __syncthreads();
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
       // ---------------------------------------------------------------- S: readout of row r = level-order id 0, softmax, dEmb
       if (warp == 0) {
         for (int l = 1; l <= L; ++l)
-          if (lane < wout_of(l - 1)) emb[hid * (l - 1) + lane] = Hh(l)[lane];
+          for (int c = lane; c < wout_of(l - 1); c += 32) emb[hid * (l - 1) + c] = Hh(l)[c];
         __syncwarp();
         for (int c = 0; c < C; ++c) {
           float t = 0.f;
@@ -218,54 +250,77 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
       // ---------------------------------------------------------------- backward, layer by layer
       for (int l = L; l >= 1; --l) {
         const int win = win_of(l - 1), wout = wout_of(l - 1);
-        const float* const Ws = sm + S.W[l - 1];
+        const float* const Ws = Wl[l - 1];
         for (int i = warp; i < R[l]; i += nwarps) {
           // dL/dH_l[i] = (A_m^T dZ_{l+1})[i] over the neighbours that are rows of layer l+1 (a prefix of row i) + the readout's share
-          float g = 0.f;
+          float g[KW], yh[KW];
+#pragma unroll
+          for (int k = 0; k < KW; ++k) g[k] = 0.f;
           if (l < L) {
             const int r0 = irp[i], r1 = irp[i + 1], bound = R[l + 1];
             const float* const dZn = dZ(l + 1);
             for (int e = r0; e < r1; ++e) {
               const int j = icol[e];
               if (j >= bound) break;   // columns are partitioned by level
-              if (lane < wout) g = fmaf(a[e], dZn[(int64_t)j * VW + lane], g);
+              const float ae = a[e];
+#pragma unroll
+              for (int k = 0; k < KW; ++k)
+                if (lane + 32 * k < wout) g[k] = fmaf(ae, dZn[(int64_t)j * VW + lane + 32 * k], g[k]);
             }
           }
-          if (i == 0 && lane < wout) g += dEmb[hid * (l - 1) + lane];
-          const float yh = Yh(l)[(int64_t)i * VW + lane];
+#pragma unroll
+          for (int k = 0; k < KW; ++k) {
+            if (i == 0 && lane + 32 * k < wout) g[k] += dEmb[hid * (l - 1) + lane + 32 * k];
+            yh[k] = Yh(l)[(int64_t)i * VW + lane + 32 * k];
+          }
           if (l < L) {
             if (kBn) {   // backward of the per-node standardisation: (g - mean(g) - Hb mean(g Hb)) * istd
-              const float hb = Hh(l)[(int64_t)i * VW + lane];
-              const float m1 = warp_sum(lane < wout ? g : 0.f) / (float)wout;
-              const float m2 = warp_sum(lane < wout ? g * hb : 0.f) / (float)wout;
-              g = lane < wout ? (g - m1 - hb * m2) * istd(l)[i] : 0.f;
+              float hb[KW], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int k = 0; k < KW; ++k) {
+                hb[k] = Hh(l)[(int64_t)i * VW + lane + 32 * k];
+                if (lane + 32 * k < wout) { s1 += g[k]; s2 += g[k] * hb[k]; }
+              }
+              const float m1 = warp_sum(s1) / (float)wout, m2 = warp_sum(s2) / (float)wout, is = istd(l)[i];
+#pragma unroll
+              for (int k = 0; k < KW; ++k) g[k] = lane + 32 * k < wout ? (g[k] - m1 - hb[k] * m2) * is : 0.f;
             }
-            g = yh > 0.f ? g : 0.f;   // relu backward
+#pragma unroll
+            for (int k = 0; k < KW; ++k) g[k] = yh[k] > 0.f ? g[k] : 0.f;   // relu backward
           }
-          const float sdot = warp_sum(lane < wout ? yh * g : 0.f);
-          const float dy = lane < wout ? (g - yh * sdot) / qn(l)[i] : 0.f;   // backward of y / max(|y|, eps)
+          float sl = 0.f;
+#pragma unroll
+          for (int k = 0; k < KW; ++k) sl += lane + 32 * k < wout ? yh[k] * g[k] : 0.f;
+          const float sdot = warp_sum(sl);
+          const float qi = qn(l)[i];
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < KW; ++k)
+            if (lane + 32 * k < wout) zs[lane + 32 * k] = (g[k] - yh[k] * sdot) / qi;   // dY: backward of y / max(|y|, eps)
+          __syncwarp();
           // dZ[f] = sum_c dY[c] W[f][c]
           if (l == 1) {
             for (int f0 = 0; f0 < d; f0 += 32) {
               const int f = f0 + lane;
               float t = 0.f;
-              for (int c = 0; c < wout; ++c) {
-                const float dc = __shfl_sync(0xffffffffu, dy, c);
-                if (f < d) t = fmaf(dc, Ws[f * wout + c], t);
-              }
+              if (f < d)
+                for (int c = 0; c < wout; ++c) t = fmaf(zs[c], Ws[f * wout + c], t);
               if (f < d) {
                 gFp[warp * dp + f] = fmaf(t, U[(int64_t)i * dp + f], gFp[warp * dp + f]);   // dL/dsF partial (U = A_m X)
                 dZ1[(int64_t)i * dp + f] = t * sF[f];                                        // kept masked for the edge dots
               }
             }
           } else {
-            float t = 0.f;
-            for (int c = 0; c < wout; ++c) {
-              const float dc = __shfl_sync(0xffffffffu, dy, c);
-              if (lane < win) t = fmaf(dc, Ws[lane * wout + c], t);
+#pragma unroll
+            for (int k = 0; k < KW; ++k) {
+              const int f = lane + 32 * k;
+              float t = 0.f;
+              if (f < win)
+                for (int c = 0; c < wout; ++c) t = fmaf(zs[c], Ws[f * wout + c], t);
+              dZ(l)[(int64_t)i * VW + f] = f < win ? t : 0.f;
             }
-            dZ(l)[(int64_t)i * VW + lane] = lane < win ? t : 0.f;
           }
+          __syncwarp();
         }
         __syncthreads();
       }
@@ -345,6 +400,7 @@ __global__ void __launch_bounds__(kVarThreads) explain_var_kernel(const ExplainA
 }  // namespace
 
 int gx_var_smem_bytes(int d, int L, int hid, int emb, int C) { return var_smem(d, L, hid, emb, C, kVarThreads / 32).total * 4; }
+int gx_var_row_stride(int hid, int emb) { return 32 * var_kw(hid, emb); }
 
 cudaError_t gx_launch_explain_var(const GxExplainLaunch& cfg, const GxGraphDev& g, const GxModelDev& m,
                                   const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
@@ -356,15 +412,19 @@ cudaError_t gx_launch_explain_var(const GxExplainLaunch& cfg, const GxGraphDev& 
   args.g = g; args.m = m; args.hp = hp; args.plan = plan;
   args.m0 = m0; args.out_mask = out_mask; args.out_feat = out_feat; args.dbg = cfg.dbg; args.x = cfg.x;
   const int bytes = gx_var_smem_bytes(m.d, m.L, m.hid, m.emb, m.C);
-  cudaError_t e;
+  const int kw = var_kw(m.hid, m.emb);
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<cfg.grid, kVarThreads, bytes, s>>>(args);
+    return cudaGetLastError();
+  };
   if (m.bn) {
-    e = cudaFuncSetAttribute(explain_var_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    explain_var_kernel<true><<<cfg.grid, kVarThreads, bytes, s>>>(args);
-  } else {
-    e = cudaFuncSetAttribute(explain_var_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    explain_var_kernel<false><<<cfg.grid, kVarThreads, bytes, s>>>(args);
+    if (kw == 1) return go(explain_var_kernel<true, 1>);
+    if (kw == 2) return go(explain_var_kernel<true, 2>);
+    return go(explain_var_kernel<true, 4>);
   }
-  return cudaGetLastError();
+  if (kw == 1) return go(explain_var_kernel<false, 1>);
+  if (kw == 2) return go(explain_var_kernel<false, 2>);
+  return go(explain_var_kernel<false, 4>);
 }

@@ -204,7 +204,7 @@ struct GxVarLayout {
   int64_t a, U, dZ1, lapg, Yh, H, dZ, q, istd;
   int64_t total_words;
 };
-__host__ __device__ inline GxVarLayout gx_make_var_layout(int n, int n2, int e1, int np_in, int d, int L) {
+__host__ __device__ inline GxVarLayout gx_make_var_layout(int n, int n2, int e1, int np_in, int d, int L, int vw = 32) {
   GxVarLayout Lo;
   const int dp = gx_round_up(d, 4);
   int64_t o = 0;
@@ -214,9 +214,9 @@ __host__ __device__ inline GxVarLayout gx_make_var_layout(int n, int n2, int e1,
   Lo.U = take((int64_t)n2 * dp);              // A_m X
   Lo.dZ1 = take((int64_t)n2 * dp);            // dL/d(A_m X') (.) sigmoid(feat_mask)
   Lo.lapg = take(np_in);
-  Lo.Yh = take((int64_t)L * n2 * 32);         // per layer: normalised pre-activations
-  Lo.H = take((int64_t)L * n2 * 32);          // per layer: relu (+ standardisation) output = input of the next layer / the readout
-  Lo.dZ = take((int64_t)(L - 1) * n2 * 32);   // layers 2..L: dL/d(A_m H_{l-1})
+  Lo.Yh = take((int64_t)L * n2 * vw);         // per layer: normalised pre-activations (row stride vw = 32 * ceil(width / 32))
+  Lo.H = take((int64_t)L * n2 * vw);          // per layer: relu (+ standardisation) output = input of the next layer / the readout
+  Lo.dZ = take((int64_t)(L - 1) * n2 * vw);   // layers 2..L: dL/d(A_m H_{l-1})
   Lo.q = take((int64_t)L * n2);
   Lo.istd = take((int64_t)L * n2);
   Lo.total_words = o;
@@ -325,6 +325,7 @@ cudaError_t gx_launch_explain_var(const GxExplainLaunch& cfg, const GxGraphDev& 
                                   const GxHparamsDev& hp, const GxPlanArrays& plan, const float* m0,
                                   float* out_mask, float* out_feat, cudaStream_t s);
 int gx_var_smem_bytes(int d, int L, int hid, int emb, int C);
+int gx_var_row_stride(int hid, int emb);
 cudaError_t gx_launch_model_forward(const GxGraphDev& g, const GxModelDev& m, float* H, float* pred, float* emb_out, cudaStream_t s);
 constexpr int GX_STREAM_THREADS = 768;  // 24 warps: 80 registers per thread, 5 KB of cp.async staging per warp
 int gx_explain_max_smem();

@@ -50,8 +50,9 @@ typedef struct gx_model_dims {
   int32_t num_layers;  /* num_gc_layers: 2, 3 (reference default) or 4    */
   int32_t flags;       /* GX_MODEL_* bits                               */
 } gx_model_dims;
-#define GX_MODEL_BN 1u /* args.bn (models.py:222-228): per-node standardisation after every hidden ReLU.  num_layers != 3 or bn
-                        * select the model-variant kernel (node mode, mask optimisation only: no trace / optimiser state / grad) */
+#define GX_MODEL_BN 1u /* args.bn (models.py:222-228): per-node standardisation after every hidden ReLU.  num_layers != 3, bn or a
+                        * hidden / output width of 33..128 select the model-variant kernel (node mode, mask optimisation only: no
+                        * trace / optimiser state / grad) */
 
 /* Optimisation hyper-parameters: explainer_main.py:143-167 defaults + ExplainModule.coeffs
  * (explainer/explain.py:624-631) + torch.optim.Adam defaults (utils/train_utils.py:10). */

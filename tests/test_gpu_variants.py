@@ -174,3 +174,10 @@ def test_model_forward_matches_reference_predictions(tmp_path):
     torch.manual_seed(3); a = nopred.explain(300)
     torch.manual_seed(3); b = ex.explain(300)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed,L,bn,hid,emb,d,C", [(11, 3, False, 64, 64, 10, 4), (12, 3, True, 48, 40, 17, 3), (13, 2, False, 128, 96, 6, 2), (14, 4, True, 64, 33, 128, 5)])
+def test_wide_models_match_oracle(seed, L, bn, hid, emb, d, C):
+    """--hidden-dim / --output-dim above 32 (explainer_main.py:51-56): the variant kernel with 2 / 4 lane chunks per row, against the
+    line-by-line torch port."""
+    test_variant_matches_oracle_random(seed, L, bn, hid, emb, d, C)

@@ -58,6 +58,18 @@ def main():
             eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS, init=_abi.GX_INIT_PHILOX, seed=2), None, out)
             print("var ok", tag, float(out.sum()))
             eng.close()
+        rng = np.random.default_rng(5)   # a wide model (hidden 64 / output 48): two lane chunks per row
+        sc = lambda *s_: (rng.normal(size=s_) * 0.4).astype(np.float32)
+        d0 = g["feat"].shape[1]
+        ww = dict(W1=sc(d0, 64), b1=sc(64), W2=sc(64, 64), b2=sc(64), W3=sc(64, 48), b3=sc(48), Wp=sc(3, 176), bp=sc(3))
+        eng = gnnx.Engine(0)
+        eng.set_model(ww, num_layers=3, bn=False)
+        eng.set_graph_csr(rowptr, col, g["feat"].astype(np.float32), g["label"].astype(np.int32), np.zeros(N, np.int32))
+        plan = eng.plan_nodes([0, 17], 3)
+        out = np.zeros(plan.total_edges, np.float32)
+        eng.explain_nodes_host(eng.make_hparams(num_epochs=EPOCHS, init=_abi.GX_INIT_PHILOX, seed=2), None, out)
+        print("var ok wide", float(out.sum()))
+        eng.close()
         eng = util.make_engine(fx)     # default model, optimiser other than Adam -> the variant kernel
         plan = eng.plan_nodes([300, 5], 3)
         out = np.zeros(plan.total_edges, np.float32)
