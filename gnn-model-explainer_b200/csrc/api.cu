@@ -115,7 +115,7 @@ struct gx_handle {
   int64_t g_total_e = 0;
   int g_max_smem = 0, g_max_np = 0;
   // graph mode launch classes (by shared-memory footprint, like node mode): tasks per class, the class's largest footprint / pair count
-  int g_class_n[4] = {0, 0, 0, 0}, g_class_smem[4] = {0, 0, 0, 0}, g_class_np[4] = {0, 0, 0, 0};
+  int g_class_n[6] = {}, g_class_smem[6] = {}, g_class_np[6] = {};
   // slot workspace
   DevBuf ws_buf;
   GxSlotWs ws{};
@@ -1074,20 +1074,21 @@ int gx_plan_graphs(gx_handle* h, const int32_t* graph_ids, int32_t count, int64_
     tn += na; te += T.e_d; tp += T.npairs;
   }
   // Launch classes by footprint: a batch padded to 100 nodes mostly holds 20-40-node molecules; one launch sized for the largest graph
-  // left 3 CTAs per SM where 9 fit.  Classes <= 24 / 48 / 110 / 226 KB -> 9 / 4 / 2 / 1 CTAs per SM, most expensive first inside a class.
-  static const int kGraphCap[4] = {24 * 1024, 48 * 1024, 110 * 1024, 226 * 1024};
-  std::vector<int32_t> cls_tasks[4];
-  for (int c = 0; c < 4; ++c) { h->g_class_n[c] = 0; h->g_class_smem[c] = 0; h->g_class_np[c] = 0; }
+  // left 3 CTAs per SM where 5-11 fit (~12 KB of every footprint are the weights).  Classes <= 18 / 27 / 36 / 44 / 80 / 226 KB ->
+  // 11 / 8 / 6 / 5 / 2 / 1 CTAs per SM (each launch requests its class's largest footprint), most expensive first inside a class.
+  static const int kGraphCap[6] = {18 * 1024, 27 * 1024, 36 * 1024, 44 * 1024, 80 * 1024, 226 * 1024};
+  std::vector<int32_t> cls_tasks[6];
+  for (int c = 0; c < 6; ++c) { h->g_class_n[c] = 0; h->g_class_smem[c] = 0; h->g_class_np[c] = 0; }
   for (int t = 0; t < count; ++t) {
     int c = 0;
-    while (c < 3 && h->tasks[t].smem_bytes > kGraphCap[c]) ++c;
+    while (c < 5 && h->tasks[t].smem_bytes > kGraphCap[c]) ++c;
     cls_tasks[c].push_back(t);
     h->g_class_smem[c] = std::max(h->g_class_smem[c], h->tasks[t].smem_bytes);
     h->g_class_np[c] = std::max(h->g_class_np[c], h->tasks[t].npairs);
   }
   std::vector<int32_t> order;
   order.reserve(count);
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 6; ++c) {
     std::stable_sort(cls_tasks[c].begin(), cls_tasks[c].end(), [&](int32_t x, int32_t y) { return h->tasks[x].e_d + 4 * h->tasks[x].n > h->tasks[y].e_d + 4 * h->tasks[y].n; });
     h->g_class_n[c] = (int)cls_tasks[c].size();
     order.insert(order.end(), cls_tasks[c].begin(), cls_tasks[c].end());
@@ -1143,20 +1144,21 @@ static int explain_graphs_impl(gx_handle* h, const gx_hparams* hp, gx_memspace s
   if (rc != GX_OK) return rc;
   hd.adam_tab = h->d_adam.as<float2>();
   // one persistent launch per footprint class, on its own stream (the classes overlap like the node-mode classes)
-  int grids[4]; int64_t pstride[4], poff[5] = {0, 0, 0, 0, 0};
-  for (int c = 0; c < 4; ++c) {
+  int grids[6]; int64_t pstride[6], poff[7] = {};
+  for (int c = 0; c < 6; ++c) {
     const int smem_c = std::max(h->g_class_smem[c], 1024);
     const int per_sm = std::max(1, std::min(16, (227 * 1024) / (smem_c + 1024)));
     grids[c] = std::min(h->g_class_n[c], h->num_sms * per_sm);
     pstride[c] = ((int64_t)h->g_class_np[c] * 8 + 3) / 4 * 4;
     poff[c + 1] = poff[c] + pstride[c] * grids[c];
   }
-  GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(poff[4], 4) * 4));
+  GX_CUDA_CHECK(h->d_pws.reserve((size_t)std::max<int64_t>(poff[6], 4) * 4));
   GX_CUDA_CHECK(cudaMemsetAsync(h->d_counters.p, 0, kNumClasses * 4, h->stream));
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->stream));
   GX_CUDA_CHECK(cudaEventRecord(h->ev_fork, h->stream));
-  int offs[4] = {0, h->g_class_n[0], h->g_class_n[0] + h->g_class_n[1], h->g_class_n[0] + h->g_class_n[1] + h->g_class_n[2]};
-  for (int c = 3; c >= 0; --c) {   // largest graphs first
+  int offs[6];
+  for (int c = 0, acc = 0; c < 6; ++c) { offs[c] = acc; acc += h->g_class_n[c]; }
+  for (int c = 5; c >= 0; --c) {   // largest graphs first
     if (h->g_class_n[c] == 0) continue;
     GxExplainLaunch cfg;
     cfg.order = h->d_order.as<int32_t>() + offs[c]; cfg.ntasks = h->g_class_n[c]; cfg.counter = h->d_counters.as<int32_t>() + c;
