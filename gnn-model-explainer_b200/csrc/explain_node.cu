@@ -705,7 +705,8 @@ outer_pairs_kernel(const GxHparamsDev hp, const GxGraphDev g, const GxPlanArrays
       for (int k = threadIdx.x; k < hp.iters * 4; k += blockDim.x) s_acc[k] = 0.0;
       __syncthreads();
     }
-    for (int p = np_in + threadIdx.x; p < np; p += blockDim.x) {
+    // blockIdx.y slices the pairs of a task (large tasks, few of them: configs[4] has 2.2 M outer pairs per task and 148 tasks)
+    for (int p = np_in + blockIdx.y * blockDim.x + threadIdx.x; p < np; p += gridDim.y * blockDim.x) {
       const int i = plan.pair_i[pair_off + p], j = plan.pair_j[pair_off + p];
       const int64_t oij = edge_off + plan.pair_oij[pair_off + p], oji = edge_off + plan.pair_oji[pair_off + p];
       if (hp.mode) {   // gradient baseline: no gradient reaches an edge outside the receptive field -> sigmoid(0)
@@ -814,12 +815,13 @@ int gx_explain_max_smem() { return 227 * 1024; }
 cudaError_t gx_launch_outer_pairs(const GxHparamsDev& hp, const GxGraphDev& g, const GxPlanArrays& plan, int count,
                                   const float* m0, float* out_mask, const GxExtra& x, cudaStream_t s) {
   const int grid = count < 148 * 8 ? count : 148 * 8;
-  if (x.trace != nullptr) {
+  if (x.trace != nullptr) {   // (the per-task trace sums are accumulated by ONE CTA per task: no slicing)
     const size_t smem = (size_t)(hp.iters > 0 ? hp.iters : 1) * 4 * sizeof(double);
     if (smem > 48 * 1024) return cudaErrorInvalidValue;   // > 1536 epochs with a trace: refused by gx_explain_nodes_ex
     outer_pairs_kernel<true><<<grid, 256, smem, s>>>(hp, g, plan, count, m0, out_mask, x);
   } else {
-    outer_pairs_kernel<false><<<grid, 256, 0, s>>>(hp, g, plan, count, m0, out_mask, x);
+    const int slices = std::max(1, std::min(32, (148 * 8) / grid));   // fill the machine when the batch has few (large) tasks
+    outer_pairs_kernel<false><<<dim3(grid, slices), 256, 0, s>>>(hp, g, plan, count, m0, out_mask, x);
   }
   return cudaGetLastError();
 }
