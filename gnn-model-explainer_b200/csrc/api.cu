@@ -59,8 +59,9 @@ constexpr int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 constexpr int kStreamClass = 5;    // explain_stream.cu: state in a global slab
 constexpr int kClusterClass = 6;   // explain_node.cu with a thread-block cluster per task: the most expensive shared-memory tasks
 constexpr int kOneClass = 4, kTwoClass = 3;
-// A shared-memory task whose cost exceeds the handle's cluster_cost runs on a cluster of cluster_size CTAs (gx_debug_set_cluster;
-// off by default: a 700-node batch is throughput bound, splitting its tasks only adds barrier and DSMEM overhead -- profiles/r02_cluster.md).
+// Cluster class: forced by gx_debug_set_cluster (every task above cluster_cost), otherwise chosen by gx_plan_nodes for the most expensive
+// tasks of a batch that leaves SMs idle.  A full 700-node batch is throughput bound: splitting its tasks only adds barrier and DSMEM
+// overhead (profiles/r02a_bench_cluster_default_on_REJECTED.json), so it gets none.
 constexpr int kNumStreams = kNumClasses;
 
 }  // namespace
@@ -80,7 +81,8 @@ struct gx_handle {
   int64_t cluster_cost = 0;
   int plan_cluster = 1;       // cluster size the current plan was classified with
   bool force_stream = false;  // test knob (gx_debug_force_stream / GNNX_FORCE_STREAM): every task goes to the streaming class
-  cudaEvent_t ev_join[kNumStreams] = {};
+  cudaEvent_t ev_join[kNumStreams] = {}, ev_begin[kNumStreams] = {};
+  bool class_used[kNumStreams] = {};   // launch classes of the last gx_explain_nodes call (gx_last_class_ms)
   int64_t launches = 0;
 
   // graph
@@ -236,7 +238,8 @@ int gx_create(int device, gx_handle** out) {
   if (const char* env = getenv("GNNX_IEEE_EDGE")) h->ieee_edge = atoi(env) != 0;
   for (int i = 0; i < kNumStreams; ++i) {
     GX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
-    GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    GX_CUDA_CHECK(cudaEventCreate(&h->ev_join[i]));
+    GX_CUDA_CHECK(cudaEventCreate(&h->ev_begin[i]));
   }
   GX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   GX_CUDA_CHECK(cudaEventCreate(&h->ev_t0));
@@ -261,6 +264,7 @@ int gx_destroy(gx_handle* h) {
   for (int i = 0; i < kNumStreams; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->ev_begin[i]) cudaEventDestroy(h->ev_begin[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -283,6 +287,18 @@ int gx_sync(gx_handle* h) {
 }
 
 int64_t gx_launch_count(gx_handle* h) { return h ? h->launches : 0; }
+int gx_plan_class_counts(gx_handle* h, int32_t counts[7], int32_t smem_bytes[7], int32_t* cluster_size) {
+  if (!h || !counts || !h->has_plan) { gx_set_error("gx_plan_class_counts: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
+  for (int c = 0; c < kNumClasses; ++c) {
+    counts[c] = (int32_t)h->class_order[c].size();
+    if (smem_bytes) {
+      smem_bytes[c] = 0;
+      for (int32_t t : h->class_order[c]) smem_bytes[c] = std::max(smem_bytes[c], h->tasks[t].smem_bytes);
+    }
+  }
+  if (cluster_size) *cluster_size = h->plan_cluster;
+  return GX_OK;
+}
 
 /* debug only (not in gnnx.h): device buffer receiving the shared-memory slab of the first task of each class */
 int gx_debug_set_dump(gx_handle* h, float* dev_buf) { if (!h) return GX_ERR_INVALID; h->dbg = dev_buf; return GX_OK; }
@@ -323,6 +339,20 @@ int gx_last_explain_ms(gx_handle* h, float* ms) {
   GX_CUDA_CHECK(cudaSetDevice(h->device));
   GX_CUDA_CHECK(cudaEventSynchronize(h->ev_t1));
   GX_CUDA_CHECK(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return GX_OK;
+}
+
+int gx_last_class_ms(gx_handle* h, float begin_ms[7], float end_ms[7]) {
+  if (!h || !begin_ms || !end_ms) { gx_set_error("gx_last_class_ms: NULL argument"); return GX_ERR_INVALID; }
+  if (!h->timed) { gx_set_error("gx_last_class_ms: no gx_explain_nodes call yet"); return GX_ERR_INVALID; }
+  GX_CUDA_CHECK(cudaSetDevice(h->device));
+  GX_CUDA_CHECK(cudaEventSynchronize(h->ev_t1));
+  for (int c = 0; c < kNumClasses; ++c) {
+    begin_ms[c] = end_ms[c] = -1.f;
+    if (!h->class_used[c]) continue;
+    GX_CUDA_CHECK(cudaEventElapsedTime(&begin_ms[c], h->ev_t0, h->ev_begin[c]));
+    GX_CUDA_CHECK(cudaEventElapsedTime(&end_ms[c], h->ev_t0, h->ev_join[c]));
+  }
   return GX_OK;
 }
 
@@ -554,6 +584,53 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     h->class_order[cls].push_back(t);
   }
   h->gws_stride_words = (gws_words + 3) / 4 * 4;
+  if (h->cluster_size == 0 && !h->m.variant && !h->force_stream && h->class_order[kStreamClass].empty()) {
+    // Automatic cluster class: a batch that leaves SMs idle (one explain() call, a shard of a strong-scaled list) is bounded by the
+    // latency of its most expensive tasks, so those run on thread-block clusters of the spare SMs.  A full batch (700 syn1 nodes on one
+    // GPU needs ~200 SM-slots) has no spare SM and stays as it is.  Only tasks of the 512-thread classes qualify: the cluster kernel is
+    // the same 512-thread kernel with the same summation tree (gx_vwarps), so the choice never changes a bit of a task's masks.
+    // Latency model from profiles/r02b_cluster_study_syn1.json: 6 us per 1000 cost units on one CTA; a cluster divides that by its
+    // size and adds 0.55 ms (2 CTAs) / 0.8 ms (4 CTAs) of cluster-barrier time per 100 epochs.
+    double demand = 0;
+    for (int c = 0; c < kStreamClass; ++c) demand += (double)h->class_order[c].size() / kClasses[c].ctas_per_sm;
+    const int spare = h->num_sms - (int)(demand + 0.999);
+    std::vector<int32_t> cand;
+    for (int c : {kTwoClass, kOneClass}) for (int32_t t : h->class_order[c]) cand.push_back(t);
+    std::stable_sort(cand.begin(), cand.end(), [&](int32_t x, int32_t y) { return cost(x) > cost(y); });
+    auto lat = [&](int32_t t) { return 6e-6 * (double)cost(t); };
+    int best_cs = 1, best_k = 0;
+    if (!cand.empty() && spare >= 2) {
+      double best = lat(cand[0]);
+      for (int cs : {2, 4}) {
+        const double ovh = cs == 2 ? 0.55 : 0.8;
+        // the k most expensive tasks on clusters: every one of them must gain, and all of them must fit the class and the spare SMs
+        int k = 0;
+        while (k < (int)cand.size() && (k + 1) * cs <= spare && lat(cand[k]) / cs + ovh < lat(cand[k])) {
+          const GxTask& T = h->tasks[cand[k]];
+          const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, h->m.d, h->m.hid, h->m.emb, h->m.C, kClasses[kClusterClass].threads / 32, 2, cs);
+          if ((int64_t)L.total_words * 4 > kClasses[kClusterClass].cap_bytes) break;
+          ++k;
+        }
+        if (k == 0) continue;
+        const double span = std::max(lat(cand[0]) / cs + ovh, k < (int)cand.size() ? lat(cand[k]) : 0.0);
+        if (span < best * 0.95) { best = span; best_cs = cs; best_k = k; }
+      }
+    }
+    if (best_cs > 1) {
+      h->plan_cluster = best_cs;
+      for (int i = 0; i < best_k; ++i) {
+        const int32_t t = cand[i];
+        GxTask& T = h->tasks[t];
+        const GxLayout L = gx_make_layout(T.n, T.n1, T.n2, T.e1, T.npairs_in, h->m.d, h->m.hid, h->m.emb, h->m.C, kClasses[kClusterClass].threads / 32, 2, best_cs);
+        T.smem_bytes = L.total_words * 4;
+        for (int c : {kTwoClass, kOneClass}) {
+          auto& v = h->class_order[c];
+          v.erase(std::remove(v.begin(), v.end(), t), v.end());
+        }
+        h->class_order[kClusterClass].push_back(t);
+      }
+    }
+  }
   std::vector<int32_t> order_all;
   for (int c = 0; c < kNumClasses; ++c) {
     auto& v = h->class_order[c];
@@ -886,6 +963,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   GX_CUDA_CHECK(cudaEventRecord(h->ev_fork, h->stream));
   int off = 0;
   std::vector<int> used;
+  for (int c = 0; c < kNumClasses; ++c) h->class_used[c] = false;
   // most expensive class first so that its long tasks start at t=0 and the small ones fill around them
   std::vector<int> offs(kNumClasses);
   for (int c = 0; c < kNumClasses; ++c) { offs[c] = off; off += (int)h->class_order[c].size(); }
@@ -910,9 +988,12 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
       // shrink the dynamic smem request to what the class actually needs (more CTAs can co-reside)
       int need = 0;
       for (int32_t t : h->class_order[c]) need = std::max(need, h->tasks[t].smem_bytes);
-      cfg.smem_bytes = c == kOneClass ? kClasses[c].cap_bytes : std::max(need, 1024);
+      // the 1-per-SM class and the cluster class request the whole SM: a CTA of another class next to them would take the room the
+      // scheduler's breadth-first placement needs for the small classes launched last (profiles/r02cl_cluster_auto.md)
+      cfg.smem_bytes = (c == kOneClass || c == kClusterClass) ? kClasses[c].cap_bytes : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
+    GX_CUDA_CHECK(cudaEventRecord(h->ev_begin[c], h->side[c]));
     if (c == kStreamClass && h->m.variant) {
       GX_CUDA_CHECK(gx_launch_explain_var(cfg, h->g, h->m, hd, h->plan, m0_dev, out_dev, feat_dev, h->side[c]));
     } else if (c == kStreamClass && gang > 0) {
@@ -928,6 +1009,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
     h->launches += 1;
     GX_CUDA_CHECK(cudaEventRecord(h->ev_join[c], h->side[c]));
     used.push_back(c);
+    h->class_used[c] = true;
   }
   // pairs between two outermost nodes: independent scalar recurrences, whole batch in one launch
   GX_CUDA_CHECK(gx_launch_outer_pairs(hd, h->g, h->plan, count, m0_dev, out_dev, D.x, h->stream));

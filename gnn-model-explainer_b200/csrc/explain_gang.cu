@@ -26,7 +26,14 @@ namespace {
 #define GXG_UNROLL 4   // steps of six edges a warp keeps in flight in the sparse passes (8 measured no faster: profiles/r02_gang.md)
 #endif
 constexpr int kGangThreads = 512;    // 16 warps, 128 registers per thread (the tensor-core passes hold 24 A fragments + 32 accumulators)
-constexpr int kDenseWarps = 6;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
+#ifndef GXG_DENSE_WARPS
+#define GXG_DENSE_WARPS 6
+#endif
+#ifndef GXG_TILE_BUFS
+#define GXG_TILE_BUFS 2
+#endif
+constexpr int kTileBufs = GXG_TILE_BUFS;   // tile buffers per dense warp (2 = the next tile is in flight while the current one is consumed)
+constexpr int kDenseWarps = GXG_DENSE_WARPS;       // warps of a CTA that run the TMA + tensor-core feature passes (two 8.4 KB tiles each; 8 would not fit 227 KB at d = 128)
 constexpr int kLongEdges = 512;      // rows with more edges are sliced over all warps of one CTA
 constexpr int kBlockTiles = 8;       // dL/dsF is reduced over fixed blocks of 8 tiles (128 nodes): independent of the gang size
 
@@ -54,8 +61,8 @@ __host__ __device__ inline GangSmem gang_smem(int d, int hid, int emb, int C, in
   S.Wp = take(C * (2 * hid + emb + 1) <= GX_WP_SMEM_MAX ? C * (2 * hid + emb + 1) : 0);
   S.part = take(nwarps * hid);             // long rows: per-warp partial aggregates
   S.red = take(kGangThreads > dp ? kGangThreads : dp);   // dL/dsF: slice partials
-  S.xt = take(kDenseWarps * 2 * 16 * S.xs);              // feature tiles (TMA destination), two per dense warp
-  S.pt = take(kDenseWarps * 2 * 16 * hid);               // dP tiles
+  S.xt = take(kDenseWarps * kTileBufs * 16 * S.xs);      // feature tiles (TMA destination), kTileBufs per dense warp
+  S.pt = take(kDenseWarps * kTileBufs * 16 * hid);       // dP tiles
   S.bar = take(kDenseWarps * 2 * 2);                     // one mbarrier (8 bytes) per tile buffer
   S.total = o;
   return S;
@@ -378,9 +385,10 @@ __device__ __forceinline__ void dense_forward(int n, const GangSmem& S, int dwar
   TileIter it{dwarp * G + grank, 0, nb, ntile, kDenseWarps * G};
   TileIter nx = it;
   int buf = 0;
-  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0, nullptr, bar0, pol); nx.next(); }
+  if (kTileBufs == 2 && nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0, nullptr, bar0, pol); nx.next(); }
   while (it.valid()) {
-    if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8, pol); nx.next(); }
+    if (kTileBufs == 1) { tile_issue<HID>(it.tile(), n, xs, false, lane, xlo, nullptr, xt0, nullptr, bar0, pol); }
+    else if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, false, lane, xlo, nullptr, xt0 + (buf ^ 1) * 16 * xs, nullptr, bar0 + (buf ^ 1) * 8, pol); nx.next(); }
     mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u); phase ^= 1u << buf;
     const float* xr = xt0 + buf * 16 * xs;
     // 3xTF32 with two accumulators per n-tile (small terms lo*hi + hi*lo, big term hi*hi) and the MMAs of the n-tiles interleaved:
@@ -420,7 +428,7 @@ __device__ __forceinline__ void dense_forward(int n, const GangSmem& S, int dwar
       }
     }
     __syncwarp();   // every lane is done with this buffer before the next issue overwrites it
-    buf ^= 1;
+    if (kTileBufs == 2) buf ^= 1;
     it.next();
   }
 }
@@ -442,9 +450,10 @@ __device__ __forceinline__ void dense_backward(int n, int dp, const GangSmem& S,
   float ga[NF8][2];
 #pragma unroll
   for (int nt = 0; nt < NF8; ++nt) { ga[nt][0] = 0.f; ga[nt][1] = 0.f; }
-  if (nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, true, lane, xlo, dP, xt0, pt0, bar0, pol); nx.next(); }
+  if (kTileBufs == 2 && nx.valid()) { tile_issue<HID>(nx.tile(), n, xs, true, lane, xlo, dP, xt0, pt0, bar0, pol); nx.next(); }
   while (it.valid()) {
-    if (nx.valid()) {
+    if (kTileBufs == 1) { tile_issue<HID>(it.tile(), n, xs, true, lane, xlo, dP, xt0, pt0, bar0, pol); }
+    else if (nx.valid()) {
       tile_issue<HID>(nx.tile(), n, xs, true, lane, xlo, dP, xt0 + (buf ^ 1) * 16 * xs, pt0 + (buf ^ 1) * 16 * HID, bar0 + (buf ^ 1) * 8, pol);
       nx.next();
     }
@@ -499,7 +508,7 @@ __device__ __forceinline__ void dense_backward(int n, int dp, const GangSmem& S,
     }
     __syncwarp();
     const int b = it.b;
-    buf ^= 1;
+    if (kTileBufs == 2) buf ^= 1;
     it.next();
     if (!it.valid() || it.b != b) {   // end of the block: sum the eight row groups (fixed order) and write the block partial
 #pragma unroll
@@ -567,8 +576,8 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
   const bool wp_smem = C * (PD + 1) <= GX_WP_SMEM_MAX;
   const float* const Wpp = wp_smem ? sm + S.Wp : m.Wp;
   const float* const bpp = wp_smem ? sm + S.Wp + C * PD : m.bp;
-  float* const xt0 = sm + S.xt + (warp < kDenseWarps ? warp : 0) * 2 * 16 * S.xs;
-  float* const pt0 = sm + S.pt + (warp < kDenseWarps ? warp : 0) * 2 * 16 * HID;
+  float* const xt0 = sm + S.xt + (warp < kDenseWarps ? warp : 0) * kTileBufs * 16 * S.xs;
+  float* const pt0 = sm + S.pt + (warp < kDenseWarps ? warp : 0) * kTileBufs * 16 * HID;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(sm + S.bar) + (warp < kDenseWarps ? warp : 0) * 16;
   uint32_t tile_phase = 0;
 
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
     for (int idx = tid; idx < C * PD; idx += NT) Wps[idx] = __ldg(m.Wp + idx);
     for (int idx = tid; idx < C; idx += NT) Wps[C * PD + idx] = __ldg(m.bp + idx);
   }
-  for (int idx = tid; idx < kDenseWarps * 2 * 16 * S.xs; idx += NT) sm[S.xt + idx] = 0.f;   // the pad columns [d, dp8) stay zero
+  for (int idx = tid; idx < kDenseWarps * kTileBufs * 16 * S.xs; idx += NT) sm[S.xt + idx] = 0.f;   // the pad columns [d, dp8) stay zero
   if (tid < kDenseWarps * 2) mbar_init((uint32_t)__cvta_generic_to_shared(sm + S.bar) + tid * 8, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();

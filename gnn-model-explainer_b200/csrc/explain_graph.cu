@@ -501,6 +501,10 @@ cudaError_t gx_launch_explain_graphs(const GxExplainLaunch& cfg, const GxGraphBa
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
     if (e != cudaSuccess) return e;
+    // every launch class asks for the largest shared-memory carveout: CTAs of different classes (= different kernels / footprints) can then
+    // share an SM; with per-kernel carveouts a CTA waits for an SM that is completely idle (profiles/r02cl_cluster_auto.md)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
     return cudaGetLastError();
   };

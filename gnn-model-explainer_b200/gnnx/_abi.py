@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("GNNX_LIB_PATH") or os.path.join(_HERE, "lib", "libgnn
 GX_OK = 0
 GX_HOST, GX_DEVICE = 0, 1
 GX_INIT_M0, GX_INIT_PHILOX, GX_INIT_STATE = 0, 1, 2
-GX_VERSION = 210
+GX_VERSION = 211
 GX_TRACE_COLS = 8
 TR_LOSS_EDGES, TR_PRED, TR_SIZE, TR_ENT, TR_LAP, TR_FEAT, TR_DENSITY, TR_PGT = range(8)
 GX_MODEL_BN = 1
@@ -22,6 +22,7 @@ EXPORTS = [
     "gx_explain_nodes_ex", "gx_explain_graphs_ex", "gx_offedge_regularisers",
     "gx_debug_force_stream", "gx_debug_ieee_edge", "gx_debug_set_dump", "gx_debug_set_gang", "gx_debug_set_cluster", "gx_denoise_topk",
     "gx_model_forward", "gx_comm_unique_id", "gx_comm_init", "gx_comm_destroy", "gx_count_nodes", "gx_allgather_masks", "gx_unshard_masks",
+    "gx_plan_class_counts", "gx_last_class_ms",
 ]
 
 
@@ -105,6 +106,8 @@ def lib():
     L.gx_debug_set_gang.argtypes = [vp, C.c_int]
     L.gx_debug_set_cluster.argtypes = [vp, C.c_int, C.c_int64]
     L.gx_launch_count.argtypes = [vp]
+    L.gx_plan_class_counts.argtypes = [vp, i32p, i32p, i32p]
+    L.gx_last_class_ms.argtypes = [vp, f32p, f32p]
     L.gx_launch_count.restype = C.c_int64
     L.gx_last_explain_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for name in EXPORTS:

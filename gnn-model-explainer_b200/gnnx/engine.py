@@ -370,6 +370,22 @@ class Engine:
         """Test knob: IEEE exp/div/sqrt in the edge phase instead of the hardware approximations."""
         _abi.check(self._lib.gx_debug_ieee_edge(self._h, int(bool(on))))
 
+    def plan_class_counts(self, with_smem=False):
+        """(tasks per launch class [7], cluster size) of the current node plan (gx_plan_class_counts); with_smem: also the largest per-CTA
+        shared-memory footprint of each class."""
+        counts = np.zeros(7, np.int32)
+        smem = np.zeros(7, np.int32)
+        cs = np.zeros(1, np.int32)
+        _abi.check(self._lib.gx_plan_class_counts(self._h, _np_ptr(counts), _np_ptr(smem), _np_ptr(cs)))
+        return (counts, int(cs[0]), smem) if with_smem else (counts, int(cs[0]))
+
+    def last_class_ms(self):
+        """(begin_ms[7], end_ms[7]) of the launch classes of the last explain call, relative to its first event (gx_last_class_ms)."""
+        b = np.zeros(7, np.float32)
+        e = np.zeros(7, np.float32)
+        _abi.check(self._lib.gx_last_class_ms(self._h, _np_ptr(b), _np_ptr(e)))
+        return b, e
+
     def launch_count(self):
         return int(self._lib.gx_launch_count(self._h))
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GX_VERSION 210
+#define GX_VERSION 211
 
 typedef struct gx_handle gx_handle;
 
@@ -257,6 +257,12 @@ int gx_model_forward(gx_handle* h, gx_memspace space, float* pred);
 /* Counters for bench.py: number of kernels this handle has launched so far, and the device time
  * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);
+/* Tasks of the current node plan per launch class: counts[0..4] = shared-memory classes by footprint (13 / 27 / 55 / 112 / 226 KB),
+ * counts[5] = streaming class, counts[6] = cluster class; smem_bytes (may be NULL) = largest per-CTA shared-memory footprint of each class; *cluster_size = CTAs per task of the cluster class (1 = none). */
+int gx_plan_class_counts(gx_handle* h, int32_t counts[7], int32_t smem_bytes[7], int32_t* cluster_size);
+/* Device timeline of the last gx_explain_nodes call: per launch class (indices as above) the time its stream reached the launch and the
+ * time its kernel finished, in ms after the call's first event; -1 for classes without tasks.  Synchronises like gx_last_explain_ms. */
+int gx_last_class_ms(gx_handle* h, float begin_ms[7], float end_ms[7]);
 int gx_last_explain_ms(gx_handle* h, float* ms);
 
 /* ---- test / measurement knobs (used by tests/ and tools/ only; they never change what the product computes by default) ----
@@ -265,10 +271,11 @@ int gx_last_explain_ms(gx_handle* h, float* ms);
  * gx_debug_set_dump:     device buffer (>= 4 MiB) receiving the shared-memory slab of the first task and phase timers;
  * gx_debug_set_gang:     CTAs per task of the streaming kernel explain_gang.cu (0 = automatic: the tasks in flight keep their
  *                        scattered state L2 resident; -1 = the first-generation kernel explain_stream.cu);
- * gx_debug_set_cluster:  thread-block cluster size (1, 2, 4; 0 = automatic) and cost threshold of the shared-memory kernel's
- *                        cluster class (off by default: a latency tool for small batches).  The gang size never changes a bit of the
- *                        result (tests/test_gpu_stream.py); a cluster sums the per-warp dL/dsF partials in another order, so it
- *                        agrees with the single-CTA run to round-off (tests/test_gpu_cluster.py). */
+ * gx_debug_set_cluster:  thread-block cluster class of the shared-memory kernel.  cluster_size 0 = automatic (default): when a batch leaves
+ *                        SMs idle (one explain() call, a shard of a strong-scaled list) its most expensive 512-thread tasks run on
+ *                        clusters of 2 / 4 CTAs; 1 = never; 2 / 4 = every shared-memory task whose cost exceeds min_cost.  Neither
+ *                        the gang size (tests/test_gpu_stream.py) nor the automatic cluster choice (tests/test_gpu_cluster.py)
+ *                        changes a bit of a task's result: both kernels sum in the same fixed tree. */
 int gx_debug_set_gang(gx_handle* h, int ctas_per_task);
 int gx_debug_set_cluster(gx_handle* h, int cluster_size, int64_t min_cost);
 int gx_debug_force_stream(gx_handle* h, int on);

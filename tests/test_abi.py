@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libgnnx.so does not export %s" % s
     assert set(_abi.EXPORTS) == set(syms), "python binding and header disagree"
-    assert _abi.lib().gx_version() == _abi.GX_VERSION == 210
+    assert _abi.lib().gx_version() == _abi.GX_VERSION == 211
 
 
 def test_struct_layout_matches_defaults():

@@ -1,6 +1,7 @@
-"""Thread-block-cluster launch class of the shared-memory kernel (explain_node.cu, CS = 2 / 4 CTAs share one task through DSMEM):
-an opt-in latency tool for small batches (gx_debug_set_cluster; profiles/r02_interim_notes.md).  Same arithmetic per row; only
-the order in which the per-warp dL/dsF partials are summed differs from the single-CTA run, so results agree to round-off."""
+"""Thread-block-cluster launch class of the shared-memory kernel (explain_node.cu, CS = 2 / 4 CTAs share one task through DSMEM).
+Chosen automatically by gx_plan_nodes for the most expensive 512-thread tasks of a batch that leaves SMs idle (bit-identical to the
+single-CTA run: same summation tree, gx_vwarps), or forced for every task by gx_debug_set_cluster (a task of the 256-thread classes then
+changes kernels, so it agrees to round-off)."""
 import numpy as np
 import pytest
 
@@ -57,3 +58,34 @@ def test_cluster_trace_and_philox():
         res[cs] = (out, tr)
     assert util.rel_l2(res[4][0], res[1][0]) < 2e-6
     assert np.allclose(res[4][1], res[1][1], rtol=2e-5, atol=1e-6)
+
+
+def test_automatic_cluster_never_changes_a_bit():
+    """A small batch (here: the 8 hub nodes of syn1 + 16 others) gets clusters for its expensive tasks; the masks are the SAME BITS as
+    with clusters switched off, and as the same nodes' masks inside the full 700-node batch (which gets no cluster at all)."""
+    fx = util.load_fixture("syn1")
+    N = fx.rowptr.shape[0] - 1
+    nodes = np.arange(24, dtype=np.int32)
+    hp = dict(num_epochs=30, init=_abi.GX_INIT_PHILOX, seed=11)
+    eng = util.make_engine(fx)
+    plan = eng.plan_nodes(nodes, 3)
+    counts, cs = eng.plan_class_counts()
+    assert counts[6] > 0 and cs in (2, 4), (counts, cs)          # the automatic policy used the cluster class
+    auto = np.zeros(plan.total_edges, np.float32); fa = np.zeros((plan.count, fx.feat.shape[1]), np.float32)
+    eng.explain_nodes_host(eng.make_hparams(**hp), None, auto, fa)
+    eng.debug_cluster(1, 0)
+    plan1 = eng.plan_nodes(nodes, 3)
+    counts1, cs1 = eng.plan_class_counts()
+    assert counts1[6] == 0 and cs1 == 1
+    off = np.zeros_like(auto); fo = np.zeros_like(fa)
+    eng.explain_nodes_host(eng.make_hparams(**hp), None, off, fo)
+    assert np.array_equal(auto, off) and np.array_equal(fa, fo)
+    eng.debug_cluster(0, 0)
+    full = eng.plan_nodes(np.arange(N, dtype=np.int32), 3)
+    countsf, csf = eng.plan_class_counts()
+    assert countsf[6] == 0, countsf                               # a full batch has no spare SM
+    whole = np.zeros(full.total_edges, np.float32)
+    eng.explain_nodes_host(eng.make_hparams(**hp), None, whole)   # Philox streams are keyed by node id: same M0 as above
+    eng.close()
+    for t in range(len(nodes)):
+        assert np.array_equal(whole[full.edge_off[t]:full.edge_off[t + 1]], auto[plan.edge_off[t]:plan.edge_off[t + 1]]), t
