@@ -483,8 +483,22 @@ def bench_python_dropin(c, g, reps=3):
         res[key] = {"value": len(nodes) / min(ts), "ms_per_call": 1e3 * min(ts)}
         assert len(out) == len(nodes) and out[5].dtype == np.float64
         ex.engine.close()
+    # latency of ONE Explainer.explain(node) call (the reference's unit of use) on the most expensive node, default and latency mode
+    ex = make_explainer(g, c.local_rank, init="device")
+    for key, lat in (("single_explain_call_ms", False), ("single_explain_call_ms_latency_mode", True)):
+        ex.engine.debug_cluster(0 if lat else 1, 0)
+        ex.explain(0)
+        ts = []
+        for _ in range(10):
+            torch.cuda.synchronize(c.dev)
+            t0 = time.perf_counter()
+            ex.explain(0)
+            ts.append(time.perf_counter() - t0)
+        res[key] = {"wall_ms": 1e3 * float(np.median(ts)), "kernel_ms": ex.engine.last_explain_ms()}
+    ex.engine.close()
     res["value"] = res["device_init"]["value"]
-    res["note"] = ("torch_init draws the reference's n^2 normals per node on the host (bit-compatible M0 under torch.manual_seed); save_npy writes the "
+    res["note"] = ("single_explain_call: Explainer.explain(0), node 0 = the most expensive syn1 task; latency mode (args.gnnx_latency / gx_debug_set_cluster(h, 0, 0)) runs it on a 4-CTA cluster. "
+                   "torch_init draws the reference's n^2 normals per node on the host (bit-compatible M0 under torch.manual_seed); save_npy writes the "
                    "reference's 700 .npy files (~0.3 GB); *_views returns views of a pinned buffer reused by the next call")
     return res
 
@@ -513,6 +527,19 @@ def bench_sharded(a, c):
         if key == "weak":
             res[key]["clocks"] = clocks
             res[key]["wall"] = wall
+    # the strong-scaled 700-node list again in latency mode (gx_debug_set_cluster(h, 0, 0)): a shard leaves SMs idle, so its most expensive
+    # tasks run on thread-block clusters; masks agree with the default mode to round-off, not bit for bit, hence opt-in
+    ex.engine.debug_cluster(0, 0)
+    nodes = lists["strong_700"]
+
+    def step_lat():
+        keep["out"] = explain_nodes_sharded(ex, nodes)
+    l0 = ex.engine.launch_count()
+    ms, kern, _w, _c = timed(c, step_lat, a.steps, a.warmup, None, after=ex.engine.last_explain_ms)
+    counts, cs = ex.engine.plan_class_counts()
+    res["strong_700_latency_mode"] = {"nodes": int(len(nodes)), "ms_per_step": ms / a.steps, "value": len(nodes) * a.steps / (ms / 1e3), "kernel_ms_per_step": float(np.mean(kern)),
+                                      "launches_per_step": (ex.engine.launch_count() - l0) // (a.steps + a.warmup), "rank0_cluster_tasks": int(counts[6]), "rank0_cluster_size": cs}
+    ex.engine.debug_cluster(1, 0)
     # e2e: the same sharded call + delivery of ALL gathered masks into pinned host memory on every rank (what explain_nodes returns)
     values, offsets, _ = explain_nodes_sharded(ex, lists["weak"])
     host = torch.empty(int(offsets[-1]), dtype=torch.float32).pin_memory()
@@ -582,8 +609,8 @@ def main_ours(a):
                          "kernel": "explain_node_kernel, per GPU", "kernel_ms_per_step": w["kernel_ms_per_step"], "algorithmic_bytes_per_step": algo,
                          "sm": _sm_metrics("syn1"), "note": "equivalent bandwidth of rank 0's shard, see the N = 1 line"},
             "cpu_baseline": None,
-            "strong": {"list_700": res["strong_700"], "list_5600": res["strong_5600"],
-                       "note": "the SAME list sharded over the N ranks (total work fixed); the 700-node list is bounded by its largest task's critical path"},
+            "strong": {"list_700": res["strong_700"], "list_700_latency_mode": res["strong_700_latency_mode"], "list_5600": res["strong_5600"],
+                       "note": "the SAME list sharded over the N ranks (total work fixed); the 700-node list is bounded by its largest task's critical path, which latency mode (thread-block clusters for the expensive tasks of a shard that leaves SMs idle; round-off instead of bit identity) shortens"},
             "shard_bit_identical": ident,
         }
         print(json.dumps(line), flush=True)

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
 #include <vector>
@@ -59,12 +60,18 @@ constexpr int kNumClasses = sizeof(kClasses) / sizeof(kClasses[0]);
 constexpr int kStreamClass = 5;    // explain_stream.cu: state in a global slab
 constexpr int kClusterClass = 6;   // explain_node.cu with a thread-block cluster per task: the most expensive shared-memory tasks
 constexpr int kOneClass = 4, kTwoClass = 3;
-// Cluster class: forced by gx_debug_set_cluster (every task above cluster_cost), otherwise chosen by gx_plan_nodes for the most expensive
-// tasks of a batch that leaves SMs idle.  A full 700-node batch is throughput bound: splitting its tasks only adds barrier and DSMEM
-// overhead (profiles/r02a_bench_cluster_default_on_REJECTED.json), so it gets none.
+// Cluster class (gx_debug_set_cluster / GNNX_CLUSTER_SIZE): off by default, so that a task's masks never depend on the batch it is in;
+// 0 = latency mode, gx_plan_nodes moves the most expensive tasks of a batch that leaves SMs idle to clusters; 2 / 4 = every task above
+// cluster_cost.  A full 700-node batch is throughput bound: splitting its tasks only adds barrier and DSMEM overhead
+// (profiles/r02a_bench_cluster_default_on_REJECTED.json), so the latency mode gives it none.
 constexpr int kNumStreams = kNumClasses;
 
 }  // namespace
+
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline bool host_timing() { static const bool on = [] { const char* v = getenv("GNNX_HOST_TIMING"); return v && v[0] == '1'; }(); return on; }   // stderr breakdown of the host side (tools/)
+
+struct AdamKey { float lr, b1, b2, decay_rate; int32_t opt, sched, decay_step, restart, iters, start; };
 
 struct gx_handle {
   int device = 0;
@@ -77,7 +84,7 @@ struct gx_handle {
   float* dbg = nullptr;
   bool ieee_edge = false;     // test knob (gx_debug_ieee_edge / GNNX_IEEE_EDGE): IEEE arithmetic in the edge phase
   int gang_override = 0;      // test knob (gx_debug_set_gang / GNNX_GANG): CTAs per task of explain_gang.cu, 0 = automatic, -1 = explain_stream.cu
-  int cluster_size = 0;       // test knob (gx_debug_set_cluster): 0 = automatic
+  int cluster_size = 1;       // gx_debug_set_cluster / GNNX_CLUSTER_SIZE: 1 = never (default: results independent of the batch composition), 0 = automatic, 2 / 4 = forced
   int64_t cluster_cost = 0;
   int plan_cluster = 1;       // cluster size the current plan was classified with
   bool force_stream = false;  // test knob (gx_debug_force_stream / GNNX_FORCE_STREAM): every task goes to the streaming class
@@ -98,6 +105,9 @@ struct gx_handle {
   int count = 0, n_hops = 0;
   int64_t total_n = 0, total_e = 0;
   std::vector<GxTask> tasks;
+  AdamKey adam_key{};
+  bool adam_valid = false;
+  bool tasks_fetched = true;   // false: idx_new of the host copy is stale (filled on the device by khop_fill, fetched by gx_plan_fetch)
   std::vector<int32_t> class_order[kNumClasses];
   int64_t gws_stride_words = 0;
   DevBuf d_nodes, d_tasks, d_nbrs, d_lo2gid, d_srp, d_scol, d_irp, d_icol, d_pairs, d_order, d_counters;
@@ -226,14 +236,15 @@ int gx_create(int device, gx_handle** out) {
     int v[kNumClasses], k = 0;
     const char* p = env;
     while (*p && k < kNumClasses) { v[k++] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
-    for (int c = 0; c < k; ++c) if (v[c] >= 32 && v[c] <= 512 && v[c] % 32 == 0) kClasses[c].threads = v[c];
+    // (a 512-thread class keeps 512 threads or drops to the 256-thread kernel: its summation bins assume 16 warps per CTA)
+    for (int c = 0; c < k; ++c) if (v[c] >= 32 && v[c] % 32 == 0 && (v[c] <= 256 || v[c] == 512)) kClasses[c].threads = v[c];
   }
   gx_handle* h = new gx_handle();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* env = getenv("GNNX_FORCE_STREAM")) h->force_stream = atoi(env) != 0;
   if (const char* env = getenv("GNNX_GANG")) h->gang_override = atoi(env);
-  if (const char* env = getenv("GNNX_CLUSTER_SIZE")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) h->cluster_size = v; }
+  if (const char* env = getenv("GNNX_CLUSTER_SIZE")) { const int v = atoi(env); if (v == 0 || v == 1 || v == 2 || v == 4) h->cluster_size = v; }
   if (const char* env = getenv("GNNX_CLUSTER_COST")) { const long long v = atoll(env); if (v > 0) h->cluster_cost = v; }
   if (const char* env = getenv("GNNX_IEEE_EDGE")) h->ieee_edge = atoi(env) != 0;
   for (int i = 0; i < kNumStreams; ++i) {
@@ -538,6 +549,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   if (h->has_label && (h->label_min < 0 || h->label_max >= h->m.C)) { gx_set_error("gx_plan_nodes: label values span [%d,%d], model has %d classes", h->label_min, h->label_max, h->m.C); return GX_ERR_INVALID; }
   if (h->pred_min < 0 || h->pred_max >= h->m.C) { gx_set_error("gx_plan_nodes: pred_label values span [%d,%d], model has %d classes", h->pred_min, h->pred_max, h->m.C); return GX_ERR_INVALID; }
   GX_CUDA_CHECK(cudaSetDevice(h->device));
+  const double t0 = host_timing() ? now_us() : 0.0;
   h->has_plan = false;
   h->has_gplan = false;
   int rc = ensure_slot_ws(h);
@@ -551,6 +563,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   h->tasks.resize(count);
   GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
   GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  const double t1 = host_timing() ? now_us() : 0.0;
   // host: offsets, launch classes, work order
   int64_t tn = 0, te = 0, tp = 0;
   for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
@@ -585,10 +598,11 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   }
   h->gws_stride_words = (gws_words + 3) / 4 * 4;
   if (h->cluster_size == 0 && !h->m.variant && !h->force_stream && h->class_order[kStreamClass].empty()) {
-    // Automatic cluster class: a batch that leaves SMs idle (one explain() call, a shard of a strong-scaled list) is bounded by the
+    // Latency mode (cluster_size 0): a batch that leaves SMs idle (one explain() call, a shard of a strong-scaled list) is bounded by the
     // latency of its most expensive tasks, so those run on thread-block clusters of the spare SMs.  A full batch (700 syn1 nodes on one
-    // GPU needs ~200 SM-slots) has no spare SM and stays as it is.  Only tasks of the 512-thread classes qualify: the cluster kernel is
-    // the same 512-thread kernel with the same summation tree (gx_vwarps), so the choice never changes a bit of a task's masks.
+    // GPU needs ~180 SM-slots) has no spare SM and stays as it is.  A cluster sums the per-warp dL/dsF partials of its 32 / 64 warps in
+    // another order than one CTA's 16 warps: the masks agree with the single-CTA run to round-off (2e-6 after 10 epochs), not bit for
+    // bit -- which is why this mode is opt-in.
     // Latency model from profiles/r02b_cluster_study_syn1.json: 6 us per 1000 cost units on one CTA; a cluster divides that by its
     // size and adds 0.55 ms (2 CTAs) / 0.8 ms (4 CTAs) of cluster-barrier time per 100 epochs.
     double demand = 0;
@@ -684,12 +698,20 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   int32_t* pb = h->d_pairs.as<int32_t>();
   h->plan.pair_i = pb; h->plan.pair_j = pb + tp; h->plan.pair_pij = pb + 2 * tp;
   h->plan.pair_pji = pb + 3 * tp; h->plan.pair_oij = pb + 4 * tp; h->plan.pair_oji = pb + 5 * tp;
+  const double t2 = host_timing() ? now_us() : 0.0;
   GX_CUDA_CHECK(gx_launch_khop_fill(h->g, count, n_hops, h->ws, h->plan, h->stream));
   h->launches += 1;
-  // idx_new comes back with the canonical description
-  GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
+  // idx_new (the canonical description's position of the node) is copied back by gx_plan_fetch on demand.  The host still waits for the
+  // fill kernel: explainer launches queued BEHIND it all become runnable at the same instant and the block scheduler interleaves the
+  // launch classes arbitrarily, which costs the batch 0.5 ms (kernels 2.9 -> 3.5 ms, profiles/r02cl_cluster_auto.md); issued one by
+  // one onto an idle GPU the most expensive class is placed first.
   GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->tasks_fetched = false;
   h->has_plan = true;
+  if (host_timing()) {
+    const double t3 = now_us();
+    fprintf(stderr, "[gnnx] gx_plan_nodes(%d): count kernel + copy %.0f us, host classes/order %.0f us, fill kernel %.0f us\n", count, t1 - t0, t2 - t1, t3 - t2);
+  }
   if (total_nodes) *total_nodes = tn;
   if (total_edges) *total_edges = te;
   return GX_OK;
@@ -702,7 +724,14 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
   const int count = h->count;
   if (node_off) { for (int t = 0; t < count; ++t) node_off[t] = h->tasks[t].node_off; node_off[count] = h->total_n; }
   if (edge_off) { for (int t = 0; t < count; ++t) edge_off[t] = h->tasks[t].edge_off; edge_off[count] = h->total_e; }
-  if (node_idx_new) for (int t = 0; t < count; ++t) node_idx_new[t] = h->tasks[t].idx_new;
+  if (node_idx_new) {
+    if (!h->tasks_fetched) {
+      GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
+      GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      h->tasks_fetched = true;
+    }
+    for (int t = 0; t < count; ++t) node_idx_new[t] = h->tasks[t].idx_new;
+  }
   if (neighbors) GX_CUDA_CHECK(cudaMemcpyAsync(neighbors, h->d_nbrs.p, (size_t)h->total_n * 4, cudaMemcpyDeviceToHost, h->stream));
   if (sub_rowptr) GX_CUDA_CHECK(cudaMemcpyAsync(sub_rowptr, h->d_srp.p, (size_t)(h->total_n + count) * 4, cudaMemcpyDeviceToHost, h->stream));
   if (sub_col) GX_CUDA_CHECK(cudaMemcpyAsync(sub_col, h->d_scol.p, (size_t)h->total_e * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -814,6 +843,9 @@ int check_optimiser(const char* who, const gx_hparams* hp) {
   return GX_OK;
 }
 int upload_adam_table(gx_handle* h, const gx_hparams* hp, int iters, int start) {
+  // the table on the device is reused while the optimiser settings do not change (one explain call per step in a serving loop)
+  AdamKey key{hp->lr, hp->beta1, hp->beta2, hp->opt_decay_rate, hp->opt, hp->opt_scheduler, hp->opt_decay_step, hp->opt_restart, iters, start};
+  if (h->adam_valid && memcmp(&key, &h->adam_key, sizeof(key)) == 0 && h->d_adam.p) return GX_OK;
   std::vector<float2> tab(std::max(iters, 1));
   for (int k = 1; k <= iters; ++k) {
     const double t = (double)(start + k);
@@ -834,6 +866,7 @@ int upload_adam_table(gx_handle* h, const gx_hparams* hp, int iters, int start) 
   GX_CUDA_CHECK(h->d_adam.reserve(tab.size() * sizeof(float2)));
   // pageable source: the copy is staged before the call returns, the vector may go out of scope
   GX_CUDA_CHECK(cudaMemcpyAsync(h->d_adam.p, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+  h->adam_key = key; h->adam_valid = true;
   return GX_OK;
 }
 
@@ -859,6 +892,7 @@ void fill_hparams(const gx_handle* h, const gx_hparams* hp, int mode, bool trace
 static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_memspace space, const gx_explain_io* io) {
   if (!h || !hp) { gx_set_error("gx_explain_nodes: NULL argument"); return GX_ERR_INVALID; }
   if (!h->has_plan) { gx_set_error("gx_explain_nodes: no plan (call gx_plan_nodes)"); return GX_ERR_INVALID; }
+  const double t_entry = host_timing() ? now_us() : 0.0;
   // mask_act "ReLU": the reference's entropy term takes log(1 - relu(M)) with M ~ N(1, 2/n) -> NaN masks from step 1 (explain.py:755-770;
   // pinned by tests/test_oracle.py): nothing to reproduce.  mask_bias: the bias parameter starts at 0 where ReLU6'(0) = 0, so Adam never
   // moves it and the result equals the default run bit for bit (explain.py:657-660,673-676; same test): accepted, no extra state.
@@ -990,7 +1024,8 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
       for (int32_t t : h->class_order[c]) need = std::max(need, h->tasks[t].smem_bytes);
       // the 1-per-SM class and the cluster class request the whole SM: a CTA of another class next to them would take the room the
       // scheduler's breadth-first placement needs for the small classes launched last (profiles/r02cl_cluster_auto.md)
-      cfg.smem_bytes = (c == kOneClass || c == kClusterClass) ? kClasses[c].cap_bytes : std::max(need, 1024);
+      // (2 KB short of the class limit: kernels with a trace carry 1.2 KB of static shared memory)
+      cfg.smem_bytes = (c == kOneClass || c == kClusterClass) ? std::max(need, kClasses[c].cap_bytes - 2048) : std::max(need, 1024);
     }
     GX_CUDA_CHECK(cudaStreamWaitEvent(h->side[c], h->ev_fork, 0));
     GX_CUDA_CHECK(cudaEventRecord(h->ev_begin[c], h->side[c]));
@@ -1021,6 +1056,7 @@ static int explain_nodes_impl(gx_handle* h, const gx_hparams* hp, int mode, gx_m
   }
   GX_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->stream));
   h->timed = true;
+  if (host_timing()) fprintf(stderr, "[gnnx] gx_explain_nodes: host %.0f us from entry to the last launch\n", now_us() - t_entry);
   return io_finish(h, hp, space, io, count, te, h->m.d, h->m.C, D);
 }
 

@@ -30,7 +30,6 @@
 //   * edge phase: one thread per undirected edge (both directions), sigmoid cached between epochs.
 // Phases per epoch (one __syncthreads each): F1 | F2 | S (row r: layer 3 + readout + softmax +
 // layer-3 backward, one warp) | B2 | B1 | P.
-#include <cstdlib>
 #include "explain_common.cuh"
 
 namespace {
@@ -250,7 +249,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         }
       }
     }
-    for (int idx = tid; idx < gx_vwarps(nwarps, CS) * dp; idx += nthreads) gFp[idx] = 0.f;
+    for (int idx = tid; idx < cnwarps * dp; idx += nthreads) gFp[idx] = 0.f;
     const float m0_std = sqrtf(2.0f / (float)n);  // gain('relu') * sqrt(2/(n+n)) (explain.py:647-651)
     for (int p = tid; p < np; p += nthreads) {
       const int i = A.plan.pair_i[pair_off + p], j = A.plan.pair_j[pair_off + p];
@@ -494,11 +493,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         const IdxT* const llistB = reinterpret_cast<const IdxT*>(base + sL.llistB);
         float* const dZ1s = base + sL.U;  // row i of U is consumed (dL/dsF) right before dZ1[i] (.) sF overwrites it
         float* const gFp = base + sL.gFp; float* const zs = base + sL.zs + warp * 128;
-        const int ntask = nlongB1 + (n2 + epi - 1) / epi;
-        const int vwarps = gx_vwarps(nwarps, CS);   // virtual warps (gnnx_internal.cuh): the summation tree of dL/dsF is the same for every cluster size
-        for (int vw = cwarp; vw < vwarps; vw += cnwarps) {
         float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = vw; t < ntask; t += vwarps) {
+        const int ntask = nlongB1 + (n2 + epi - 1) / epi;
+        for (int t = cwarp; t < ntask; t += cnwarps) {
           float4 dh;
           const int i = row_task_gather<IdxT, false, (NT >= 512 ? 1 : GX_SHORT_DEPTH)>(t, nlongB1, llistB, n2, G, H4, irp, icol, a, dZ2, HS, cnt1, zs, dh);
           const bool act = i >= 0;
@@ -535,10 +532,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
             const float4 o = ld4(zs + (g2 * G.GW + q) * 4);
             tsum.x += o.x; tsum.y += o.y; tsum.z += o.z; tsum.w += o.w;
           }
-          peer.st4(gFp + vw * dp + 4 * q, tsum);
+          peer.st4(gFp + cwarp * dp + 4 * q, tsum);
         }
         __syncwarp();
-        }
       }
       phase_sync<CS>();
       GX_MARK(tB1)
@@ -575,14 +571,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) explain_node_kernel(const Expla
         //  serial update would hold back its 32 pairs)
         const int fthreads = min(nthreads, gx_round_up(d, 32));
         for (int f = tid - (nthreads - fthreads); f >= 0 && f < d && !hp.mode; f += fthreads) {
-          // fixed summation tree over the virtual warps' partials: 8 interleaved chains (loads in flight), combined pairwise
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          const int nv = gx_vwarps(nwarps, CS);
-          for (int w0 = 0; w0 < nv; w0 += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += (w0 + k < nv) ? gFp[(w0 + k) * dp + f] : 0.f;
-          }
-          const float gsum = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+          float gsum = 0.f;
+          for (int w = 0; w < cnwarps; ++w) gsum += gFp[w * dp + f];
           const float s = sF[f];
           const float g = s * (1.f - s) * (gsum + hp.c_feat_size / (float)d);
           float mf = mF[f], vf = vF[f], Fv = Fm[f];
@@ -788,11 +778,8 @@ cudaError_t launch_one_t(const GxExplainLaunch& cfg, const ExplainArgs& args, cu
   if (e != cudaSuccess) return e;
   // every launch class asks for the largest shared-memory carveout: CTAs of different classes (= different kernels / footprints) can then
   // share an SM; with per-kernel carveouts a CTA waits for an SM that is completely idle (profiles/r02cl_cluster_auto.md)
-  static const bool carve = [] { const char* v = getenv("GNNX_CARVEOUT"); return !(v && v[0] == '0'); }();   // GNNX_CARVEOUT=0: A/B knob (tools/)
-  if (carve) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-  }
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   if (CS == 1) {
     kern<<<cfg.grid, cfg.threads, cfg.smem_bytes, s>>>(args);
     return cudaGetLastError();

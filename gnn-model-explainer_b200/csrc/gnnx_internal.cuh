@@ -120,17 +120,6 @@ struct GxLayout {
 // shared memory, their optimiser state in a per-CTA global slab that stays in L2); pairs between two
 // outermost nodes never touch the forward and are optimised by a separate elementwise kernel.
 // idx_bytes = sizeof(IdxT) (2 or 4).  hid/emb must be multiples of 4.
-// dL/dsF is summed over the rows of a task in a fixed tree: row-task t belongs to VIRTUAL warp t % V, the V partials are added in
-// index order.  V = 64 for the 512-thread kernels whatever the cluster size (a physical warp walks 4 / 2 / 1 virtual warps when the
-// task runs on 1 / 2 / 4 CTAs), so a task's masks do not depend on whether the plan gave it a cluster: bit-identical across batches.
-__host__ __device__ inline int gx_vwarps(int nwarps, int cs) {
-  const int w = nwarps * cs;
-#ifdef GX_VWARPS_OFF   // A/B only: one partial per physical warp (a cluster then sums in another order than one CTA)
-  return w;
-#endif
-  return (nwarps >= 16 && w <= 64 && 64 % w == 0) ? 64 : w;
-}
-
 __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1, int np_in, int d,
                                                    int hid, int emb, int C, int nwarps,
                                                    int idx_bytes, int cs = 1) {
@@ -159,7 +148,7 @@ __host__ __device__ inline GxLayout gx_make_layout(int n, int n1, int n2, int e1
   L.F = takef(dp);
   L.mF = takef(dp);
   L.vF = takef(dp);
-  L.gFp = takef(gx_vwarps(nwarps, cs) * dp);   // dL/dsF partials, one per VIRTUAL warp (the same 64 for every cluster size of the 512-thread class)
+  L.gFp = takef(nwarps * cs * dp);   // per-warp dL/dsF partials of every CTA of the cluster (cs = cluster size)
   L.zs = takef(nwarps * 128);
   L.dE = takef(2 * hid);
   L.dZ3 = takef(hid);

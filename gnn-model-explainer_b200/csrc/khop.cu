@@ -14,7 +14,11 @@
 
 namespace {
 
-constexpr int KH_THREADS = 256;
+#ifndef GX_KH_THREADS
+#define GX_KH_THREADS 512
+#endif
+constexpr int KH_THREADS = GX_KH_THREADS;   // threads per extraction CTA (one CTA per explained node): the big neighbourhoods are latency bound on per-row
+                                             // dependent loads, 16 warps hide more of it than 8 (700-node syn1 plan 406 -> 301 us, profiles/r02cl_cluster_auto.md)
 constexpr int GX_RANK_SORT_MAX = 4096;  // O(n^2) rank sort of (level, degree) keys up to this many nodes
 
 struct Slot {

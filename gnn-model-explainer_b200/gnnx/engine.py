@@ -363,7 +363,8 @@ class Engine:
         _abi.check(self._lib.gx_debug_set_gang(self._h, int(ctas_per_task)))
 
     def debug_cluster(self, size=0, min_cost=0):
-        """Test knob: cluster size (1/2/4, 0 automatic) and cost threshold of the shared-memory kernel's cluster class."""
+        """Cluster class of the shared-memory kernel: size 1 = never (default), 0 = latency mode (automatic for batches that leave SMs idle),
+        2 / 4 = every task above min_cost (gx_debug_set_cluster)."""
         _abi.check(self._lib.gx_debug_set_cluster(self._h, int(size), int(min_cost)))
 
     def debug_ieee_edge(self, on=True):

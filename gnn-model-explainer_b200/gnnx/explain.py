@@ -13,6 +13,9 @@ Differences that are deliberate and documented:
     from torch's global CPU generator per node in call order, exactly the RNG consumption of
     ExplainModule.construct_edge_mask (explain.py:645-652) -> bit-identical M0 under the same
     torch.manual_seed; "device" draws N(1, 2/n) with Philox on the GPU (no n^2 host work).
+  * args.gnnx_latency (default False): True lets small batches (one explain() call, a shard of a multi-GPU run) split their most
+    expensive tasks over thread-block clusters (one syn1 hub node 2.85 -> 1.56 ms); masks then agree with the default mode to
+    round-off instead of bit for bit (gx_debug_set_cluster in include/gnnx.h).
   * a node outside its own k-hop set (isolated) raises instead of explaining a wrong row.
 """
 import math
@@ -103,6 +106,8 @@ class Explainer:
         self.engine = Engine(device)
         weights, num_layers = model_weights(model)
         self.engine.set_model(weights, num_layers=num_layers, bn=bn)
+        if getattr(args, "gnnx_latency", False):
+            self.engine.debug_cluster(0, 0)   # latency mode: thread-block clusters for the expensive tasks of batches that leave SMs idle
         # model / optimiser variants run in the variant kernel, which does not log the per-epoch trace print_training replays
         self._no_trace = bn or num_layers != 3 or getattr(args, "opt", "adam") != "adam"
         adj_np = np.asarray(adj)

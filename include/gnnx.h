@@ -271,11 +271,13 @@ int gx_last_explain_ms(gx_handle* h, float* ms);
  * gx_debug_set_dump:     device buffer (>= 4 MiB) receiving the shared-memory slab of the first task and phase timers;
  * gx_debug_set_gang:     CTAs per task of the streaming kernel explain_gang.cu (0 = automatic: the tasks in flight keep their
  *                        scattered state L2 resident; -1 = the first-generation kernel explain_stream.cu);
- * gx_debug_set_cluster:  thread-block cluster class of the shared-memory kernel.  cluster_size 0 = automatic (default): when a batch leaves
- *                        SMs idle (one explain() call, a shard of a strong-scaled list) its most expensive 512-thread tasks run on
- *                        clusters of 2 / 4 CTAs; 1 = never; 2 / 4 = every shared-memory task whose cost exceeds min_cost.  Neither
- *                        the gang size (tests/test_gpu_stream.py) nor the automatic cluster choice (tests/test_gpu_cluster.py)
- *                        changes a bit of a task's result: both kernels sum in the same fixed tree. */
+ * gx_debug_set_cluster:  thread-block cluster class of the shared-memory kernel.  cluster_size 1 = never (default: a task's masks do not
+ *                        depend on the batch it is explained in, bit for bit); 0 = latency mode: when a batch leaves SMs idle (one
+ *                        explain() call, a shard of a strong-scaled list) gx_plan_nodes runs its most expensive tasks on clusters of
+ *                        2 / 4 CTAs (one syn1 hub node 2.85 -> 1.56 ms); 2 / 4 = every shared-memory task whose cost exceeds min_cost.
+ *                        The gang size never changes a bit of the result (tests/test_gpu_stream.py); a cluster sums the per-warp
+ *                        dL/dsF partials in another order, so it agrees with the single-CTA run to round-off
+ *                        (tests/test_gpu_cluster.py).  Environment: GNNX_CLUSTER_SIZE. */
 int gx_debug_set_gang(gx_handle* h, int ctas_per_task);
 int gx_debug_set_cluster(gx_handle* h, int cluster_size, int64_t min_cost);
 int gx_debug_force_stream(gx_handle* h, int on);
