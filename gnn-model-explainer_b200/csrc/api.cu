@@ -564,14 +564,8 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
   GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   const double t1 = host_timing() ? now_us() : 0.0;
-  // host: offsets, launch classes, work order
+  // host, step 1: status checks and the offsets the fill kernel needs
   int64_t tn = 0, te = 0, tp = 0;
-  for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
-  int64_t gws_words = 0;
-  auto cost = [&](int32_t t) { const GxTask& T = h->tasks[t]; return (int64_t)T.e1 * (h->m.d + 2 * h->m.hid) + (int64_t)T.n2 * 600 + (int64_t)T.npairs * 60; };
-  const int g_cluster_size = h->cluster_size > 1 ? h->cluster_size : 1;
-  const int64_t g_cluster_cost = h->cluster_cost;
-  h->plan_cluster = g_cluster_size;
   for (int t = 0; t < count; ++t) {
     GxTask& T = h->tasks[t];
     if (T.status != 0) {
@@ -581,6 +575,42 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     if (T.e_d % 2 != 0) { gx_set_error("gx_plan_nodes: induced sub-adjacency of node %d is not symmetric", T.node); return GX_ERR_INVALID; }
     T.node_off = tn; T.rp_off = tn + t; T.edge_off = te; T.pair_off = tp;
     tn += T.n; te += T.e_d; tp += T.npairs;
+  }
+  h->count = count; h->n_hops = n_hops; h->total_n = tn; h->total_e = te;
+  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), (size_t)count * sizeof(GxTask), cudaMemcpyHostToDevice, h->stream));
+  GX_CUDA_CHECK(h->d_counters.reserve(kNumClasses * 4));
+  GX_CUDA_CHECK(h->d_nbrs.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
+  GX_CUDA_CHECK(h->d_lo2gid.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
+  GX_CUDA_CHECK(h->d_srp.reserve((size_t)(tn + count) * 4));
+  GX_CUDA_CHECK(h->d_irp.reserve((size_t)(tn + count) * 4));
+  GX_CUDA_CHECK(h->d_scol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
+  GX_CUDA_CHECK(h->d_icol.reserve((size_t)std::max<int64_t>(te, 1) * 4 * 3));
+  GX_CUDA_CHECK(h->d_pairs.reserve((size_t)std::max<int64_t>(tp, 1) * 4 * 6));
+  h->plan.tasks = h->d_tasks.as<GxTask>();
+  h->plan.nbrs = h->d_nbrs.as<int32_t>();
+  h->plan.lo2gid = h->d_lo2gid.as<int32_t>();
+  h->plan.sub_rowptr = h->d_srp.as<int32_t>();
+  h->plan.irowptr = h->d_irp.as<int32_t>();
+  h->plan.sub_col = h->d_scol.as<int32_t>();
+  h->plan.icol = h->d_icol.as<int32_t>();
+  h->plan.cs2is = h->plan.icol + te;
+  h->plan.is2cs = h->plan.icol + 2 * te;
+  int32_t* pb = h->d_pairs.as<int32_t>();
+  h->plan.pair_i = pb; h->plan.pair_j = pb + tp; h->plan.pair_pij = pb + 2 * tp;
+  h->plan.pair_pji = pb + 3 * tp; h->plan.pair_oij = pb + 4 * tp; h->plan.pair_oji = pb + 5 * tp;
+  const double t2 = host_timing() ? now_us() : 0.0;
+  GX_CUDA_CHECK(gx_launch_khop_fill(h->g, count, n_hops, h->ws, h->plan, h->stream));
+  h->launches += 1;
+  // host, step 2 (while the fill kernel runs): launch classes and work order.  Nothing here is read by the device: T.smem_bytes and the
+  // class lists stay on the host, only the order array is uploaded.
+  for (int c = 0; c < kNumClasses; ++c) h->class_order[c].clear();
+  int64_t gws_words = 0;
+  auto cost = [&](int32_t t) { const GxTask& T = h->tasks[t]; return (int64_t)T.e1 * (h->m.d + 2 * h->m.hid) + (int64_t)T.n2 * 600 + (int64_t)T.npairs * 60; };
+  const int g_cluster_size = h->cluster_size > 1 ? h->cluster_size : 1;
+  const int64_t g_cluster_cost = h->cluster_cost;
+  h->plan_cluster = g_cluster_size;
+  for (int t = 0; t < count; ++t) {
+    GxTask& T = h->tasks[t];
     int bytes = 0;
     int cls = h->m.variant ? kStreamClass : task_smem_class(T, h->m, h->force_stream, &bytes);
     if (h->m.variant) bytes = 0;
@@ -674,33 +704,8 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
     auto& v = h->class_order[c];
     order_all.insert(order_all.end(), v.begin(), v.end());
   }
-  h->count = count; h->n_hops = n_hops; h->total_n = tn; h->total_e = te;
-  GX_CUDA_CHECK(cudaMemcpyAsync(h->d_tasks.p, h->tasks.data(), (size_t)count * sizeof(GxTask), cudaMemcpyHostToDevice, h->stream));
   GX_CUDA_CHECK(h->d_order.reserve((size_t)count * 4));
   GX_CUDA_CHECK(cudaMemcpyAsync(h->d_order.p, order_all.data(), (size_t)count * 4, cudaMemcpyHostToDevice, h->stream));
-  GX_CUDA_CHECK(h->d_counters.reserve(kNumClasses * 4));
-  GX_CUDA_CHECK(h->d_nbrs.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
-  GX_CUDA_CHECK(h->d_lo2gid.reserve((size_t)std::max<int64_t>(tn, 1) * 4));
-  GX_CUDA_CHECK(h->d_srp.reserve((size_t)(tn + count) * 4));
-  GX_CUDA_CHECK(h->d_irp.reserve((size_t)(tn + count) * 4));
-  GX_CUDA_CHECK(h->d_scol.reserve((size_t)std::max<int64_t>(te, 1) * 4));
-  GX_CUDA_CHECK(h->d_icol.reserve((size_t)std::max<int64_t>(te, 1) * 4 * 3));
-  GX_CUDA_CHECK(h->d_pairs.reserve((size_t)std::max<int64_t>(tp, 1) * 4 * 6));
-  h->plan.tasks = h->d_tasks.as<GxTask>();
-  h->plan.nbrs = h->d_nbrs.as<int32_t>();
-  h->plan.lo2gid = h->d_lo2gid.as<int32_t>();
-  h->plan.sub_rowptr = h->d_srp.as<int32_t>();
-  h->plan.irowptr = h->d_irp.as<int32_t>();
-  h->plan.sub_col = h->d_scol.as<int32_t>();
-  h->plan.icol = h->d_icol.as<int32_t>();
-  h->plan.cs2is = h->plan.icol + te;
-  h->plan.is2cs = h->plan.icol + 2 * te;
-  int32_t* pb = h->d_pairs.as<int32_t>();
-  h->plan.pair_i = pb; h->plan.pair_j = pb + tp; h->plan.pair_pij = pb + 2 * tp;
-  h->plan.pair_pji = pb + 3 * tp; h->plan.pair_oij = pb + 4 * tp; h->plan.pair_oji = pb + 5 * tp;
-  const double t2 = host_timing() ? now_us() : 0.0;
-  GX_CUDA_CHECK(gx_launch_khop_fill(h->g, count, n_hops, h->ws, h->plan, h->stream));
-  h->launches += 1;
   // idx_new (the canonical description's position of the node) is copied back by gx_plan_fetch on demand.  The host still waits for the
   // fill kernel: explainer launches queued BEHIND it all become runnable at the same instant and the block scheduler interleaves the
   // launch classes arbitrarily, which costs the batch 0.5 ms (kernels 2.9 -> 3.5 ms, profiles/r02cl_cluster_auto.md); issued one by
@@ -710,7 +715,7 @@ int gx_plan_nodes(gx_handle* h, const int32_t* nodes, int32_t count, int32_t n_h
   h->has_plan = true;
   if (host_timing()) {
     const double t3 = now_us();
-    fprintf(stderr, "[gnnx] gx_plan_nodes(%d): count kernel + copy %.0f us, host classes/order %.0f us, fill kernel %.0f us\n", count, t1 - t0, t2 - t1, t3 - t2);
+    fprintf(stderr, "[gnnx] gx_plan_nodes(%d): count kernel + copy %.0f us, offsets + uploads %.0f us, fill kernel (host classes / order underneath) %.0f us\n", count, t1 - t0, t2 - t1, t3 - t2);
   }
   if (total_nodes) *total_nodes = tn;
   if (total_edges) *total_edges = te;
@@ -725,9 +730,11 @@ int gx_plan_fetch(gx_handle* h, int64_t* node_off, int64_t* edge_off, int32_t* n
   if (node_off) { for (int t = 0; t < count; ++t) node_off[t] = h->tasks[t].node_off; node_off[count] = h->total_n; }
   if (edge_off) { for (int t = 0; t < count; ++t) edge_off[t] = h->tasks[t].edge_off; edge_off[count] = h->total_e; }
   if (node_idx_new) {
-    if (!h->tasks_fetched) {
-      GX_CUDA_CHECK(cudaMemcpyAsync(h->tasks.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->tasks_fetched) {   // only idx_new comes from the device copy (the host copy carries the launch classes)
+      std::vector<GxTask> dev(count);
+      GX_CUDA_CHECK(cudaMemcpyAsync(dev.data(), h->d_tasks.p, (size_t)count * sizeof(GxTask), cudaMemcpyDeviceToHost, h->stream));
       GX_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      for (int t = 0; t < count; ++t) h->tasks[t].idx_new = dev[t].idx_new;
       h->tasks_fetched = true;
     }
     for (int t = 0; t < count; ++t) node_idx_new[t] = h->tasks[t].idx_new;
