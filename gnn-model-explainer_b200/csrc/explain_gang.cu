@@ -769,17 +769,22 @@ __global__ void __launch_bounds__(kGangThreads, 1) explain_gang_kernel(const Gan
       bar.sync();
       GXG_MARK(2)
       // ---- S: row r (= level-order id 0): layer 3, readout, softmax, -log p[gt], layer-3 backward -- every CTA for itself
+      {
+        // the explained node can be a hub (BASELINE configs[4]: thousands of neighbours): every warp of the CTA gathers a slice of its row,
+        // warp 0 adds the partials in warp order and carries on alone
+        const int r0 = irp[0], r1 = irp[1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < H4) acc = gather_row<int32_t, true, 4>(r0 + warp * epi + G8.grp, r1, epi * nwarps, icol, a, Yh2, HS, q);
+        st4(zw + lane * 4, acc);
+      }
+      __syncthreads();
       if (warp == 0) {
-        {
-          const int r0 = irp[0], r1 = irp[1];
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < H4) acc = gather_row<int32_t, true, 4>(r0 + G8.grp, r1, epi, icol, a, Yh2, HS, q);
-          st4(zw + lane * 4, acc);
-        }
-        __syncwarp();
         float z = 0.f;
         if (lane < HID)
-          for (int g2 = 0; g2 < epi; ++g2) z += zw[(g2 * 8 + (lane >> 2)) * 4 + (lane & 3)];
+          for (int w = 0; w < nwarps; ++w) {
+            const float* const zo = sm + S.zs + w * 128;
+            for (int g2 = 0; g2 < epi; ++g2) z += zo[(g2 * 8 + (lane >> 2)) * 4 + (lane & 3)];
+          }
         __syncwarp();
         if (lane < HID) zw[lane] = z;
         __syncwarp();

@@ -47,6 +47,22 @@ __device__ __forceinline__ bool member(const uint32_t* bm, int v) {
   return (__ldcg(bm + (v >> 5)) >> (v & 31)) & 1u;
 }
 
+// Row loops: the induced rows are short (a handful of neighbours), so a warp walks KH_GPW rows at a time, KH_GL lanes each -- four times
+// as many dependent load chains in flight as one row per warp.  -DGX_KH_GL=32 restores one row per warp (A/B).
+#ifndef GX_KH_GL
+#define GX_KH_GL 8
+#endif
+constexpr int KH_GL = GX_KH_GL;
+constexpr int KH_GPW = 32 / KH_GL;
+__device__ __forceinline__ int group_sum_i(int x) {
+#pragma unroll
+  for (int o = KH_GL / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ uint32_t group_bits(uint32_t ballot, int sub) {
+  return KH_GL == 32 ? ballot : ((ballot >> (sub * KH_GL)) & ((1u << KH_GL) - 1u));
+}
+
 __device__ __forceinline__ int warp_sum_i(int x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -147,22 +163,26 @@ khop_count_kernel(GxGraphDev g, const int32_t* __restrict__ nodes, int count, in
     if (tid <= GX_MAX_LEVELS) s_cnt[tid] = 0;
     if (tid < 3) s_e[tid] = 0;
     __syncthreads();
-    for (int idx = 1 + warp; idx < tail; idx += nwarps) {
-      const int u = sl.q[idx];
+    for (int idx0 = 1 + warp * KH_GPW; idx0 < tail; idx0 += nwarps * KH_GPW) {
+      const int idx = idx0 + lane / KH_GL;
+      const bool valid = idx < tail;
+      const int u = valid ? sl.q[idx] : root;
       const int du = (u == root) ? 0 : (int)sl.dist[u];
       int cnt = 0, cnt_out = 0;
-      const int e1 = g.rowptr[u + 1];
-      for (int e = g.rowptr[u] + lane; e < e1; e += 32) {
-        const int v = g.col[e];
-        if (v != u && member(sl.bm, v)) {
-          ++cnt;
-          const int dv = (v == root) ? 0 : (int)sl.dist[v];
-          cnt_out += dv > row_lvl ? 1 : 0;
+      if (valid) {
+        const int e1 = g.rowptr[u + 1];
+        for (int e = g.rowptr[u] + lane % KH_GL; e < e1; e += KH_GL) {
+          const int v = g.col[e];
+          if (v != u && member(sl.bm, v)) {
+            ++cnt;
+            const int dv = (v == root) ? 0 : (int)sl.dist[v];
+            cnt_out += dv > row_lvl ? 1 : 0;
+          }
         }
       }
-      cnt = warp_sum_i(cnt);
-      cnt_out = warp_sum_i(cnt_out);
-      if (lane == 0) {
+      cnt = group_sum_i(cnt);
+      cnt_out = group_sum_i(cnt_out);
+      if (valid && lane % KH_GL == 0) {
         atomicAdd(&s_cnt[du], 1);
         atomicAdd(&s_e[0], cnt);
         if (du <= row_lvl) { atomicAdd(&s_e[1], cnt); atomicAdd(&s_e[2], cnt_out); }
@@ -213,7 +233,8 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
   __shared__ int s_w[33];
   __shared__ int s_cum[GX_MAX_LEVELS + 2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int sub = lane / KH_GL, gl = lane % KH_GL;   // row group of this lane inside its warp, lane inside the group
+  const uint32_t lt_mask = (1u << gl) - 1u;
   const Slot sl = slot_of(ws, blockIdx.x, g.N);
   const int W = ws.W;
   for (int t = blockIdx.x; t < count; t += gridDim.x) {
@@ -251,16 +272,19 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
     };
     if (tid == 0) T->idx_new = canon(root);  // == sum(row[:node_idx]) (explain.py:496)
     // (3) induced degrees of the canonical rows
-    for (int c = warp; c < n; c += nwarps) {
-      const int u = nbrs[c];
+    for (int c0 = warp * KH_GPW; c0 < n; c0 += nwarps * KH_GPW) {
+      const int c = c0 + sub;
       int cnt = 0;
-      const int e1 = g.rowptr[u + 1];
-      for (int e = g.rowptr[u] + lane; e < e1; e += 32) {
-        const int v = g.col[e];
-        cnt += (v != u && member(sl.bm, v)) ? 1 : 0;
+      if (c < n) {
+        const int u = nbrs[c];
+        const int e1 = g.rowptr[u + 1];
+        for (int e = g.rowptr[u] + gl; e < e1; e += KH_GL) {
+          const int v = g.col[e];
+          cnt += (v != u && member(sl.bm, v)) ? 1 : 0;
+        }
       }
-      cnt = warp_sum_i(cnt);
-      if (lane == 0) srp[c] = cnt;
+      cnt = group_sum_i(cnt);
+      if (gl == 0 && c < n) srp[c] = cnt;
     }
     __syncthreads();
     // (4) level order: (distance from the node asc, induced degree desc, id asc).  Every layer's row
@@ -322,19 +346,21 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
     block_excl_scan(irp, n, s_w);
     if (tid == 0) irp[n] = e_tot;
     // (5) canonical columns: member neighbours in ascending id order (row-major nonzero order)
-    for (int c = warp; c < n; c += nwarps) {
-      const int u = nbrs[c];
-      int out = srp[c];
-      const int e0 = g.rowptr[u], e1 = g.rowptr[u + 1];
-      for (int eb = e0; eb < e1; eb += 32) {
-        const int e = eb + lane;
+    for (int c0 = warp * KH_GPW; c0 < n; c0 += nwarps * KH_GPW) {
+      const int c = c0 + sub;
+      const bool valid = c < n;
+      const int u = valid ? nbrs[c] : 0;
+      int out = valid ? srp[c] : 0;
+      const int e0 = valid ? g.rowptr[u] : 0, e1 = valid ? g.rowptr[u + 1] : 0;
+      for (int eb = e0; __any_sync(0xffffffffu, eb < e1); eb += KH_GL) {
+        const int e = eb + gl;
         int v = -1;
         bool keep = false;
         if (e < e1) {
           v = g.col[e];
           keep = (v != u) && member(sl.bm, v);
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        const uint32_t bal = group_bits(__ballot_sync(0xffffffffu, keep), sub);
         if (keep) scol[out + __popc(bal & lt_mask)] = canon(v);
         out += __popc(bal);
       }
@@ -345,19 +371,21 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
     //     canonical <-> internal are kept for the pair construction
     int32_t* cs2is = P.cs2is + T->edge_off;
     int32_t* is2cs = P.is2cs + T->edge_off;
-    for (int i = warp; i < n; i += nwarps) {
-      const int c = sl.cof[i];
-      const int r0 = srp[c], r1 = srp[c + 1];
-      int out = irp[i];
+    for (int i0 = warp * KH_GPW; i0 < n; i0 += nwarps * KH_GPW) {
+      const int i = i0 + sub;
+      const bool valid = i < n;
+      const int c = valid ? sl.cof[i] : 0;
+      const int r0 = valid ? srp[c] : 0, r1 = valid ? srp[c + 1] : 0;
+      int out = valid ? irp[i] : 0;
       for (int lv = 0; lv <= k; ++lv) {
         const int lo_b = s_cum[lv], lo_e = s_cum[lv + 1];
         if (lo_b == lo_e) continue;
-        for (int eb = r0; eb < r1; eb += 32) {
-          const int e = eb + lane;
+        for (int eb = r0; __any_sync(0xffffffffu, eb < r1); eb += KH_GL) {
+          const int e = eb + gl;
           int lo = -1;
           if (e < r1) lo = sl.loc[scol[e]];
           const bool keep = lo >= lo_b && lo < lo_e;
-          const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+          const uint32_t bal = group_bits(__ballot_sync(0xffffffffu, keep), sub);
           if (keep) {
             const int o = out + __popc(bal & lt_mask);
             icol[o] = lo;
@@ -372,24 +400,28 @@ khop_fill_kernel(GxGraphDev g, int count, int k, GxSlotWs ws, GxPlanArrays P) {
     // (7) undirected pairs, owned by the endpoint with the smaller level-order id, in (i, slot) order:
     //     pairs touching the explained node / its neighbours come first, pairs between two
     //     outermost nodes last (uniform work per warp in the explainer's edge phase)
-    for (int i = warp; i < n; i += nwarps) {
+    for (int i0 = warp * KH_GPW; i0 < n; i0 += nwarps * KH_GPW) {
+      const int i = i0 + sub;
       int cnt = 0;
-      for (int kk = irp[i] + lane; kk < irp[i + 1]; kk += 32) cnt += icol[kk] > i ? 1 : 0;
-      cnt = warp_sum_i(cnt);
-      if (lane == 0) sl.pbase[i] = cnt;
+      if (i < n)
+        for (int kk = irp[i] + gl; kk < irp[i + 1]; kk += KH_GL) cnt += icol[kk] > i ? 1 : 0;
+      cnt = group_sum_i(cnt);
+      if (gl == 0 && i < n) sl.pbase[i] = cnt;
     }
     __syncthreads();
     block_excl_scan(sl.pbase, n, s_w);
-    for (int i = warp; i < n; i += nwarps) {
-      const int r0 = irp[i], r1 = irp[i + 1];
-      const int ci = sl.cof[i];
-      int64_t out = T->pair_off + sl.pbase[i];
-      for (int kb = r0; kb < r1; kb += 32) {
-        const int kk = kb + lane;
+    for (int i0 = warp * KH_GPW; i0 < n; i0 += nwarps * KH_GPW) {
+      const int i = i0 + sub;
+      const bool valid = i < n;
+      const int r0 = valid ? irp[i] : 0, r1 = valid ? irp[i + 1] : 0;
+      const int ci = valid ? sl.cof[i] : 0;
+      int64_t out = T->pair_off + (valid ? sl.pbase[i] : 0);
+      for (int kb = r0; __any_sync(0xffffffffu, kb < r1); kb += KH_GL) {
+        const int kk = kb + gl;
         int j = -1;
         if (kk < r1) j = icol[kk];
-        const bool keep = j > i;
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        const bool keep = valid && j > i;
+        const uint32_t bal = group_bits(__ballot_sync(0xffffffffu, keep), sub);
         if (keep) {
           const int64_t p = out + __popc(bal & lt_mask);
           const int cj = sl.cof[j];
