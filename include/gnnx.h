@@ -257,11 +257,14 @@ int gx_model_forward(gx_handle* h, gx_memspace space, float* pred);
 /* Counters for bench.py: number of kernels this handle has launched so far, and the device time
  * (CUDA events on the handle's streams) of the explainer kernels of the last gx_explain_nodes call. */
 int64_t gx_launch_count(gx_handle* h);
-/* Tasks of the current node plan per launch class: counts[0..4] = shared-memory classes by footprint (13 / 27 / 55 / 112 / 226 KB),
- * counts[5] = streaming class, counts[6] = cluster class; smem_bytes (may be NULL) = largest per-CTA shared-memory footprint of each class; *cluster_size = CTAs per task of the cluster class (1 = none). */
+/* Measurement only (no counterpart in the reference, which explains one node at a time and has no scheduler).
+ * gx_plan_class_counts: tasks of the current node plan per launch class -- counts[0..4] = shared-memory classes by footprint
+ * (13 / 27 / 55 / 112 / 226 KB), counts[5] = streaming class, counts[6] = cluster class; smem_bytes (may be NULL) = largest per-CTA
+ * shared-memory footprint of each class; *cluster_size = CTAs per task of the cluster class (1 = none). */
 int gx_plan_class_counts(gx_handle* h, int32_t counts[7], int32_t smem_bytes[7], int32_t* cluster_size);
-/* Device timeline of the last gx_explain_nodes call: per launch class (indices as above) the time its stream reached the launch and the
- * time its kernel finished, in ms after the call's first event; -1 for classes without tasks.  Synchronises like gx_last_explain_ms. */
+/* gx_last_class_ms: device timeline of the last gx_explain_nodes call -- per launch class (indices as above) the time its stream reached
+ * the launch and the time its kernel finished, in ms after the call's first event; -1 for classes without tasks.  Synchronises like
+ * gx_last_explain_ms.  (tools/cluster_study.py; this timeline found the carveout serialisation, profiles/r02cl_cluster_auto.md.) */
 int gx_last_class_ms(gx_handle* h, float begin_ms[7], float end_ms[7]);
 int gx_last_explain_ms(gx_handle* h, float* ms);
 
