@@ -236,7 +236,7 @@ int gx_create(int device, gx_handle** out) {
     int v[kNumClasses], k = 0;
     const char* p = env;
     while (*p && k < kNumClasses) { v[k++] = atoi(p); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
-    // (a 512-thread class keeps 512 threads or drops to the 256-thread kernel: its summation bins assume 16 warps per CTA)
+    // (a class runs the 256-thread kernel with up to 256 threads or the 512-thread kernel with exactly 512)
     for (int c = 0; c < k; ++c) if (v[c] >= 32 && v[c] % 32 == 0 && (v[c] <= 256 || v[c] == 512)) kClasses[c].threads = v[c];
   }
   gx_handle* h = new gx_handle();
